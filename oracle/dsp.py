@@ -188,7 +188,8 @@ def to_local_average_cents(salience: np.ndarray, cents: np.ndarray, threshold: f
     """rmvpe.rs:118-133, LITERAL: `starts` is the argmax in the padded
     row (= c+4) but indexes the UNPADDED salience, so taps come from bins c+4..c+12 and are
     paired with the cents of bins c..c+8.  The reference panics for c >= 348; here taps past
-    bin 359 are treated as absent (documented divergence from a crash).
+    bin 359 are treated as absent and a frame with no tap left (c >= 356) is unvoiced
+    (documented divergence from a crash).
 
     Returns (cents[T] f32, argmax c[T] int) - c is the index in the unpadded row.
     """
@@ -213,8 +214,9 @@ def to_local_average_cents(salience: np.ndarray, cents: np.ndarray, threshold: f
                 c = cents[s + y]
             ps = F32(ps + F32(w * c))
             ws = F32(ws + w)
-        with np.errstate(invalid="ignore", divide="ignore"):
-            d = F32(ps / ws)
+        # c >= 356: every tap is past bin 359 (reference: OOB panic) -> no estimate -> 0 cents,
+        # which decode() maps to f0 == 10.0 -> 0 (unvoiced)
+        d = F32(ps / ws) if ws != 0 else F32(0.0)
         mx = salience[t].max()
         out[t] = d if mx > F32(threshold) else F32(0.0)
     return out, (starts - 4).astype(np.int64)
