@@ -1,0 +1,100 @@
+// model.h - RVCW container reader, weight packing and plan construction (host-only C++).
+//
+// Replaces the reference's ORT session builders (rvc/src/models.rs:7-76): instead of handing an
+// opaque .onnx graph to ONNX Runtime, the tensors are read from an `.rvcw` container, re-laid
+// out once for the implicit-GEMM kernels (channels-last, tap-major K, BN / weight-norm / constant
+// conditioning folded) and kept resident in HBM.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ops.h"
+
+namespace rvc {
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    int32_t dtype = 0;  // 0 f32, 1 i32
+    const void* data = nullptr;
+    int64_t numel() const { int64_t n = 1; for (auto d : shape) n *= d; return n; }
+    const float* f() const { return static_cast<const float*>(data); }
+    const int32_t* i() const { return static_cast<const int32_t*>(data); }
+};
+
+struct RvcwFile {
+    std::vector<uint8_t> blob;
+    std::map<std::string, HostTensor> t;
+    bool load(const std::string& path, std::string& err);
+    const HostTensor* find(const std::string& name) const;
+};
+
+// One weight arena in host staging memory; uploaded verbatim to the device.
+struct Packed {
+    std::vector<float> host;
+    std::map<std::string, int64_t> off;  // element offsets
+    int64_t add(const std::string& name, int64_t elems);  // 256-byte aligned, zero-filled
+    int64_t at(const std::string& name) const;
+    float* p(int64_t o) { return host.data() + o; }
+};
+
+struct CvInfo { int32_t n_layers = 12, out_dim = 768; bool final_proj = false; };
+struct F0Info { float in_scale = 1.f, in_shift = 0.f; int32_t mel_nnz = 0; };
+struct SynInfo { int32_t sr = 40000, phone_dim = 768; float lin_w = 1.f, lin_b = 0.f; };
+
+bool pack_contentvec(const RvcwFile& f, Packed& out, CvInfo& info, std::string& err);
+bool pack_rmvpe(const RvcwFile& f, Packed& out, F0Info& info, std::string& err);
+bool pack_synth(const RvcwFile& f, Packed& out, SynInfo& info, std::string& err);
+
+// Geometry of one call (obs-rvc/src/lib.rs:200-227).
+struct Geometry {
+    int32_t n16k = 0, sf16k = 0, skip_head = 0, return_length = 0;
+    bool operator<(const Geometry& o) const {
+        if (n16k != o.n16k) return n16k < o.n16k;
+        if (sf16k != o.sf16k) return sf16k < o.sf16k;
+        if (skip_head != o.skip_head) return skip_head < o.skip_head;
+        return return_length < o.return_length;
+    }
+};
+
+struct PlanOptions {
+    int32_t index_k = 8;
+    int32_t upstream_cents_window = 0;
+    bool with_index = false; int32_t index_rows = 0;
+    bool multi_lane = true;  // independent branches on separate stream lanes
+};
+
+struct Plan {
+    std::vector<Op> ops;
+    std::vector<NamedBuf> bufs;
+    int64_t work_bytes = 0;
+    int32_t n_lanes = 1;
+    // well-known buffers
+    Ref pcm, audio, params, cache;
+    int32_t hubert_T = 0, hubert_C = 0, f0_T = 0, audio_len = 0, knn_q = 0;
+    const NamedBuf* find(const std::string& name) const;
+};
+
+enum PlanKind : int32_t { PLAN_INFER = 0, PLAN_HUBERT = 1, PLAN_PITCH = 2, PLAN_MEL = 3,
+                          PLAN_KNN = 4, PLAN_FEATURE = 5 };
+
+// Builds the op list.  `cv`/`f0`/`syn` may be null when the plan kind does not need them.
+// Persistent buffers (params, pitch cache, pcm in, audio out, knn queries) live in SP_STATE at
+// the fixed offsets of `StateLayout`, identical for every plan of a context.
+bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const Packed* cv,
+                const CvInfo* cvi, const Packed* f0, const F0Info* f0i, const Packed* syn,
+                const SynInfo* syi, Plan& plan, std::string& err);
+
+struct StateLayout {
+    static const int64_t PCM_CAP = 1 << 20;     // samples (65 s @16 kHz)
+    static const int64_t AUDIO_CAP = 1 << 22;   // floats: audio out / generic result staging
+    static const int64_t CACHE_LEN = 1024;      // rvc.rs:42
+    static const int64_t off_params = 0;                                   // RunParams (64 B)
+    static const int64_t off_cache = 256;                                  // f32[1024]
+    static const int64_t off_pcm = off_cache + CACHE_LEN * 4;              // f32[PCM_CAP]
+    static const int64_t off_audio = off_pcm + PCM_CAP * 4;                // f32[AUDIO_CAP]
+    static const int64_t bytes = off_audio + AUDIO_CAP * 4;
+};
+
+}  // namespace rvc

@@ -1,0 +1,597 @@
+// plan.cpp - builds the per-window op list (host-only).  See ops.h / model.h.
+//
+// Layout rules used throughout (DESIGN.md "Data layout in HBM"):
+//   * activations are fp32 channels-last; 1-D sequences are [rows, C], 2-D maps are
+//     [T+2, F+2, C] with a one-pixel zero halo (+ a small zero guard after the last row);
+//   * halo rows/pixels are zeroed once when the work arena is created and every op preserves
+//     them (masked epilogues), so "same" padding costs nothing at run time;
+//   * every convolution is the implicit GEMM of ops.h over overlapping / segmented rows.
+#include <cmath>
+#include <cstdio>
+
+#include "model.h"
+
+namespace rvc {
+
+namespace {
+
+struct PB {
+    Plan& plan;
+    std::string& err;
+    bool ok = true;
+    int64_t work = 0;
+    int lane = 0;
+
+    void fail(const std::string& m) { if (ok) err = m; ok = false; }
+
+    Ref alloc(const std::string& name, int64_t elems, bool is_int = false) {
+        work = (work + 255) & ~int64_t(255);
+        Ref r{SP_WORK, work};
+        work += elems * 4;
+        if (!name.empty()) plan.bufs.push_back(NamedBuf{name, r, elems, is_int ? 1 : 0});
+        return r;
+    }
+    void alias(const std::string& name, Ref r, int64_t elems, bool is_int = false) {
+        plan.bufs.push_back(NamedBuf{name, r, elems, is_int ? 1 : 0});
+    }
+    // halo-padded NHWC map: interior T x F, C channels; 4 guard pixels at the end
+    Ref pad2d(const std::string& name, int T, int F, int C) {
+        return alloc(name, (int64_t(T + 2) * (F + 2) + 4) * C);
+    }
+    Ref w(const Packed* p, Space sp, const std::string& name) {
+        int64_t o = p ? p->at(name) : -1;
+        if (o < 0) { fail("packed tensor missing: " + name); return Ref{}; }
+        return Ref{sp, o * 4};
+    }
+    Op& add(OpKind k, const std::string& name) {
+        plan.ops.emplace_back();
+        Op& op = plan.ops.back();
+        op.kind = k; op.lane = lane; op.name = name;
+        return op;
+    }
+    void wait(int src, int dst) {
+        if (src == dst) return;
+        Op& op = add(OP_WAIT, "wait");
+        op.wait.src_lane = src; op.wait.dst_lane = dst;
+        if (src + 1 > plan.n_lanes) plan.n_lanes = src + 1;
+        if (dst + 1 > plan.n_lanes) plan.n_lanes = dst + 1;
+    }
+    GemmOp& gemm(const std::string& name, Ref A, int64_t lda, int seg_len, int64_t seg_stride, Ref W,
+                 int64_t ldw, Ref bias, Ref C, int64_t ldc, int M, int N, int K, int act) {
+        Op& op = add(OP_GEMM, name);
+        GemmOp& g = op.gemm;
+        g.A = A; g.lda = lda; g.seg_len = seg_len; g.seg_stride = seg_stride;
+        g.W = W; g.ldw = ldw; g.bias = bias; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.act = act;
+        return g;
+    }
+    void layernorm(const std::string& name, Ref X, int64_t ldx, Ref Y, int64_t ldy, Ref g, Ref b, int rows,
+                   int cols) {
+        Op& op = add(OP_LAYERNORM, name);
+        op.ln.X = X; op.ln.ldx = ldx; op.ln.Y = Y; op.ln.ldy = ldy; op.ln.gamma = g; op.ln.beta = b;
+        op.ln.rows = rows; op.ln.cols = cols; op.ln.eps = 1e-5f;
+    }
+};
+
+std::string S(int i) { return std::to_string(i); }
+
+// ------------------------------------------------------------------------------------------
+// ContentVec (rvc.rs:81-97 `hubert`): pcm[N] -> [T, C]
+// ------------------------------------------------------------------------------------------
+Ref build_contentvec(PB& b, const Packed* P, const CvInfo& info, Ref pcm, int N, int& T_out) {
+    static const int K[7] = {10, 3, 3, 3, 3, 2, 2};
+    auto W = [&](const std::string& n) { return b.w(P, SP_CV, n); };
+    if (N < 400) { b.fail("input shorter than one HuBERT frame"); return Ref{}; }
+    int T0 = (N - 10) / 5 + 1;
+    Ref stats = b.alloc("cv.gn_stats", 1024);
+    {
+        Op& op = b.add(OP_CONV0_STATS, "cv.conv0_stats");
+        op.c0s.pcm = pcm; op.c0s.w = W("conv0.w"); op.c0s.stats = stats; op.c0s.T = T0; op.c0s.C = 512;
+        op.c0s.k = 10; op.c0s.stride = 5; op.c0s.eps = 1e-5f;
+    }
+    Ref prev = b.alloc("cv.conv0", int64_t(T0) * 512);
+    {
+        Op& op = b.add(OP_CONV0_APPLY, "cv.conv0");
+        op.c0a.pcm = pcm; op.c0a.w = W("conv0.w"); op.c0a.stats = stats; op.c0a.gamma = W("gn.g");
+        op.c0a.beta = W("gn.b"); op.c0a.Y = prev; op.c0a.T = T0; op.c0a.C = 512; op.c0a.k = 10; op.c0a.stride = 5;
+    }
+    int Tp = T0;
+    for (int i = 1; i < 7; ++i) {
+        int Ti = (Tp - K[i]) / 2 + 1;
+        Ref y = b.alloc("cv.conv" + S(i), int64_t(Ti) * 512);
+        // stride-2 conv over channels-last rows: row t of the im2col matrix is the contiguous
+        // span x[2t .. 2t+k) -> plain GEMM with overlapping rows (lda = 2*512)
+        b.gemm("cv.conv" + S(i), prev, 2 * 512, K[i] * 512, 0, W("conv" + S(i) + ".w"), K[i] * 512, Ref{}, y,
+               512, Ti, 512, K[i] * 512, ACT_GELU);
+        prev = y; Tp = Ti;
+    }
+    const int T = Tp;
+    T_out = T;
+    Ref ln0 = b.alloc("cv.ln0", int64_t(T) * 512);
+    b.layernorm("cv.ln0", prev, 512, ln0, 512, W("ln.g"), W("ln.b"), T, 512);
+    Ref xpad = b.alloc("", int64_t(T + 128) * 768);  // 64 zero rows either side (pos_conv pad)
+    Ref x = xpad.plus(64 * 768);
+    b.alias("cv.proj", x, int64_t(T) * 768);
+    b.gemm("cv.proj", ln0, 512, 512, 0, W("proj.w"), 512, W("proj.b"), x, 768, T, 768, 512, ACT_NONE);
+    Ref pc = b.alloc("cv.posconv", int64_t(T) * 768);
+    {   // grouped Conv1d(768,768,k=128,pad=64,groups=16), last output dropped, GELU, + x
+        GemmOp& g = b.gemm("cv.posconv", xpad, 768, 48, 768, W("pos.w"), 128 * 48, W("pos.b"), pc, 768, T, 48,
+                           128 * 48, ACT_GELU);
+        g.R = x; g.ldr = 768; g.batch = 16; g.sA = 48; g.sW = int64_t(48) * 128 * 48; g.sBias = 48; g.sC = 48;
+        g.sR = 48;
+    }
+    Ref cur = b.alloc("cv.enc_in", int64_t(T) * 768);
+    b.layernorm("cv.enc_in", pc, 768, cur, 768, W("eln.g"), W("eln.b"), T, 768);
+    for (int i = 0; i < info.n_layers; ++i) {
+        std::string d = "L" + S(i) + ".", n = "cv.L" + S(i) + ".";
+        Ref qkv = b.alloc(n + "qkv", int64_t(T) * 2304);
+        b.gemm(n + "qkv", cur, 768, 768, 0, W(d + "qkv.w"), 768, W(d + "qkv.b"), qkv, 2304, T, 2304, 768, ACT_NONE);
+        Ref a = b.alloc(n + "attn", int64_t(T) * 768);
+        {
+            Op& op = b.add(OP_ATTN, n + "attn");
+            op.attn.qkv = qkv; op.attn.ldqkv = 2304; op.attn.out = a; op.attn.ldo = 768; op.attn.T = T;
+            op.attn.heads = 12; op.attn.dim = 64;
+        }
+        Ref t1 = b.alloc(n + "o", int64_t(T) * 768);
+        { GemmOp& g = b.gemm(n + "o", a, 768, 768, 0, W(d + "o.w"), 768, W(d + "o.b"), t1, 768, T, 768, 768, ACT_NONE);
+          g.R = cur; g.ldr = 768; }
+        Ref x1 = b.alloc(n + "ln1", int64_t(T) * 768);
+        b.layernorm(n + "ln1", t1, 768, x1, 768, W(d + "ln1.g"), W(d + "ln1.b"), T, 768);
+        Ref h = b.alloc(n + "fc1", int64_t(T) * 3072);
+        b.gemm(n + "fc1", x1, 768, 768, 0, W(d + "fc1.w"), 768, W(d + "fc1.b"), h, 3072, T, 3072, 768, ACT_GELU);
+        Ref t2 = b.alloc(n + "fc2", int64_t(T) * 768);
+        { GemmOp& g = b.gemm(n + "fc2", h, 3072, 3072, 0, W(d + "fc2.w"), 3072, W(d + "fc2.b"), t2, 768, T, 768, 3072, ACT_NONE);
+          g.R = x1; g.ldr = 768; }
+        Ref x2 = b.alloc("cv.layer" + S(i), int64_t(T) * 768);
+        b.layernorm("cv.layer" + S(i), t2, 768, x2, 768, W(d + "ln2.g"), W(d + "ln2.b"), T, 768);
+        cur = x2;
+    }
+    if (info.final_proj) {
+        Ref o = b.alloc("cv.out", int64_t(T) * 256);
+        b.gemm("cv.out", cur, 768, 768, 0, W("fp.w"), 768, W("fp.b"), o, 256, T, 256, 768, ACT_NONE);
+        cur = o;
+    } else {
+        b.alias("cv.out", cur, int64_t(T) * 768);
+    }
+    return cur;
+}
+
+// ------------------------------------------------------------------------------------------
+// RMVPE (rmvpe.rs:250-261 `pitch`): last L samples -> salience [T,360] -> f0 [T]
+// ------------------------------------------------------------------------------------------
+
+struct Map2d { Ref base; int T, F, C; };  // halo-padded NHWC, C = full pixel stride
+
+int64_t interior(const Map2d& m) { return (int64_t(m.F + 2) + 1) * m.C; }
+
+void conv3x3(PB& b, const Packed* P, const std::string& name, const std::string& wname, const Map2d& in,
+             int cout, Ref dst_interior, int64_t ld_dst, int act, Ref R, int64_t ldr) {
+    GemmOp& g = b.gemm(name, in.base, in.C, 3 * in.C, int64_t(in.F + 2) * in.C, b.w(P, SP_F0, wname + ".w"),
+                       9 * in.C, b.w(P, SP_F0, wname + ".b"), dst_interior, ld_dst, in.T * (in.F + 2), cout,
+                       9 * in.C, act);
+    g.mask_period = in.F + 2; g.mask_valid = in.F; g.R = R; g.ldr = ldr;
+}
+
+// ConvBlockRes: relu(bn(conv(relu(bn(conv(x)))))) + (shortcut(x) | x); result written into the
+// interior of `dst` (which may be a channel slice of a wider map: ld_dst = its pixel stride).
+void conv_block_res(PB& b, const Packed* P, const std::string& name, const std::string& wp, const Map2d& in,
+                    int cout, Ref dst_interior, int64_t ld_dst) {
+    Map2d t1{b.pad2d(name + "t1", in.T, in.F, cout), in.T, in.F, cout};
+    conv3x3(b, P, name + "c1", wp + "c1", in, cout, t1.base.plus(interior(t1)), cout, ACT_RELU, Ref{}, 0);
+    Ref R; int64_t ldr;
+    const int M = in.T * (in.F + 2);
+    if (in.C != cout) {
+        Ref sc = b.alloc(name + "sc", int64_t(M) * cout);
+        b.gemm(name + "sc", in.base.plus(interior(in)), in.C, in.C, 0, b.w(P, SP_F0, wp + "sc.w"), in.C,
+               b.w(P, SP_F0, wp + "sc.b"), sc, cout, M, cout, in.C, ACT_NONE);
+        R = sc; ldr = cout;
+    } else {
+        R = in.base.plus(interior(in)); ldr = in.C;
+    }
+    conv3x3(b, P, name + "c2", wp + "c2", t1, cout, dst_interior, ld_dst, ACT_RELU, R, ldr);
+}
+
+struct F0Out { Ref salience, f0, argmax, mel; int T; };
+
+F0Out build_rmvpe(PB& b, const Packed* P, const F0Info& info, Ref pcm_window, int L, Ref params,
+                  bool mel_only, int upstream_window) {
+    F0Out o{};
+    const int T = 1 + L / 160, F = 128;
+    o.T = T;
+    auto W = [&](const std::string& n) { return b.w(P, SP_F0, n); };
+    o.mel = b.alloc("mel", int64_t(T) * 128);
+    Map2d in0{Ref{}, T, F, 1};
+    if (!mel_only) {
+        if (T % 32 != 0) { b.fail("mel frame count must be a multiple of 32 (rmvpe.rs:227)"); return o; }
+        in0.base = b.pad2d("rm.in", T, F, 1);
+    }
+    {
+        Op& op = b.add(OP_STFTMEL, "mel");
+        StftMelOp& s = op.stft;
+        s.pcm = pcm_window; s.L = L; s.T = T; s.window = W("window"); s.band_start = W("mel.start");
+        s.band_count = W("mel.count"); s.band_off = W("mel.off"); s.band_w = W("mel.w"); s.mel = o.mel;
+        if (!mel_only) { s.out2 = in0.base.plus(interior(in0)); s.out2_pitch = F + 2; }
+        s.scale = info.in_scale; s.shift = info.in_shift; s.clamp = 1e-5f;
+    }
+    if (mel_only) return o;
+
+    // encoder: 5 levels x 4 ConvBlockRes, 2x2 average pool; the un-pooled output of level i is
+    // written straight into the upper channel half of the decoder's concat map
+    Map2d cat[5];
+    Map2d cur = in0;
+    int C = 16, Tl = T, Fl = F;
+    for (int i = 0; i < 5; ++i) {
+        cat[i] = Map2d{b.pad2d("rm.cat" + S(i), Tl, Fl, 2 * C), Tl, Fl, 2 * C};
+        for (int j = 0; j < 4; ++j) {
+            std::string nm = "rm.enc" + S(i) + "." + S(j) + ".", wp = "enc" + S(i) + "." + S(j) + ".";
+            if (j < 3) {
+                Map2d y{b.pad2d(nm + "y", Tl, Fl, C), Tl, Fl, C};
+                conv_block_res(b, P, nm, wp, cur, C, y.base.plus(interior(y)), C);
+                cur = y;
+            } else {
+                conv_block_res(b, P, nm, wp, cur, C, cat[i].base.plus(interior(cat[i]) + C), 2 * C);
+            }
+        }
+        Map2d pooled{b.pad2d("rm.pool" + S(i), Tl / 2, Fl / 2, C), Tl / 2, Fl / 2, C};
+        {
+            Op& op = b.add(OP_AVGPOOL, "rm.pool" + S(i));
+            op.pool.in = cat[i].base.plus(C); op.pool.ldin = 2 * C; op.pool.out = pooled.base;
+            op.pool.T = Tl; op.pool.F = Fl; op.pool.C = C;
+        }
+        cur = pooled; Tl /= 2; Fl /= 2; C *= 2;
+    }
+    // intermediate: 16 blocks at (T/32) x 4, 256 -> 512
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            std::string nm = "rm.mid" + S(i) + "." + S(j) + ".", wp = "mid" + S(i) + "." + S(j) + ".";
+            Map2d y{b.pad2d(nm + "y", Tl, Fl, 512), Tl, Fl, 512};
+            conv_block_res(b, P, nm, wp, cur, 512, y.base.plus(interior(y)), 512);
+            cur = y;
+        }
+    b.alias("rm.inter", cur.base, (int64_t(Tl + 2) * (Fl + 2)) * 512);
+    // decoder: ConvTranspose2d(k3,s2) as one GEMM over the 2x2 input neighbourhood with the
+    // four output phases stacked along N, scattered pixel-shuffle style into the concat map
+    int cin = 512;
+    for (int i = 0; i < 5; ++i) {
+        int cout = cin / 2;
+        const Map2d& ct = cat[4 - i];
+        std::string d = "dec" + S(i) + ".";
+        {
+            GemmOp& g = b.gemm("rm.dec" + S(i) + ".up", cur.base.plus(interior(cur)), cin, 2 * cin,
+                               int64_t(cur.F + 2) * cin, W(d + "up.w"), 4 * cin, W(d + "up.b"),
+                               ct.base.plus(interior(ct)), 2 * cout, cur.T * (cur.F + 2), 4 * cout, 4 * cin,
+                               ACT_RELU);
+            g.out_mode = OUT_PIXSHUF2; g.om_a = cur.F + 2; g.om_b = cout; g.om_c = ct.F + 2;
+        }
+        cur = ct;
+        for (int j = 0; j < 4; ++j) {
+            std::string nm = "rm.dec" + S(i) + "." + S(j) + ".";
+            Map2d y{b.pad2d(nm + "y", ct.T, ct.F, cout), ct.T, ct.F, cout};
+            conv_block_res(b, P, nm, d + S(j) + ".", cur, cout, y.base.plus(interior(y)), cout);
+            cur = y;
+        }
+        cin = cout;
+    }
+    b.alias("rm.dec4", cur.base, (int64_t(T + 2) * (F + 2)) * 16);
+    Map2d cn{b.pad2d("rm.cnn", T, F, 3), T, F, 3};
+    conv3x3(b, P, "rm.cnn", "cnn", cur, 3, cn.base.plus(interior(cn)), 3, ACT_NONE, Ref{}, 0);
+    // BiGRU input projections for both directions: rows of the padded cnn map are the GEMM rows
+    const int KI = (F + 2) * 3;
+    Ref gi = b.alloc("rm.gi", int64_t(T) * 1536);
+    b.gemm("rm.gi", cn.base.plus(KI), KI, KI, 0, W("gru.wih"), KI, W("gru.bih"), gi, 1536, T, 1536, KI, ACT_NONE);
+    Ref h = b.alloc("rm.gru", int64_t(T) * 512);
+    {
+        Op& op = b.add(OP_GRU, "rm.gru");
+        op.gru.gi = gi; op.gru.whh_t = W("gru.whh_t"); op.gru.bhh = W("gru.bhh"); op.gru.out = h; op.gru.T = T;
+        op.gru.H = 256;
+    }
+    o.salience = b.alloc("rm.salience", int64_t(T) * 360);
+    b.gemm("rm.salience", h, 512, 512, 0, W("fc.w"), 512, W("fc.b"), o.salience, 360, T, 360, 512, ACT_SIGMOID);
+    o.f0 = b.alloc("f0", T);
+    o.argmax = b.alloc("f0_argmax", T, true);
+    {
+        Op& op = b.add(OP_F0DECODE, "f0");
+        op.f0d.salience = o.salience; op.f0d.f0 = o.f0; op.f0d.argmax = o.argmax; op.f0d.params = params;
+        op.f0d.T = T; op.f0d.bins = 360; op.f0d.threshold = 0.03f; op.f0d.upstream_window = upstream_window;
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthesizer (rvc.rs:193-214): phone [R,C], pitch i32[R], pitchf [R] -> audio [R*400]
+// ------------------------------------------------------------------------------------------
+Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitch, Ref pitchf, Ref params,
+                Ref audio, int R, bool multi_lane) {
+    const int H = 192;
+    auto W = [&](const std::string& n) { return b.w(P, SP_SYN, n); };
+    // ---- enc_p ---------------------------------------------------------------------------
+    Ref xpad = b.alloc("", int64_t(R + 2) * H);  // 1 zero row either side (FFN k=3)
+    Ref x = xpad.plus(H);
+    b.alias("sy.emb", x, int64_t(R) * H);
+    {
+        Op& op = b.add(OP_EMBED, "sy.emb");
+        op.embed.phone = phone; op.embed.pitch = pitch; op.embed.wp = W("emb.wp"); op.embed.bp = W("emb.bp");
+        op.embed.emb_pitch = W("emb.pitch"); op.embed.out = x; op.embed.ldo = H; op.embed.R = R;
+        op.embed.Cin = info.phone_dim; op.embed.H = H;
+    }
+    for (int i = 0; i < 6; ++i) {
+        std::string d = "E" + S(i) + ".", n = "sy.E" + S(i) + ".";
+        Ref qkv = b.alloc(n + "qkv", int64_t(R) * 3 * H);
+        b.gemm(n + "qkv", x, H, H, 0, W(d + "qkv.w"), H, W(d + "qkv.b"), qkv, 3 * H, R, 3 * H, H, ACT_NONE);
+        Ref a = b.alloc(n + "attn", int64_t(R) * H);
+        {
+            Op& op = b.add(OP_RELATTN, n + "attn");
+            op.relattn.qkv = qkv; op.relattn.ldqkv = 3 * H; op.relattn.out = a; op.relattn.ldo = H;
+            op.relattn.rel_k = W(d + "relk"); op.relattn.rel_v = W(d + "relv"); op.relattn.T = R;
+            op.relattn.heads = 2; op.relattn.dim = 96; op.relattn.window = 10;
+        }
+        Ref t1 = b.alloc(n + "o", int64_t(R) * H);
+        { GemmOp& g = b.gemm(n + "o", a, H, H, 0, W(d + "o.w"), H, W(d + "o.b"), t1, H, R, H, H, ACT_NONE);
+          g.R = x; g.ldr = H; }
+        Ref x1pad = b.alloc("", int64_t(R + 2) * H);
+        Ref x1 = x1pad.plus(H);
+        b.alias(n + "ln1", x1, int64_t(R) * H);
+        b.layernorm(n + "ln1", t1, H, x1, H, W(d + "ln1.g"), W(d + "ln1.b"), R, H);
+        Ref hpad = b.alloc("", int64_t(R + 2) * 768);
+        Ref h = hpad.plus(768);
+        b.alias(n + "ffn1", h, int64_t(R) * 768);
+        b.gemm(n + "ffn1", x1pad, H, 3 * H, 0, W(d + "ffn1.w"), 3 * H, W(d + "ffn1.b"), h, 768, R, 768, 3 * H, ACT_RELU);
+        Ref t2 = b.alloc(n + "ffn2", int64_t(R) * H);
+        { GemmOp& g = b.gemm(n + "ffn2", hpad, 768, 3 * 768, 0, W(d + "ffn2.w"), 3 * 768, W(d + "ffn2.b"), t2, H, R, H, 3 * 768, ACT_NONE);
+          g.R = x1; g.ldr = H; }
+        Ref x2pad = b.alloc("", int64_t(R + 2) * H);
+        Ref x2 = x2pad.plus(H);
+        b.alias("sy.enc" + S(i), x2, int64_t(R) * H);
+        b.layernorm("sy.enc" + S(i), t2, H, x2, H, W(d + "ln2.g"), W(d + "ln2.b"), R, H);
+        xpad = x2pad; x = x2;
+    }
+    Ref stats = b.alloc("sy.stats", int64_t(R) * 2 * H);
+    b.gemm("sy.stats", x, H, H, 0, W("proj.w"), H, W("proj.b"), stats, 2 * H, R, 2 * H, H, ACT_NONE);
+    // ---- z_p + flow (reverse) --------------------------------------------------------------
+    Ref zpad = b.alloc("", int64_t(R + 6) * H);  // 3 zero rows either side (conv_pre k=7)
+    Ref z = zpad.plus(3 * H);
+    b.alias("sy.z", z, int64_t(R) * H);
+    {
+        Op& op = b.add(OP_ZP, "sy.z_p");
+        op.zp.stats = stats; op.zp.out = z; op.zp.ldo = H; op.zp.params = params; op.zp.R = R; op.zp.H = H;
+    }
+    for (int fl = 3; fl >= 0; --fl) {
+        const bool flipped = (fl == 3 || fl == 1);
+        std::string d = "F" + S(fl) + ".", n = "sy.F" + S(fl) + ".";
+        Ref xopad = b.alloc("", int64_t(R + 4) * 2 * H);  // [x | skip-sum], 2 zero rows either side
+        Ref xo = xopad.plus(2 * 2 * H);
+        b.alias(n + "xo", xo, int64_t(R) * 2 * H);
+        b.gemm(n + "pre", flipped ? z.plus(96) : z, H, 96, 0, W(d + "pre.w"), 96, W(d + "pre.b"), xo, 2 * H, R,
+               2 * H, 96, ACT_NONE);
+        for (int i = 0; i < 3; ++i) {
+            Ref acts = b.alloc(n + "acts" + S(i), int64_t(R) * H);
+            b.gemm(n + "in" + S(i), xopad, 2 * H, H, 2 * H, W(d + "in" + S(i) + ".w"), 5 * H,
+                   W(d + "in" + S(i) + ".b"), acts, H, R, 2 * H, 5 * H, ACT_GATE);
+            int rs = i < 2 ? 2 * H : H;
+            Ref dst = i < 2 ? xo : xo.plus(H);
+            GemmOp& g = b.gemm(n + "rs" + S(i), acts, H, H, 0, W(d + "rs" + S(i) + ".w"), H,
+                               W(d + "rs" + S(i) + ".b"), dst, 2 * H, R, rs, H, ACT_NONE);
+            g.R = dst; g.ldr = 2 * H;
+        }
+        Ref x1 = flipped ? z : z.plus(96);
+        GemmOp& g = b.gemm("sy.flow" + S(fl), xo.plus(H), 2 * H, H, 0, W(d + "post.w"), H, W(d + "post.b"), x1, H, R,
+                           96, H, ACT_NONE);
+        g.alpha = -1.0f; g.R = x1; g.ldr = H;
+    }
+    // ---- GeneratorNSF ----------------------------------------------------------------------
+    const int upp = 400, L = R * upp, HH = 32;
+    Ref harpad = b.alloc("", L + 2 * HH);
+    Ref har = harpad.plus(HH);
+    b.alias("sy.har", har, L);
+    Ref sine_dbg = b.alloc("sy.sine", L);
+    {
+        Op& op = b.add(OP_SINEGEN, "sy.sine");
+        op.sine.pitchf = pitchf; op.sine.out = har; op.sine.sine_dbg = sine_dbg; op.sine.params = params;
+        op.sine.R = R; op.sine.upp = upp; op.sine.sr = float(info.sr); op.sine.lin_w = info.lin_w;
+        op.sine.lin_b = info.lin_b;
+    }
+    static const int RATES[4] = {10, 10, 2, 2}, UK[4] = {16, 16, 4, 4}, RK[3] = {3, 7, 11}, RD[3] = {1, 3, 5};
+    // conv_pre (+ cond(g) folded into the bias); lrelu'd copy feeds ups[0] (1 halo row)
+    Ref pre_raw = b.alloc("sy.conv_pre", int64_t(R) * 512);
+    Ref upin_pad = b.alloc("", int64_t(R + 2) * 512);
+    {
+        GemmOp& g = b.gemm("sy.conv_pre", zpad, H, 7 * H, 0, W("pre.w"), 7 * H, W("pre.b"), pre_raw, 512, R, 512,
+                           7 * H, ACT_NONE);
+        g.C2 = upin_pad.plus(512); g.ldc2 = 512; g.act2 = ACT_LRELU01;
+    }
+    int Tin = R, cin = 512;
+    for (int i = 0; i < 4; ++i) {
+        const int u = RATES[i], k = UK[i], p = (k - u) / 2, cout = cin / 2, Tout = Tin * u;
+        std::string d = "U" + S(i) + ".", n = "sy.U" + S(i) + ".";
+        Ref xu_pad = b.alloc("", int64_t(Tout + 2 * HH) * cout);
+        Ref xu = xu_pad.plus(int64_t(HH) * cout);
+        b.alias("sy.up" + S(i), xu, int64_t(Tout) * cout);
+        Ref xa_pad = b.alloc("", int64_t(Tout + 2 * HH) * cout);
+        Ref xa = xa_pad.plus(int64_t(HH) * cout);
+        {   // ConvTranspose1d: rows (q-1, q) of the input -> u output phases per row q
+            GemmOp& g = b.gemm(n + "up", upin_pad, cin, 2 * cin, 0, W(d + "up.w"), 2 * cin, W(d + "up.b"), xu, cout,
+                               Tin + 1, u * cout, 2 * cin, ACT_NONE);
+            g.out_mode = OUT_CONVT1D; g.om_a = u; g.om_b = cout; g.om_c = p; g.om_d = Tout;
+        }
+        {   // + noise_convs[i](har): Conv1d(1,cout,2sf,stride sf,pad sf/2) == GEMM over har rows
+            int sf = 1; for (int j = i + 1; j < 4; ++j) sf *= RATES[j];
+            int nk = (i + 1 < 4) ? 2 * sf : 1, npad = (i + 1 < 4) ? sf / 2 : 0;
+            GemmOp& g = b.gemm(n + "noise", har.plus(-npad), (i + 1 < 4) ? sf : 1, nk, 0, W(d + "noise.w"), nk,
+                               W(d + "noise.b"), xu, cout, Tout, cout, nk, ACT_NONE);
+            g.R = xu; g.ldr = cout; g.C2 = xa; g.ldc2 = cout; g.act2 = ACT_LRELU01;
+        }
+        Ref ys[3];
+        if (multi_lane) { b.wait(0, 1); b.wait(0, 2); }  // the three ResBlocks run concurrently
+        for (int j = 0; j < 3; ++j) {
+            b.lane = multi_lane ? j : 0;
+            const int rk = RK[j];
+            std::string rn = n + "rb" + S(j) + ".";
+            Ref ta_pad = b.alloc("", int64_t(Tout + 2 * HH) * cout);
+            Ref ya_pad = b.alloc("", int64_t(Tout + 2 * HH) * cout);
+            Ref y = b.alloc(rn + "y", int64_t(Tout) * cout);
+            ys[j] = y;
+            Ref in_act_pad = xa_pad, res = xu;
+            for (int dd = 0; dd < 3; ++dd) {
+                const int dil = RD[dd], pad1 = (rk * dil - dil) / 2, pad2 = (rk - 1) / 2;
+                std::string wn = d + "rb" + S(j) + "." + S(dd) + ".";
+                b.gemm(rn + S(dd) + ".c1", in_act_pad.plus(int64_t(HH - pad1) * cout), cout, cout, int64_t(dil) * cout,
+                       W(wn + "c1.w"), rk * cout, W(wn + "c1.b"), ta_pad.plus(int64_t(HH) * cout), cout, Tout, cout,
+                       rk * cout, ACT_LRELU01);
+                GemmOp& g = b.gemm(rn + S(dd) + ".c2", ta_pad.plus(int64_t(HH - pad2) * cout), cout, rk * cout, 0,
+                                   W(wn + "c2.w"), rk * cout, W(wn + "c2.b"), y, cout, Tout, cout, rk * cout,
+                                   ACT_NONE);
+                g.R = res; g.ldr = cout;
+                if (dd < 2) { g.C2 = ya_pad.plus(int64_t(HH) * cout); g.ldc2 = cout; g.act2 = ACT_LRELU01; }
+                in_act_pad = ya_pad; res = y;
+            }
+            b.lane = 0;
+        }
+        if (multi_lane) { b.wait(1, 0); b.wait(2, 0); }
+        Ref raw = b.alloc("sy.stage" + S(i), int64_t(Tout) * cout);
+        Op& op = b.add(OP_AVG3, "sy.stage" + S(i));
+        op.avg3.a = ys[0]; op.avg3.b = ys[1]; op.avg3.c = ys[2]; op.avg3.ld = cout; op.avg3.raw = raw;
+        op.avg3.ldraw = cout; op.avg3.T = Tout; op.avg3.C = cout;
+        if (i < 3) {
+            upin_pad = b.alloc("", int64_t(Tout + 2) * cout);
+            op.avg3.out = upin_pad.plus(cout); op.avg3.ldo = cout; op.avg3.slope = 0.1f;
+        } else {
+            Ref post_pad = b.alloc("", int64_t(Tout + 6) * cout);
+            op.avg3.out = post_pad.plus(3 * cout); op.avg3.ldo = cout; op.avg3.slope = 0.01f;  // F.leaky_relu default
+            Op& cp = b.add(OP_CONVPOST, "sy.audio");
+            cp.cpost.in = post_pad; cp.cpost.w = W("post.w"); cp.cpost.out = audio; cp.cpost.T = Tout;
+            cp.cpost.C = cout; cp.cpost.k = 7;
+        }
+        Tin = Tout; cin = cout;
+    }
+    return audio;
+}
+
+}  // namespace
+
+bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const Packed* cv, const CvInfo* cvi,
+                const Packed* f0, const F0Info* f0i, const Packed* syn, const SynInfo* syi, Plan& plan,
+                std::string& err) {
+    plan = Plan{};
+    PB b{plan, err};
+    plan.params = Ref{SP_STATE, StateLayout::off_params};
+    plan.cache = Ref{SP_STATE, StateLayout::off_cache};
+    plan.pcm = Ref{SP_STATE, StateLayout::off_pcm};
+    plan.audio = Ref{SP_STATE, StateLayout::off_audio};
+    plan.n_lanes = 1;
+    const int N = g.n16k;
+    if (kind != PLAN_KNN && (N <= 0 || N > StateLayout::PCM_CAP)) { err = "bad input length"; return false; }
+
+    if (kind == PLAN_KNN) {
+        // queries staged in the audio buffer region by the caller: [Q, C]; results -> work
+        const int Q = g.n16k, C = g.sf16k, k = g.return_length, Nrows = opt.index_rows;
+        if (Q <= 0 || C <= 0 || k <= 0 || k > 32 || Nrows < k) { err = "bad kNN shape"; return false; }
+        Ref D = b.alloc("knn_D", int64_t(Q) * Nrows);
+        Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
+        Op& a = b.add(OP_KNN_DIST, "knn_dist");
+        a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = plan.audio; a.kd.ldq = C; a.kd.D = D; a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q;
+        Op& s = b.add(OP_KNN_SELECT, "knn_select");
+        s.ks.D = D; s.ks.idx = idx; s.ks.d2 = d2; s.ks.N = Nrows; s.ks.Q = Q; s.ks.k = k;
+        plan.knn_q = Q;
+        plan.work_bytes = b.work + 256;
+        return b.ok;
+    }
+    if (kind == PLAN_MEL) {
+        if (!f0) { err = "f0 model not loaded"; return false; }
+        if (N < 1024) { err = "input shorter than one FFT frame"; return false; }
+        F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm, N, plan.params, true, 0);
+        plan.f0_T = o.T;
+        plan.work_bytes = b.work + 256;
+        return b.ok;
+    }
+    if (kind == PLAN_HUBERT || kind == PLAN_FEATURE) {
+        if (!cv) { err = "contentvec not loaded"; return false; }
+        int T = 0;
+        Ref x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
+        plan.hubert_T = T; plan.hubert_C = cvi->out_dim;
+        if (kind == PLAN_FEATURE && b.ok) {
+            Op& op = b.add(OP_GATHER_ROWS, "feature");
+            op.gather.src = x; op.gather.lds = cvi->out_dim; op.gather.out = plan.audio; op.gather.T = T;
+            op.gather.C = cvi->out_dim; op.gather.skip = 0; op.gather.R = 2 * T + 1;
+            if (int64_t(2 * T + 1) * cvi->out_dim > StateLayout::AUDIO_CAP) b.fail("feature too large");
+        }
+        plan.work_bytes = b.work + 256;
+        return b.ok;
+    }
+    // PLAN_PITCH / PLAN_INFER need the f0 window
+    if (!f0) { err = "f0 model not loaded"; return false; }
+    const int Lf0 = 5120 * ((g.sf16k + 800 - 1) / 5120 + 1) - 160;  // rmvpe.rs:256
+    if (Lf0 > N) { err = "input shorter than the f0 window (rmvpe.rs:257)"; return false; }
+    if (kind == PLAN_PITCH) {
+        F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
+        plan.f0_T = o.T;
+        plan.work_bytes = b.work + 256;
+        return b.ok;
+    }
+    // ---- PLAN_INFER (rvc.rs:133-220) ---------------------------------------------------------
+    if (!cv) { err = "contentvec not loaded"; return false; }
+    if (!syn) { err = "model not loaded"; return false; }
+    if (cvi->out_dim != syi->phone_dim) { err = "contentvec width does not match the voice model"; return false; }
+    const int R = g.return_length, skip = g.skip_head;
+    if (R <= 0) { err = "return_length must be positive"; return false; }
+    const bool ml = opt.multi_lane;
+    // lane 1: F0 chain, concurrently with ContentVec on lane 0
+    if (ml) { b.wait(0, 1); b.lane = 1; }
+    F0Out fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
+    b.lane = 0;
+    plan.f0_T = fo.T;
+    int T = 0;
+    Ref x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
+    if (!b.ok) return false;
+    const int C = cvi->out_dim;
+    plan.hubert_T = T; plan.hubert_C = C;
+    const int ext = 2 * T + 1;
+    const int hubert_length = std::min(N / 160, ext);              // rvc.rs:153
+    if (skip + R > ext) { err = "skip_head + return_length exceeds the feature length (rvc.rs:155)"; return false; }
+    if (hubert_length > 1024 || 1024 - hubert_length + skip + R > 1024) { err = "pitch cache range (rvc.rs:176)"; return false; }
+    if (fo.T < 4 || 1024 + 4 - fo.T < 0) { err = "pitch length"; return false; }
+    // retrieval on the 20 ms frames that survive the slice (rvc.rs:159 TODO; upstream semantics)
+    const int first = std::min(skip / 2, T - 1), last = std::min((skip + R - 1) / 2, T - 1);
+    const int Q = last - first + 1;
+    Ref src = x; int row0 = 0;
+    if (opt.with_index) {
+        const int k = opt.index_k, Nrows = opt.index_rows;
+        if (k <= 0 || k > 32 || Nrows < k) { err = "bad index / k"; return false; }
+        Ref D = b.alloc("knn_D", int64_t(Q) * Nrows);
+        Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
+        Ref xb = b.alloc("knn_blend", int64_t(Q) * C);
+        Op& a = b.add(OP_KNN_DIST, "knn_dist");
+        a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = x.plus(int64_t(first) * C); a.kd.ldq = C; a.kd.D = D;
+        a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q;
+        Op& s = b.add(OP_KNN_SELECT, "knn_select");
+        s.ks.D = D; s.ks.idx = idx; s.ks.d2 = d2; s.ks.N = Nrows; s.ks.Q = Q; s.ks.k = k;
+        Op& m = b.add(OP_KNN_BLEND, "knn_blend");
+        m.kb.index = Ref{SP_IDX, 0}; m.kb.idx = idx; m.kb.d2 = d2; m.kb.x = x.plus(int64_t(first) * C); m.kb.ldx = C;
+        m.kb.out = xb; m.kb.params = plan.params; m.kb.C = C; m.kb.Q = Q; m.kb.k = k;
+        src = xb; row0 = first;
+        plan.knn_q = Q;
+    }
+    Ref phone = b.alloc("phone", int64_t(R) * C);
+    {
+        Op& op = b.add(OP_GATHER_ROWS, "phone");
+        op.gather.src = src; op.gather.lds = C; op.gather.out = phone; op.gather.T = T; op.gather.C = C;
+        op.gather.skip = skip; op.gather.R = R; op.gather.row0 = row0;
+    }
+    if (ml) b.wait(1, 0);
+    Ref pitch = b.alloc("pitch", R, true), pitchf = b.alloc("pitchf", R);
+    {
+        Op& op = b.add(OP_F0POST, "pitch");
+        F0PostOp& p = op.f0p;
+        p.f0 = fo.f0; p.cache = plan.cache; p.pitch = pitch; p.pitchf = pitchf; p.pitch_len = fo.T;
+        p.shift = g.sf16k / 160; p.hubert_length = hubert_length; p.skip_head = skip; p.return_length = R;
+        p.cache_len = 1024;
+        p.mel_min = std::log(50.0f / 700.0f + 1.0f) * 1127.0f;   // rvc.rs:31-34 (f32)
+        p.mel_max = std::log(500.0f / 700.0f + 1.0f) * 1127.0f;
+    }
+    const int audio_len = R * (syi->sr / 100);
+    if (audio_len > StateLayout::AUDIO_CAP) { err = "output too long"; return false; }
+    build_synth(b, syn, *syi, phone, pitch, pitchf, plan.params, plan.audio, R, ml);
+    plan.audio_len = audio_len;
+    plan.work_bytes = b.work + 256;
+    return b.ok;
+}
+
+}  // namespace rvc
