@@ -1,0 +1,602 @@
+// engine.cu - context, weight residency, plan cache, CUDA-graph replay and the C ABI
+// (include/rvc_b200.h).  Replaces rvc::RvcInfer (reference rvc/src/rvc.rs:18-220) and the
+// rvc-rpc dispatch around it (rvc-rpc/src/main.rs:56-101) with an in-process engine:
+//   * weights are packed once (model.cpp) and stay resident in HBM;
+//   * per (call kind, geometry) an op list is built (plan.cpp), its work arena allocated and
+//     zeroed once (halo invariants), and after one eager run the whole window is captured into a
+//     CUDA graph spanning up to three stream lanes (F0 chain || ContentVec, 3 ResBlocks);
+//   * per-call variability (pitch shift, window counter, index rate) travels in a 64-byte
+//     parameter block written by a one-thread kernel, so graph replays need no re-instantiation;
+//   * the pitch cache (rvc.rs:26,168-179) is per-context device state.
+// There is no CPU execution path: every op is a kernel launch and a missing device is an error.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/rvc_b200.h"
+#include "launch.h"
+#include "model.h"
+
+using namespace rvc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    uint8_t* d = nullptr; size_t bytes = 0;
+    void release() { if (d) cudaFree(d); d = nullptr; bytes = 0; }
+};
+
+struct Model {
+    Packed packed;  // offsets kept; host copy dropped after upload
+    DevBuf dev;
+    bool loaded = false;
+    void unload() { dev.release(); packed = Packed{}; loaded = false; }
+};
+
+struct PlanKey {
+    int kind; Geometry g; int with_index; int index_rows; int k;
+    bool operator<(const PlanKey& o) const {
+        if (kind != o.kind) return kind < o.kind;
+        if (g < o.g) return true;
+        if (o.g < g) return false;
+        if (with_index != o.with_index) return with_index < o.with_index;
+        if (index_rows != o.index_rows) return index_rows < o.index_rows;
+        return k < o.k;
+    }
+};
+
+struct PlanEntry {
+    Plan plan;
+    DevBuf work;
+    cudaGraphExec_t exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    int runs = 0;
+    int launches = 0;
+    ~PlanEntry() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        work.release();
+    }
+};
+
+constexpr int MAX_LANES = 4;
+
+__global__ void set_params_kernel(RunParams* p, float uppower, float index_rate, unsigned long long seed,
+                                  unsigned long long window, int noise_mode) {
+    p->uppower = uppower; p->index_rate = index_rate; p->noise_seed = seed; p->window = window; p->noise_mode = noise_mode;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    __shared__ float tile[32][33];
+    int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) if (r0 + i < rows && c < cols) tile[i][threadIdx.x] = in[(long long)(r0 + i) * cols + c];
+    __syncthreads();
+    int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) if (c0 + i < cols && r < rows) out[(long long)(c0 + i) * rows + r] = tile[threadIdx.x][i];
+}
+
+}  // namespace
+
+struct rvc_ctx {
+    std::string data_path, err;
+    rvc_config cfg{};
+    cudaStream_t streams[MAX_LANES] = {nullptr};
+    std::vector<cudaEvent_t> events;
+    Model cv, f0, syn;
+    CvInfo cvi; F0Info f0i; SynInfo syi;
+    DevBuf index; int index_rows = 0, index_c = 0; float index_rate = 0.f;
+    DevBuf state;
+    std::map<PlanKey, std::unique_ptr<PlanEntry>> plans;
+    PlanEntry* last = nullptr;
+    uint64_t window = 0, total_launches = 0;
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return RVC_ERR_CUDA;
+    }
+    void drop_plans() { sync_all(); plans.clear(); last = nullptr; }
+    void sync_all() { for (auto s : streams) if (s) cudaStreamSynchronize(s); }
+    DeviceBases bases(const PlanEntry& e) const {
+        DeviceBases B;
+        B.b[SP_CV] = cv.dev.d; B.b[SP_F0] = f0.dev.d; B.b[SP_SYN] = syn.dev.d; B.b[SP_IDX] = index.d;
+        B.b[SP_WORK] = e.work.d; B.b[SP_STATE] = state.d;
+        return B;
+    }
+};
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call); } while (0)
+
+int upload(rvc_ctx* ctx, Model& m) {
+    size_t bytes = m.packed.host.size() * sizeof(float);
+    m.dev.release();
+    CK(cudaMalloc(&m.dev.d, bytes + 256));
+    m.dev.bytes = bytes;
+    CK(cudaMemcpy(m.dev.d, m.packed.host.data(), bytes, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
+    std::vector<float>().swap(m.packed.host);
+    m.loaded = true;
+    return RVC_OK;
+}
+
+int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
+    const DeviceBases B = ctx->bases(e);
+    size_t ev = 0;
+    int n = 0;
+    for (const Op& op : e.plan.ops) {
+        cudaStream_t s = ctx->streams[op.lane];
+        switch (op.kind) {
+            case OP_GEMM: n += launch_gemm(op.gemm, B, s); break;
+            case OP_LAYERNORM: n += launch_layernorm(op.ln, B, s); break;
+            case OP_ATTN: n += launch_attn(op.attn, B, s); break;
+            case OP_RELATTN: n += launch_relattn(op.relattn, B, s); break;
+            case OP_CONV0_STATS: n += launch_conv0_stats(op.c0s, B, s); break;
+            case OP_CONV0_APPLY: n += launch_conv0_apply(op.c0a, B, s); break;
+            case OP_STFTMEL: n += launch_stftmel(op.stft, B, s); break;
+            case OP_AVGPOOL: n += launch_avgpool(op.pool, B, s); break;
+            case OP_GRU: n += launch_gru(op.gru, B, s); break;
+            case OP_F0DECODE: n += launch_f0decode(op.f0d, B, s); break;
+            case OP_F0POST: n += launch_f0post(op.f0p, B, s); break;
+            case OP_EMBED: n += launch_embed(op.embed, B, s); break;
+            case OP_ZP: n += launch_zp(op.zp, B, s); break;
+            case OP_SINEGEN: n += launch_sinegen(op.sine, B, s); break;
+            case OP_AVG3: n += launch_avg3(op.avg3, B, s); break;
+            case OP_CONVPOST: n += launch_convpost(op.cpost, B, s); break;
+            case OP_KNN_SCAN: n += launch_knn_scan(op.kd, B, s); break;
+            case OP_KNN_SELECT: n += launch_knn_select(op.ks, B, s); break;
+            case OP_KNN_BLEND: n += launch_knn_blend(op.kb, B, s); break;
+            case OP_GATHER_ROWS: n += launch_gather_rows(op.gather, B, s); break;
+            case OP_FILL: CK(cudaMemsetAsync(B.p<uint8_t>(op.fill.dst), 0, op.fill.bytes, s)); break;
+            case OP_WAIT: {
+                if (ev >= ctx->events.size()) {
+                    cudaEvent_t x; CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+                    ctx->events.push_back(x);
+                }
+                CK(cudaEventRecord(ctx->events[ev], ctx->streams[op.wait.src_lane]));
+                CK(cudaStreamWaitEvent(ctx->streams[op.wait.dst_lane], ctx->events[ev], 0));
+                ++ev;
+                break;
+            }
+        }
+    }
+    CK(cudaGetLastError());
+    *launches = n;
+    return RVC_OK;
+}
+
+int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
+    PlanKey key{int(kind), g, (ctx->index.d && kind == PLAN_INFER) ? 1 : 0, ctx->index_rows, ctx->cfg.index_k};
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) { *out = it->second.get(); return RVC_OK; }
+    PlanOptions opt;
+    opt.index_k = ctx->cfg.index_k; opt.upstream_cents_window = ctx->cfg.upstream_cents_window;
+    opt.with_index = key.with_index || kind == PLAN_KNN; opt.index_rows = ctx->index_rows; opt.multi_lane = true;
+    auto e = std::make_unique<PlanEntry>();
+    std::string err;
+    if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.packed : nullptr,
+                    &ctx->f0i, ctx->syn.loaded ? &ctx->syn.packed : nullptr, &ctx->syi, e->plan, err))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, err);
+    if (e->plan.n_lanes > MAX_LANES) return ctx->fail(RVC_ERR_INVALID_ARG, "too many lanes");
+    CK(cudaMalloc(&e->work.d, size_t(e->plan.work_bytes)));
+    e->work.bytes = size_t(e->plan.work_bytes);
+    CK(cudaMemsetAsync(e->work.d, 0, e->work.bytes, ctx->streams[0]));  // establishes the zero halos once
+    *out = e.get();
+    ctx->plans[key] = std::move(e);
+    return RVC_OK;
+}
+
+// enqueues one execution of the plan on the context streams (lane 0 = ctx->streams[0])
+int run_plan(rvc_ctx* ctx, PlanEntry& e) {
+    int n = 0;
+    if (ctx->cfg.use_cuda_graph && e.exec) {
+        CK(cudaGraphLaunch(e.exec, ctx->streams[0]));
+        n = e.launches;
+    } else if (ctx->cfg.use_cuda_graph && e.runs >= 1) {
+        CK(cudaStreamBeginCapture(ctx->streams[0], cudaStreamCaptureModeThreadLocal));
+        int rc = issue_ops(ctx, e, &n);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(ctx->streams[0], &g);
+        if (rc != RVC_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) return ctx->cuda_fail(ce, "cudaStreamEndCapture");
+        e.graph = g; e.launches = n;
+        CK(cudaGraphInstantiate(&e.exec, g, 0));
+        CK(cudaGraphLaunch(e.exec, ctx->streams[0]));
+    } else {
+        int rc = issue_ops(ctx, e, &n);
+        if (rc != RVC_OK) return rc;
+        e.launches = n;
+    }
+    e.runs++;
+    ctx->total_launches += uint64_t(n);
+    ctx->last = &e;
+    return RVC_OK;
+}
+
+int set_params(rvc_ctx* ctx, int32_t pitch_shift) {
+    float up;
+    if (ctx->cfg.upstream_pitch_shift) up = std::pow(2.0f, float(pitch_shift) / 12.0f);
+    else up = std::ldexp(1.0f, pitch_shift / 12);  // 2.0f32.powi(pitch_shift / 12): i32 division (rvc.rs:121)
+    set_params_kernel<<<1, 1, 0, ctx->streams[0]>>>(reinterpret_cast<RunParams*>(ctx->state.d + StateLayout::off_params), up,
+                                                    ctx->index_rate, ctx->cfg.noise_seed, ctx->window, ctx->cfg.noise_mode);
+    ctx->total_launches++;
+    return RVC_OK;
+}
+
+int enter(rvc_ctx* ctx) {
+    if (!ctx) return RVC_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->cfg.device));
+    return RVC_OK;
+}
+
+float* state_pcm(rvc_ctx* ctx) { return reinterpret_cast<float*>(ctx->state.d + StateLayout::off_pcm); }
+float* state_audio(rvc_ctx* ctx) { return reinterpret_cast<float*>(ctx->state.d + StateLayout::off_audio); }
+
+int enqueue_infer(rvc_ctx* ctx, const float* pcm, size_t n, bool pcm_on_device, uint32_t sf16k, int32_t shift, uint32_t skip_head,
+                  uint32_t return_length, float* out, bool out_on_device, size_t cap, size_t* out_len) {
+    if (!ctx->syn.loaded) return ctx->fail(RVC_ERR_MODEL_NOT_LOADED, "ModelNotLoaded");          // rvc.rs:141
+    if (!ctx->cv.loaded) return ctx->fail(RVC_ERR_CONTENTVEC_NOT_LOADED, "ContentvecNotLoaded");  // rvc.rs:85
+    if (!ctx->f0.loaded) return ctx->fail(RVC_ERR_F0_NOT_LOADED, "F0NotLoaded");
+    if (!pcm || !out || n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    Geometry g{int32_t(n), int32_t(sf16k), int32_t(skip_head), int32_t(return_length)};
+    PlanEntry* e = nullptr;
+    int rc = get_plan(ctx, PLAN_INFER, g, &e);
+    if (rc != RVC_OK) return rc;
+    if (size_t(e->plan.audio_len) > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    CK(cudaMemcpyAsync(state_pcm(ctx), pcm, n * sizeof(float), pcm_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    set_params(ctx, shift);
+    rc = run_plan(ctx, *e);
+    if (rc != RVC_OK) return rc;
+    ctx->window++;
+    CK(cudaMemcpyAsync(out, state_audio(ctx), size_t(e->plan.audio_len) * sizeof(float),
+                       out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (out_len) *out_len = size_t(e->plan.audio_len);
+    return RVC_OK;
+}
+
+int copy_named(rvc_ctx* ctx, const PlanEntry& e, const std::string& name, void* out, size_t cap_bytes, size_t* out_bytes) {
+    const NamedBuf* nb = e.plan.find(name);
+    if (!nb) return ctx->fail(RVC_ERR_INVALID_ARG, "no such buffer: " + name);
+    size_t bytes = size_t(nb->elems) * 4;
+    if (out_bytes) *out_bytes = bytes;
+    if (!out) return RVC_OK;
+    if (bytes > cap_bytes) return ctx->fail(RVC_ERR_INVALID_ARG, "buffer too small for " + name);
+    ctx->sync_all();
+    const DeviceBases B = ctx->bases(e);
+    CK(cudaMemcpy(out, B.b[nb->ref.space] + nb->ref.off, bytes, cudaMemcpyDeviceToHost));
+    return RVC_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* rvc_version(void) { return "rvc_b200 0.1 (sm_100a)"; }
+
+void rvc_config_default(rvc_config* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->device = 0; cfg->noise_mode = 1; cfg->noise_seed = 0; cfg->index_k = 8; cfg->use_cuda_graph = 1;
+}
+
+const char* rvc_last_create_error(void) { return g_create_error.c_str(); }
+const char* rvc_last_error(const rvc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
+    if (!out || !data_path) { g_create_error = "null argument"; return RVC_ERR_INVALID_ARG; }
+    *out = nullptr;
+    auto ctx = std::make_unique<rvc_ctx>();
+    if (cfg) ctx->cfg = *cfg; else rvc_config_default(&ctx->cfg);
+    if (ctx->cfg.index_k <= 0 || ctx->cfg.index_k > 16) { g_create_error = "index_k must be in [1,16]"; return RVC_ERR_INVALID_ARG; }
+    ctx->data_path = data_path;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU path)";
+        return RVC_ERR_CUDA;
+    }
+    if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) { g_create_error = "bad device ordinal"; return RVC_ERR_INVALID_ARG; }
+    if ((e = cudaSetDevice(ctx->cfg.device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return RVC_ERR_CUDA; }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, ctx->cfg.device);
+    if (prop.major != 10) {
+        g_create_error = "device is not sm_100 (kernels are built for sm_100a only): " + std::string(prop.name);
+        return RVC_ERR_CUDA;
+    }
+    init_kernel_attributes();
+    for (int i = 0; i < MAX_LANES; ++i)
+        if ((e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
+            g_create_error = cudaGetErrorString(e); return RVC_ERR_CUDA;
+        }
+    if ((e = cudaMalloc(&ctx->state.d, size_t(StateLayout::bytes))) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return RVC_ERR_CUDA; }
+    ctx->state.bytes = size_t(StateLayout::bytes);
+    cudaMemsetAsync(ctx->state.d, 0, ctx->state.bytes, ctx->streams[0]);
+    cudaStreamSynchronize(ctx->streams[0]);
+    *out = ctx.release();
+    return RVC_OK;
+}
+
+void rvc_destroy(rvc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    ctx->sync_all();
+    ctx->plans.clear();
+    ctx->cv.unload(); ctx->f0.unload(); ctx->syn.unload(); ctx->index.release(); ctx->state.release();
+    for (auto ev : ctx->events) cudaEventDestroy(ev);
+    for (auto s : ctx->streams) if (s) cudaStreamDestroy(s);
+    delete ctx;
+}
+
+int rvc_load_contentvec(rvc_ctx* ctx, int32_t model_version) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (model_version != RVC_MODEL_V1 && model_version != RVC_MODEL_V2) model_version = RVC_MODEL_V2;  // enums.rs:42-49
+    const int c = model_version == RVC_MODEL_V1 ? 256 : 768, l = model_version == RVC_MODEL_V1 ? 9 : 12;   // enums.rs:9-23
+    std::string path = ctx->data_path + "/contentvec/vec-" + std::to_string(c) + "-layer-" + std::to_string(l) + ".rvcw";
+    RvcwFile f; std::string err;
+    if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
+    ctx->drop_plans(); ctx->cv.unload();
+    if (!pack_contentvec(f, ctx->cv.packed, ctx->cvi, err)) return ctx->fail(RVC_ERR_IO, err);
+    return upload(ctx, ctx->cv);
+}
+
+int rvc_load_f0(rvc_ctx* ctx, int32_t pitch_algorithm) {
+    int rc = enter(ctx); if (rc) return rc;
+    (void)pitch_algorithm;  // enums.rs:106-113: every value maps to Rmvpe
+    std::string path = ctx->data_path + "/f0/rmvpe.rvcw";
+    RvcwFile f; std::string err;
+    if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
+    ctx->drop_plans(); ctx->f0.unload();
+    if (!pack_rmvpe(f, ctx->f0.packed, ctx->f0i, err)) return ctx->fail(RVC_ERR_IO, err);
+    return upload(ctx, ctx->f0);
+}
+
+int rvc_load_model(rvc_ctx* ctx, const char* model_path) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!model_path) return ctx->fail(RVC_ERR_INVALID_ARG, "null path");
+    RvcwFile f; std::string err;
+    if (!f.load(model_path, err)) return ctx->fail(RVC_ERR_IO, err);
+    ctx->drop_plans(); ctx->syn.unload();
+    if (!pack_synth(f, ctx->syn.packed, ctx->syi, err)) return ctx->fail(RVC_ERR_IO, err);
+    return upload(ctx, ctx->syn);
+}
+
+int rvc_unload_model(rvc_ctx* ctx) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->drop_plans(); ctx->syn.unload();
+    return RVC_OK;
+}
+
+int rvc_set_index(rvc_ctx* ctx, const float* rows, size_t n, size_t c, float index_rate) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->drop_plans(); ctx->index.release(); ctx->index_rows = 0; ctx->index_c = 0;
+    ctx->index_rate = index_rate;
+    if (!rows || n == 0) return RVC_OK;  // clears the index
+    if (c % 4 != 0 || c > 1024 || n > 0x7fffffffull || n < size_t(ctx->cfg.index_k)) return ctx->fail(RVC_ERR_BAD_SHAPE, "index must be N x C with C % 4 == 0, C <= 1024, N >= k");
+    CK(cudaMalloc(&ctx->index.d, n * c * sizeof(float)));
+    ctx->index.bytes = n * c * sizeof(float);
+    CK(cudaMemcpy(ctx->index.d, rows, ctx->index.bytes, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
+    ctx->index_rows = int(n); ctx->index_c = int(c);
+    return RVC_OK;
+}
+
+int rvc_load_index(rvc_ctx* ctx, const char* index_path, float index_rate) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!index_path) return ctx->fail(RVC_ERR_INVALID_ARG, "null path");
+    RvcwFile f; std::string err;
+    if (!f.load(index_path, err)) return ctx->fail(RVC_ERR_IO, err);
+    const HostTensor* t = f.find("big_npy");
+    if (!t || t->dtype != 0 || t->shape.size() != 2) return ctx->fail(RVC_ERR_IO, "index file has no big_npy [N,C] tensor");
+    return rvc_set_index(ctx, t->f(), size_t(t->shape[0]), size_t(t->shape[1]), index_rate);
+}
+
+int rvc_set_index_rate(rvc_ctx* ctx, float index_rate) {
+    if (!ctx) return RVC_ERR_INVALID_ARG;
+    ctx->index_rate = index_rate;
+    return RVC_OK;
+}
+
+int rvc_infer(rvc_ctx* ctx, const float* pcm, size_t n, uint32_t sf16k, int32_t pitch_shift, uint32_t skip_head,
+              uint32_t return_length, float* out, size_t cap, size_t* out_len) {
+    int rc = enter(ctx); if (rc) return rc;
+    rc = enqueue_infer(ctx, pcm, n, false, sf16k, pitch_shift, skip_head, return_length, out, false, cap, out_len);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    return RVC_OK;
+}
+
+int rvc_infer_dev(rvc_ctx* ctx, const float* pcm_dev, size_t n, uint32_t sf16k, int32_t pitch_shift, uint32_t skip_head,
+                  uint32_t return_length, float* out_dev, size_t cap, size_t* out_len) {
+    int rc = enter(ctx); if (rc) return rc;
+    return enqueue_infer(ctx, pcm_dev, n, true, sf16k, pitch_shift, skip_head, return_length, out_dev, true, cap, out_len);
+}
+
+int rvc_infer_batch(rvc_ctx* const* ctxs, size_t n_ctx, const float* const* pcm, size_t n, uint32_t sf16k, int32_t pitch_shift,
+                    uint32_t skip_head, uint32_t return_length, float* const* out, size_t cap, size_t* out_len) {
+    if (!ctxs || !pcm || !out) return RVC_ERR_INVALID_ARG;
+    for (size_t i = 0; i < n_ctx; ++i) {
+        int rc = enter(ctxs[i]); if (rc) return rc;
+        rc = enqueue_infer(ctxs[i], pcm[i], n, false, sf16k, pitch_shift, skip_head, return_length, out[i], false, cap, out_len);
+        if (rc) return rc;
+    }
+    for (size_t i = 0; i < n_ctx; ++i) {
+        rvc_ctx* ctx = ctxs[i];
+        cudaSetDevice(ctx->cfg.device);
+        CK(cudaStreamSynchronize(ctx->streams[0]));
+    }
+    return RVC_OK;
+}
+
+int rvc_hubert(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap, size_t* out_c, size_t* out_t) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->cv.loaded) return ctx->fail(RVC_ERR_CONTENTVEC_NOT_LOADED, "ContentvecNotLoaded");
+    if (!pcm || !out || n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    PlanEntry* e = nullptr;
+    rc = get_plan(ctx, PLAN_HUBERT, Geometry{int32_t(n), 0, 0, 0}, &e); if (rc) return rc;
+    const int T = e->plan.hubert_T, C = e->plan.hubert_C;
+    if (size_t(T) * C > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    CK(cudaMemcpyAsync(state_pcm(ctx), pcm, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = run_plan(ctx, *e); if (rc) return rc;
+    const NamedBuf* nb = e->plan.find("cv.out");
+    const float* src = reinterpret_cast<const float*>(e->work.d + nb->ref.off);
+    dim3 grid((C + 31) / 32, (T + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(src, state_audio(ctx), T, C);  // (T,C) -> (C,T) as rvc.rs:96
+    ctx->total_launches++;
+    CK(cudaMemcpyAsync(out, state_audio(ctx), size_t(T) * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out_c) *out_c = size_t(C);
+    if (out_t) *out_t = size_t(T);
+    return RVC_OK;
+}
+
+int rvc_extract_feature(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap, size_t* out_frames, size_t* out_c) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->cv.loaded) return ctx->fail(RVC_ERR_CONTENTVEC_NOT_LOADED, "ContentvecNotLoaded");
+    if (!pcm || !out || n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    PlanEntry* e = nullptr;
+    rc = get_plan(ctx, PLAN_FEATURE, Geometry{int32_t(n), 0, 0, 0}, &e); if (rc) return rc;
+    const size_t frames = 2 * size_t(e->plan.hubert_T) + 1, C = size_t(e->plan.hubert_C);
+    if (frames * C > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    CK(cudaMemcpyAsync(state_pcm(ctx), pcm, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = run_plan(ctx, *e); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, state_audio(ctx), frames * C * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out_frames) *out_frames = frames;
+    if (out_c) *out_c = C;
+    return RVC_OK;
+}
+
+int rvc_pitch(rvc_ctx* ctx, const float* pcm, size_t n, int32_t pitch_shift, size_t sf16k, float* out, size_t cap, size_t* out_len) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->f0.loaded) return ctx->fail(RVC_ERR_F0_NOT_LOADED, "F0NotLoaded");
+    if (!pcm || !out || n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    PlanEntry* e = nullptr;
+    rc = get_plan(ctx, PLAN_PITCH, Geometry{int32_t(n), int32_t(sf16k), 0, 0}, &e); if (rc) return rc;
+    if (size_t(e->plan.f0_T) > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    CK(cudaMemcpyAsync(state_pcm(ctx), pcm, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    set_params(ctx, pitch_shift);
+    rc = run_plan(ctx, *e); if (rc) return rc;
+    const NamedBuf* nb = e->plan.find("f0");
+    CK(cudaMemcpyAsync(out, e->work.d + nb->ref.off, size_t(e->plan.f0_T) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out_len) *out_len = size_t(e->plan.f0_T);
+    return RVC_OK;
+}
+
+int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap, size_t* out_frames) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->f0.loaded) return ctx->fail(RVC_ERR_F0_NOT_LOADED, "F0NotLoaded");
+    if (!pcm || !out || n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    PlanEntry* e = nullptr;
+    rc = get_plan(ctx, PLAN_MEL, Geometry{int32_t(n), 0, 0, 0}, &e); if (rc) return rc;
+    const int T = e->plan.f0_T;
+    if (size_t(T) * 128 > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    CK(cudaMemcpyAsync(state_pcm(ctx), pcm, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = run_plan(ctx, *e); if (rc) return rc;
+    const NamedBuf* nb = e->plan.find("mel");
+    dim3 grid(4, (T + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const float*>(e->work.d + nb->ref.off), state_audio(ctx), T, 128);
+    ctx->total_launches++;
+    CK(cudaMemcpyAsync(out, state_audio(ctx), size_t(T) * 128 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (out_frames) *out_frames = size_t(T);
+    return RVC_OK;
+}
+
+int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32_t k, float* d2, int32_t* idx) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->index.d) return ctx->fail(RVC_ERR_INVALID_ARG, "no index loaded");
+    if (!queries || !d2 || !idx || q == 0 || c != size_t(ctx->index_c) || k <= 0 || k > 16 || q * c > size_t(StateLayout::AUDIO_CAP))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "bad kNN query shape");
+    PlanEntry* e = nullptr;
+    rc = get_plan(ctx, PLAN_KNN, Geometry{int32_t(q), int32_t(c), 0, k}, &e); if (rc) return rc;
+    cudaStream_t s = ctx->streams[0];
+    CK(cudaMemcpyAsync(state_audio(ctx), queries, q * c * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = run_plan(ctx, *e); if (rc) return rc;
+    CK(cudaMemcpyAsync(idx, e->work.d + e->plan.find("knn_idx")->ref.off, q * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(d2, e->work.d + e->plan.find("knn_d2")->ref.off, q * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return RVC_OK;
+}
+
+int rvc_get_last(rvc_ctx* ctx, const char* name, void* out, size_t cap_bytes, size_t* out_bytes) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!name) return ctx->fail(RVC_ERR_INVALID_ARG, "null name");
+    if (!ctx->last) return ctx->fail(RVC_ERR_INVALID_ARG, "nothing has run yet");
+    std::string nm(name);
+    if (nm == "salience") nm = "rm.salience";
+    if (nm == "hubert") nm = "cv.out";
+    return copy_named(ctx, *ctx->last, nm, out, cap_bytes, out_bytes);
+}
+
+int rvc_debug_tensor(rvc_ctx* ctx, const char* name, float* out, size_t cap, size_t* out_len) {
+    size_t bytes = 0;
+    int rc = rvc_get_last(ctx, name, out, cap * 4, &bytes);
+    if (out_len) *out_len = bytes / 4;
+    return rc;
+}
+
+int rvc_debug_list(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) {
+    if (!ctx || !ctx->last) return RVC_ERR_INVALID_ARG;
+    std::string s;
+    for (const auto& b : ctx->last->plan.bufs) { s += b.name; s += '\n'; }
+    if (out_bytes) *out_bytes = s.size();
+    if (out && cap_bytes > 0) { size_t n = s.size() < cap_bytes - 1 ? s.size() : cap_bytes - 1; std::memcpy(out, s.data(), n); out[n] = 0; }
+    return RVC_OK;
+}
+
+int rvc_reset_state(rvc_ctx* ctx) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->sync_all();
+    CK(cudaMemsetAsync(ctx->state.d + StateLayout::off_cache, 0, StateLayout::CACHE_LEN * 4, ctx->streams[0]));
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    ctx->window = 0;
+    return RVC_OK;
+}
+
+int rvc_sync(rvc_ctx* ctx) {
+    int rc = enter(ctx); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    return RVC_OK;
+}
+
+void* rvc_cuda_stream(rvc_ctx* ctx) { return ctx ? static_cast<void*>(ctx->streams[0]) : nullptr; }
+
+int rvc_kernel_launches(rvc_ctx* ctx, uint64_t* total) {
+    if (!ctx || !total) return RVC_ERR_INVALID_ARG;
+    *total = ctx->total_launches;
+    return RVC_OK;
+}
+
+int rvc_plan_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) {
+    if (!ctx || !ctx->last) return RVC_ERR_INVALID_ARG;
+    const Plan& p = ctx->last->plan;
+    char buf[512];
+    int n = std::snprintf(buf, sizeof(buf),
+                          "{\"ops\": %zu, \"kernels_per_run\": %d, \"lanes\": %d, \"work_bytes\": %lld, \"hubert_T\": %d, \"hubert_C\": %d, "
+                          "\"f0_T\": %d, \"audio_len\": %d, \"knn_q\": %d, \"graph\": %d}",
+                          p.ops.size(), ctx->last->launches, p.n_lanes, (long long)p.work_bytes, p.hubert_T, p.hubert_C, p.f0_T,
+                          p.audio_len, p.knn_q, ctx->last->exec ? 1 : 0);
+    if (out_bytes) *out_bytes = size_t(n);
+    if (out && cap_bytes > 0) { size_t m = size_t(n) < cap_bytes - 1 ? size_t(n) : cap_bytes - 1; std::memcpy(out, buf, m); out[m] = 0; }
+    return RVC_OK;
+}
+
+}  // extern "C"

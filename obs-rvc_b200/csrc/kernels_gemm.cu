@@ -1,0 +1,299 @@
+// kernels_gemm.cu - fp32 implicit-GEMM kernel family (CUDA cores) for sm_100a.
+//
+// One contraction serves every conv1d / conv2d-3x3 / transposed conv / linear layer of the three
+// networks (ops.h GemmOp): A rows are "segmented" views of channels-last halo-padded activations,
+// W is [N,K] K-major.  This file is the exact-fp32 path: it is what the small, skinny and
+// oddly-shaped contractions run on and what parity is established with.  The dense, large-M
+// contractions are additionally served by the tcgen05/TMA kernel in kernels_umma.cu.
+//
+// Tiling: BMxBN output tile per CTA, BK=16, 256 threads as a 16x16 grid of TMxTN micro-tiles,
+// double-buffered shared memory with register prefetch (one __syncthreads per k-tile).  Global
+// loads are float4 along K (each lane a different row -> transposed, conflict-free STS); the
+// k-major shared layout gives LDS.128 operand fetches.
+#include <cstdio>
+
+#include "launch.h"
+
+namespace rvc {
+
+namespace {
+
+constexpr int BK = 16;
+
+struct GemmParams {
+    const float* A; long long lda; int seg_len; long long seg_stride;
+    const float* W; long long ldw;
+    const float* bias;
+    float* C; long long ldc;
+    float* C2; long long ldc2; int act2;
+    const float* R; long long ldr;
+    int M, N, K, act;
+    float alpha;
+    int mask_period, mask_valid;
+    long long sA, sW, sBias, sC, sR;
+    int out_mode, om_a, om_b, om_c, om_d;
+    int vec_store;
+};
+
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ float apply_act(int act, float v) {
+    switch (act) {
+        case ACT_GELU: return gelu_f(v);
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_LRELU01: return v > 0.0f ? v : 0.1f * v;
+        case ACT_LRELU001: return v > 0.0f ? v : 0.01f * v;
+        case ACT_SIGMOID: return sigmoid_f(v);
+        case ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+
+// loads 4 consecutive k of one row (zero beyond the row / K range)
+template <bool VEC>
+__device__ __forceinline__ float4 load_a4(const GemmParams& p, const float* __restrict__ A, int m, int kk) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= p.M || kk >= p.K) return v;
+    if constexpr (VEC) {
+        int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
+        return __ldg(reinterpret_cast<const float4*>(A + (long long)m * p.lda + (long long)seg * p.seg_stride + within));
+    }
+    float t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int k = kk + j;
+        if (k < p.K) {
+            int seg = k / p.seg_len, within = k - seg * p.seg_len;
+            t[j] = __ldg(A + (long long)m * p.lda + (long long)seg * p.seg_stride + within);
+        } else {
+            t[j] = 0.f;
+        }
+    }
+    return make_float4(t[0], t[1], t[2], t[3]);
+}
+
+template <bool VEC>
+__device__ __forceinline__ float4 load_w4(const GemmParams& p, const float* __restrict__ W, int n, int kk) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n >= p.N || kk >= p.K) return v;
+    if constexpr (VEC) return __ldg(reinterpret_cast<const float4*>(W + (long long)n * p.ldw + kk));
+    float t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = (kk + j < p.K) ? __ldg(W + (long long)n * p.ldw + kk + j) : 0.f;
+    return make_float4(t[0], t[1], t[2], t[3]);
+}
+
+template <int BM, int BN, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
+    static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+    static_assert(BN / TN == 16, "16 thread columns");
+    constexpr int A_F4 = BM * BK / 4, W_F4 = BN * BK / 4;  // float4 loads per k-tile
+    constexpr int A_PER = (A_F4 + 255) / 256, W_PER = (W_F4 + 255) / 256;
+    __shared__ __align__(16) float As[2][BK][BM];
+    __shared__ __align__(16) float Ws[2][BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int bz = blockIdx.z;
+    const float* __restrict__ A = p.A + bz * p.sA;
+    const float* __restrict__ W = p.W + bz * p.sW;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    float4 ra[A_PER], rw[W_PER];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            int f = tid + i * 256;
+            if (A_F4 >= 256 || f < A_F4) ra[i] = load_a4<VEC>(p, A, m0 + (f % BM), k0 + (f / BM) * 4);
+        }
+#pragma unroll
+        for (int i = 0; i < W_PER; ++i) {
+            int f = tid + i * 256;
+            if (W_F4 >= 256 || f < W_F4) rw[i] = load_w4<VEC>(p, W, n0 + (f % BN), k0 + (f / BN) * 4);
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            int f = tid + i * 256;
+            if (A_F4 >= 256 || f < A_F4) {
+                int r = f % BM, kq = (f / BM) * 4;
+                As[buf][kq + 0][r] = ra[i].x; As[buf][kq + 1][r] = ra[i].y;
+                As[buf][kq + 2][r] = ra[i].z; As[buf][kq + 3][r] = ra[i].w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W_PER; ++i) {
+            int f = tid + i * 256;
+            if (W_F4 >= 256 || f < W_F4) {
+                int r = f % BN, kq = (f / BN) * 4;
+                Ws[buf][kq + 0][r] = rw[i].x; Ws[buf][kq + 1][r] = rw[i].y;
+                Ws[buf][kq + 2][r] = rw[i].z; Ws[buf][kq + 3][r] = rw[i].w;
+            }
+        }
+    };
+
+    const int nkt = (p.K + BK - 1) / BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) gload((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+            if (TM % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < TM; i += 4) {
+                    float4 v = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
+                    a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) a[i] = As[buf][k][ty * TM + i];
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                float4 v = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * TN + j]);
+                b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nkt) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- epilogue -------------------------------------------------------------------------
+    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
+    // C / C2 / R may alias (in-place accumulation: R == C): plain loads, no __restrict__
+    float* C = p.C + bz * p.sC;
+    float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
+    const float* R = p.R ? p.R + bz * p.sR : nullptr;
+    const int nbase = n0 + tx * TN;
+    float bv[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = (bias && nbase + j < p.N) ? __ldg(bias + nbase + j) : 0.f;
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
+        float v[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) v[j] = fmaf(p.alpha, acc[i][j], bv[j]);
+        if (p.act == ACT_GATE) {
+#pragma unroll
+            for (int j = 0; j < TN; j += 2) {
+                const int n = nbase + j;
+                if (n + 1 < p.N) {
+                    float g = tanhf(v[j]) * sigmoid_f(v[j + 1]);
+                    const int col = n >> 1;
+                    if (R) g += R[(long long)m * p.ldr + col];
+                    if (masked) g = 0.f;
+                    C[(long long)m * p.ldc + col] = g;
+                    if (C2) C2[(long long)m * p.ldc2 + col] = masked ? 0.f : apply_act(p.act2, g);
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) v[j] = apply_act(p.act, v[j]);
+        if (p.out_mode == OUT_PLAIN) {
+            if (R) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    if (nbase + j < p.N) v[j] += R[(long long)m * p.ldr + nbase + j];
+            }
+            if (masked) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) v[j] = 0.f;
+            }
+            if (p.vec_store && nbase + TN <= p.N) {
+#pragma unroll
+                for (int j = 0; j < TN; j += 4)
+                    *reinterpret_cast<float4*>(C + (long long)m * p.ldc + nbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (C2) {
+#pragma unroll
+                    for (int j = 0; j < TN; j += 4)
+                        *reinterpret_cast<float4*>(C2 + (long long)m * p.ldc2 + nbase + j) =
+                            make_float4(masked ? 0.f : apply_act(p.act2, v[j]), masked ? 0.f : apply_act(p.act2, v[j + 1]),
+                                        masked ? 0.f : apply_act(p.act2, v[j + 2]), masked ? 0.f : apply_act(p.act2, v[j + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    if (nbase + j >= p.N) continue;
+                    C[(long long)m * p.ldc + nbase + j] = v[j];
+                    if (C2) C2[(long long)m * p.ldc2 + nbase + j] = masked ? 0.f : apply_act(p.act2, v[j]);
+                }
+            }
+        } else if (p.out_mode == OUT_PIXSHUF2) {
+            const int qt = m / p.om_a, qf = m - qt * p.om_a;
+            if (qf >= p.om_a - 2) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = nbase + j;
+                if (n >= p.N) continue;
+                const int ph = n / p.om_b, co = n - ph * p.om_b, rt = ph >> 1, rf = ph & 1;
+                const long long idx = ((long long)(2 * qt + rt) * p.om_c + (2 * qf + rf)) * p.ldc + co;
+                C[idx] = masked ? 0.f : v[j];
+            }
+        } else {  // OUT_CONVT1D
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = nbase + j;
+                if (n >= p.N) continue;
+                const int r = n / p.om_b, co = n - r * p.om_b;
+                const int o = m * p.om_a + r - p.om_c;
+                if (o < 0 || o >= p.om_d) continue;
+                C[(long long)o * p.ldc + co] = v[j];
+                if (C2) C2[(long long)o * p.ldc2 + co] = apply_act(p.act2, v[j]);
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+void launch_cfg(const GemmParams& p, int batch, bool vec, cudaStream_t s) {
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
+    if (vec) gemm_f32_kernel<BM, BN, TM, TN, true><<<grid, 256, 0, s>>>(p);
+    else gemm_f32_kernel<BM, BN, TM, TN, false><<<grid, 256, 0, s>>>(p);
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
+    GemmParams p;
+    p.A = B.p<float>(g.A); p.lda = g.lda; p.seg_len = g.seg_len; p.seg_stride = g.seg_stride;
+    p.W = B.p<float>(g.W); p.ldw = g.ldw; p.bias = B.p<float>(g.bias);
+    p.C = B.p<float>(g.C); p.ldc = g.ldc; p.C2 = B.p<float>(g.C2); p.ldc2 = g.ldc2; p.act2 = g.act2;
+    p.R = B.p<float>(g.R); p.ldr = g.ldr;
+    p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.alpha = g.alpha;
+    p.mask_period = g.mask_period; p.mask_valid = g.mask_valid;
+    p.sA = g.sA; p.sW = g.sW; p.sBias = g.sBias; p.sC = g.sC; p.sR = g.sR;
+    p.out_mode = g.out_mode; p.om_a = g.om_a; p.om_b = g.om_b; p.om_c = g.om_c; p.om_d = g.om_d;
+    const bool vec = al16(p.A) && al16(p.W) && g.lda % 4 == 0 && g.seg_len % 4 == 0 && g.seg_stride % 4 == 0 &&
+                     g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
+    p.vec_store = (g.out_mode == OUT_PLAIN && g.act != ACT_GATE && al16(p.C) && g.ldc % 4 == 0 && g.sC % 4 == 0 &&
+                   (!p.C2 || (al16(p.C2) && g.ldc2 % 4 == 0))) ? 1 : 0;
+    if (g.M >= 1024) launch_cfg<128, 64, 8, 4>(p, g.batch, vec, stream);
+    else if (g.M > 32) launch_cfg<64, 64, 4, 4>(p, g.batch, vec, stream);
+    else launch_cfg<16, 64, 1, 4>(p, g.batch, vec, stream);
+    return 1;
+}
+
+}  // namespace rvc

@@ -1,0 +1,219 @@
+// kernels_knn.cu - exact brute-force L2 retrieval (FAISS IndexFlatL2 semantics, upstream RVC;
+// the reference has only `// TODO: index search`, rvc/src/rvc.rs:159).
+//
+// HBM-bound design: the N x C index is streamed exactly once with coalesced 128-bit loads, one
+// index row per warp iteration; the Q query rows live in shared memory; per-lane partial sums of
+// squared differences for a group of up to 32 queries are reduced with a butterfly of warp
+// shuffles (31 shuffles per 32 queries) that leaves query j's distance in lane j; every lane keeps
+// the running top-k of "its" queries in registers, so no N x Q distance matrix ever touches memory.
+// Per-warp candidate lists are merged by a tiny second kernel.  Distances are fp32 sum (x-y)^2 in
+// a fixed order; ties resolve to the lowest row index.
+#include <cfloat>
+#include <climits>
+
+#include "launch.h"
+
+namespace rvc {
+
+namespace {
+
+template <int CV, int QN, int G, int KK>
+__global__ void __launch_bounds__(256)
+knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __restrict__ queries, long long ldq, int Q,
+                float* __restrict__ cand_d, int* __restrict__ cand_i, int parts, int k) {
+    extern __shared__ __align__(16) float qs[];  // [G*QN][C], zero padded
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C4 = C >> 2;
+    for (int e = tid; e < G * QN * C; e += 256) {
+        int q = e / C, c = e - q * C;
+        qs[e] = q < Q ? queries[(long long)q * ldq + c] : 0.f;
+    }
+    __syncthreads();
+    const int part = blockIdx.x * 8 + warp;
+    if (part >= parts) return;
+
+    float ld[G][KK]; int li[G][KK];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < KK; ++j) { ld[g][j] = FLT_MAX; li[g][j] = -1; }
+
+    const float4* qs4 = reinterpret_cast<const float4*>(qs);
+    for (int n = part; n < N; n += parts) {
+        const float4* row = reinterpret_cast<const float4*>(index + (long long)n * C);
+        float4 y[CV];
+#pragma unroll
+        for (int i = 0; i < CV; ++i) {
+            int c4 = lane + i * 32;
+            y[i] = c4 < C4 ? __ldg(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float v[QN];
+#pragma unroll
+            for (int qq = 0; qq < QN; ++qq) {
+                const float4* xq = qs4 + (size_t)(g * QN + qq) * C4;
+                float a = 0.f;
+#pragma unroll
+                for (int i = 0; i < CV; ++i) {
+                    int c4 = lane + i * 32;
+                    if (c4 < C4) {
+                        float4 x = xq[c4];
+                        float d0 = x.x - y[i].x, d1 = x.y - y[i].y, d2 = x.z - y[i].z, d3 = x.w - y[i].w;
+                        a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
+                    }
+                }
+                v[qq] = a;
+            }
+            // full-width steps while fewer than 32 values per lane group
+#pragma unroll
+            for (int s = 16; s >= QN; s >>= 1)
+#pragma unroll
+                for (int i = 0; i < QN; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
+            // halving butterfly: after it, lane l holds the total of query (l & (QN-1))
+#pragma unroll
+            for (int s = QN / 2; s >= 1; s >>= 1) {
+                const bool up = (lane & s) != 0;
+#pragma unroll
+                for (int i = 0; i < s; ++i) {
+                    float send = up ? v[i] : v[i + s];
+                    float keep = up ? v[i + s] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+            float cd = v[0];
+            if (cd < ld[g][KK - 1]) {
+                int ci = n;
+#pragma unroll
+                for (int j = 0; j < KK; ++j) {
+                    if (cd < ld[g][j]) {
+                        float td = ld[g][j]; int ti = li[g][j];
+                        ld[g][j] = cd; li[g][j] = ci; cd = td; ci = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (lane < QN) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int q = g * QN + lane;
+            if (q < Q) {
+#pragma unroll
+                for (int j = 0; j < KK; ++j)
+                    if (j < k) {
+                        cand_d[((long long)q * parts + part) * k + j] = ld[g][j];
+                        cand_i[((long long)q * parts + part) * k + j] = li[g][j];
+                    }
+            }
+        }
+    }
+}
+
+// merges parts*k candidates per query: k rounds of "smallest (d, idx) greater than the previous"
+__global__ void __launch_bounds__(256)
+knn_select_kernel(const float* __restrict__ cand_d, const int* __restrict__ cand_i, int* __restrict__ idx,
+                  float* __restrict__ d2, int M, int k) {
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* cd = cand_d + (long long)q * M;
+    const int* ci = cand_i + (long long)q * M;
+    __shared__ float sd[8]; __shared__ int si[8];
+    __shared__ float pd_s; __shared__ int pi_s;
+    float pd = -FLT_MAX; int pi = -1;
+    for (int r = 0; r < k; ++r) {
+        float bd = FLT_MAX; int bi = INT_MAX;
+        for (int m = tid; m < M; m += 256) {
+            float d = cd[m]; int i = ci[m];
+            if (i < 0) continue;
+            if (!(d > pd || (d == pd && i > pi))) continue;
+            if (d < bd || (d == bd && i < bi)) { bd = d; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, bd, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w) if (sd[w] < bd || (sd[w] == bd && si[w] < bi)) { bd = sd[w]; bi = si[w]; }
+            idx[q * k + r] = bi == INT_MAX ? -1 : bi; d2[q * k + r] = bd;
+            pd_s = bd; pi_s = bi;
+        }
+        __syncthreads();
+        pd = pd_s; pi = pi_s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+knn_blend_kernel(const float* __restrict__ index, const int* __restrict__ idx, const float* __restrict__ d2,
+                 const float* __restrict__ x, long long ldx, float* __restrict__ out, const RunParams* __restrict__ rp,
+                 int C, int k) {
+    const int q = blockIdx.x;
+    __shared__ float w[32]; __shared__ int id[32];
+    if (threadIdx.x == 0) {
+        float ws = 0.f;
+        for (int i = 0; i < k; ++i) { float r = 1.0f / d2[q * k + i]; w[i] = r * r; ws += w[i]; id[i] = idx[q * k + i]; }
+        for (int i = 0; i < k; ++i) w[i] /= ws;
+    }
+    __syncthreads();
+    const float rate = rp->index_rate;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int i = 0; i < k; ++i) a = fmaf(w[i], __ldg(index + (long long)id[i] * C + c), a);
+        out[(long long)q * C + c] = rate * a + (1.0f - rate) * x[(long long)q * ldx + c];
+    }
+}
+
+template <int CV, int QN, int G, int KK>
+void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaStream_t s) {
+    auto kern = knn_scan_kernel<CV, QN, G, KK>;
+    size_t smem = sizeof(float) * size_t(G) * QN * o.C;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    kern<<<(o.parts + 7) / 8, 256, smem, s>>>(B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
+                                              B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k,
+                                              B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
+}
+
+template <int CV, int KK>
+int scan_dispatch_q(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
+    const int maxq = (KK > 8 || o.C > 384) ? 32 : 128;  // per launch: register (top-k lists) and smem (queries) budget
+    int launches = 0;
+    for (int q0 = 0; q0 < o.Q; q0 += maxq) {
+        int nq = o.Q - q0 < maxq ? o.Q - q0 : maxq;
+        if (nq <= 8) scan_launch<CV, 8, 1, KK>(o, B, q0, nq, s);
+        else if (nq <= 16) scan_launch<CV, 16, 1, KK>(o, B, q0, nq, s);
+        else if (nq <= 32) scan_launch<CV, 32, 1, KK>(o, B, q0, nq, s);
+        else scan_launch<CV, 32, 4, 8>(o, B, q0, nq, s);
+        ++launches;
+    }
+    return launches;
+}
+
+}  // namespace
+
+int launch_knn_scan(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
+    // C must be a multiple of 4 and <= 1024; k <= 16 (validated when the index is set)
+    if (o.k <= 8) {
+        if (o.C <= 256) return scan_dispatch_q<2, 8>(o, B, s);
+        if (o.C <= 768) return scan_dispatch_q<6, 8>(o, B, s);
+        return scan_dispatch_q<8, 8>(o, B, s);
+    }
+    if (o.C <= 256) return scan_dispatch_q<2, 16>(o, B, s);
+    if (o.C <= 768) return scan_dispatch_q<6, 16>(o, B, s);
+    return scan_dispatch_q<8, 16>(o, B, s);
+}
+
+int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t s) {
+    knn_select_kernel<<<o.Q, 256, 0, s>>>(B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx), B.p<float>(o.d2), o.parts * o.k, o.k);
+    return 1;
+}
+
+int launch_knn_blend(const KnnBlendOp& o, const DeviceBases& B, cudaStream_t s) {
+    knn_blend_kernel<<<o.Q, 256, 0, s>>>(B.p<float>(o.index), B.p<int>(o.idx), B.p<float>(o.d2), B.p<float>(o.x), o.ldx, B.p<float>(o.out),
+                                         B.p<RunParams>(o.params), o.C, o.k);
+    return 1;
+}
+
+}  // namespace rvc

@@ -1,0 +1,482 @@
+// kernels_misc.cu - the non-GEMM device ops of the plan (normalisation, attention, GRU, glue).
+// All arithmetic is fp32 with the same formulas as the reference path's oracle; reductions use
+// warp shuffles; every kernel is latency-sized for one audio window.
+#include <cfloat>
+
+#include "launch.h"
+#include "noise.h"
+
+namespace rvc {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (cols <= 32*MAXV)
+// ------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 32;  // up to 1024 columns
+
+__global__ void layernorm_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int cols,
+                                 float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* x = X + (long long)warp * ldx;
+    float v[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        int c = lane + i * 32;
+        v[i] = c < cols ? x[c] : 0.f;
+        s += v[i];
+    }
+    const float mean = warp_sum(s) / float(cols);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        int c = lane + i * 32;
+        float d = c < cols ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / float(cols) + eps);
+    float* y = Y + (long long)warp * ldy;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        int c = lane + i * 32;
+        if (c < cols) y[c] = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-head attention, one CTA per (head, 16-query block); K (padded rows) and V in smem
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_QB = 16, ATT_WARPS = 8;
+
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo, int T, int heads, int dim) {
+    extern __shared__ float sm[];
+    const int h = blockIdx.x, q0 = blockIdx.y * ATT_QB;
+    const int HD = heads * dim, dk = dim + 1;
+    float* Ks = sm;                       // [T][dim+1]
+    float* Vs = Ks + (size_t)T * dk;      // [T][dim]
+    float* Qs = Vs + (size_t)T * dim;     // [ATT_WARPS][dim]
+    float* Ps = Qs + ATT_WARPS * dim;     // [ATT_WARPS][T]
+    for (int i = threadIdx.x; i < T * dim; i += blockDim.x) {
+        int t = i / dim, d = i - t * dim;
+        Ks[t * dk + d] = qkv[(long long)t * ld + HD + h * dim + d];
+        Vs[t * dim + d] = qkv[(long long)t * ld + 2 * HD + h * dim + d];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* qs = Qs + warp * dim;
+    float* ps = Ps + warp * T;
+    for (int qi = q0 + warp; qi < min(q0 + ATT_QB, T); qi += ATT_WARPS) {
+        for (int d = lane; d < dim; d += 32) qs[d] = qkv[(long long)qi * ld + h * dim + d];
+        __syncwarp();
+        float mx = -FLT_MAX;
+        for (int j = lane; j < T; j += 32) {
+            float a = 0.f;
+            for (int d = 0; d < dim; ++d) a = fmaf(qs[d], Ks[j * dk + d], a);
+            ps[j] = a;
+            mx = fmaxf(mx, a);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) { float e = expf(ps[j] - mx); ps[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        __syncwarp();
+        const float inv = 1.0f / sum;
+        for (int d = lane; d < dim; d += 32) {
+            float a = 0.f;
+            for (int j = 0; j < T; ++j) a = fmaf(ps[j], Vs[j * dim + d], a);
+            out[(long long)qi * ldo + h * dim + d] = a * inv;
+        }
+        __syncwarp();
+    }
+}
+
+// VITS windowed relative-position attention (enc_p): T <= ~64, one CTA per head
+__global__ void __launch_bounds__(256)
+relattn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo,
+               const float* __restrict__ rel_k, const float* __restrict__ rel_v, int T, int heads, int dim, int window) {
+    extern __shared__ float sm[];
+    const int h = blockIdx.x, HD = heads * dim, dk = dim + 1, nrel = 2 * window + 1;
+    float* Qs = sm;                          // [T][dim+1]
+    float* Ks = Qs + (size_t)T * dk;         // [T][dim+1]
+    float* Vs = Ks + (size_t)T * dk;         // [T][dim]
+    float* Rk = Vs + (size_t)T * dim;        // [nrel][dim+1]
+    float* Rv = Rk + (size_t)nrel * dk;      // [nrel][dim]
+    float* Ps = Rv + (size_t)nrel * dim;     // [T][T]
+    for (int i = threadIdx.x; i < T * dim; i += blockDim.x) {
+        int t = i / dim, d = i - t * dim;
+        Qs[t * dk + d] = qkv[(long long)t * ld + h * dim + d];
+        Ks[t * dk + d] = qkv[(long long)t * ld + HD + h * dim + d];
+        Vs[t * dim + d] = qkv[(long long)t * ld + 2 * HD + h * dim + d];
+    }
+    for (int i = threadIdx.x; i < nrel * dim; i += blockDim.x) {
+        int r = i / dim, d = i - r * dim;
+        Rk[r * dk + d] = rel_k[i];
+        Rv[r * dim + d] = rel_v[i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
+        int i = e / T, j = e - i * T;
+        float a = 0.f;
+        for (int d = 0; d < dim; ++d) a = fmaf(Qs[i * dk + d], Ks[j * dk + d], a);
+        int rel = j - i + window;
+        if (rel >= 0 && rel < nrel)
+            for (int d = 0; d < dim; ++d) a = fmaf(Qs[i * dk + d], Rk[rel * dk + d], a);
+        Ps[e] = a;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = warp; i < T; i += nw) {
+        float mx = -FLT_MAX;
+        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, Ps[i * T + j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) { float ev = expf(Ps[i * T + j] - mx); Ps[i * T + j] = ev; sum += ev; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < T; j += 32) Ps[i * T + j] *= inv;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < T * dim; e += blockDim.x) {
+        int i = e / dim, d = e - i * dim;
+        float a = 0.f;
+        for (int j = 0; j < T; ++j) {
+            float pv = Ps[i * T + j];
+            a = fmaf(pv, Vs[j * dim + d], a);
+            int rel = j - i + window;
+            if (rel >= 0 && rel < nrel) a = fmaf(pv, Rv[rel * dim + d], a);
+        }
+        out[(long long)i * ldo + h * dim + d] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ContentVec conv0 (1 -> 512, k=10, stride 5) + GroupNorm(512 groups) + GELU
+// ------------------------------------------------------------------------------------------
+constexpr int C0_CH = 4;  // channels per CTA in the stats pass
+
+__global__ void __launch_bounds__(256)
+conv0_stats_kernel(const float* __restrict__ pcm, const float* __restrict__ w, float* __restrict__ stats, int T, int C,
+                   int k, int stride, float eps) {
+    const int c0 = blockIdx.x * C0_CH;
+    float wr[C0_CH][10];
+#pragma unroll
+    for (int c = 0; c < C0_CH; ++c)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wr[c][j] = (j < k && c0 + c < C) ? w[(c0 + c) * k + j] : 0.f;
+    double s[C0_CH], ss[C0_CH];
+#pragma unroll
+    for (int c = 0; c < C0_CH; ++c) { s[c] = 0.0; ss[c] = 0.0; }
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        float x[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) x[j] = j < k ? __ldg(pcm + t * stride + j) : 0.f;
+#pragma unroll
+        for (int c = 0; c < C0_CH; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) a = fmaf(x[j], wr[c][j], a);
+            s[c] += double(a);
+            ss[c] += double(a) * double(a);
+        }
+    }
+    __shared__ double red[8][C0_CH][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < C0_CH; ++c) {
+        double a = warp_sum_d(s[c]), b = warp_sum_d(ss[c]);
+        if (lane == 0) { red[warp][c][0] = a; red[warp][c][1] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < C0_CH && c0 + threadIdx.x < C) {
+        double a = 0, b = 0;
+        for (int i = 0; i < 8; ++i) { a += red[i][threadIdx.x][0]; b += red[i][threadIdx.x][1]; }
+        double mean = a / T, var = b / T - mean * mean;
+        stats[2 * (c0 + threadIdx.x)] = float(mean);
+        stats[2 * (c0 + threadIdx.x) + 1] = float(1.0 / sqrt(var + double(eps)));
+    }
+}
+
+constexpr int C0_TB = 16;  // time steps per CTA in the apply pass
+
+__global__ void __launch_bounds__(256)
+conv0_apply_kernel(const float* __restrict__ pcm, const float* __restrict__ w, const float* __restrict__ stats,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, int T, int C,
+                   int k, int stride) {
+    __shared__ float xs[C0_TB * 5 + 16];
+    const int t0 = blockIdx.x * C0_TB;
+    const int nx = (min(C0_TB, T - t0) - 1) * stride + k;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = pcm[t0 * stride + i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float wr[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) wr[j] = j < k ? w[c * k + j] : 0.f;
+        const float mean = stats[2 * c], rstd = stats[2 * c + 1], g = gamma[c], b = beta[c];
+        for (int tt = 0; tt < C0_TB && t0 + tt < T; ++tt) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) a = fmaf(xs[tt * stride + j], wr[j], a);
+            Y[(long long)(t0 + tt) * C + c] = gelu_f((a - mean) * rstd * g + b);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2x2 average pool on halo-padded NHWC
+// ------------------------------------------------------------------------------------------
+__global__ void avgpool_kernel(const float* __restrict__ in, long long ldin, float* __restrict__ out, int T, int F, int C) {
+    const int To = T / 2, Fo = F / 2;
+    const long long n = (long long)To * Fo * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        int c = int(e % C);
+        long long r = e / C;
+        int f = int(r % Fo), t = int(r / Fo);
+        const float* p = in + ((long long)(2 * t + 1) * (F + 2) + 2 * f + 1) * ldin + c;
+        float v = (p[0] + p[ldin] + p[(long long)(F + 2) * ldin] + p[(long long)(F + 3) * ldin]) * 0.25f;
+        out[((long long)(t + 1) * (Fo + 2) + f + 1) * C + c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bidirectional GRU (H=256): one CTA per direction, thread g owns gate row g of W_hh
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(768)
+gru_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t, const float* __restrict__ bhh,
+           float* __restrict__ out, int T, int H) {
+    extern __shared__ float sm[];
+    float* hs = sm;          // [H]
+    float* gh = hs + H;      // [3H]
+    const int d = blockIdx.x, g = threadIdx.x, G = 3 * H;
+    const float* wt = whh_t + (long long)d * H * G;
+    const float bg = g < G ? bhh[d * G + g] : 0.f;
+    if (g < H) hs[g] = 0.f;
+    __syncthreads();
+    for (int s = 0; s < T; ++s) {
+        const int t = d == 0 ? s : T - 1 - s;
+        if (g < G) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < H; k += 4) {
+                a0 = fmaf(__ldg(wt + (long long)(k + 0) * G + g), hs[k + 0], a0);
+                a1 = fmaf(__ldg(wt + (long long)(k + 1) * G + g), hs[k + 1], a1);
+                a2 = fmaf(__ldg(wt + (long long)(k + 2) * G + g), hs[k + 2], a2);
+                a3 = fmaf(__ldg(wt + (long long)(k + 3) * G + g), hs[k + 3], a3);
+            }
+            gh[g] = bg + ((a0 + a1) + (a2 + a3));
+        }
+        __syncthreads();
+        float hn = 0.f;
+        if (g < H) {
+            const float* x = gi + (long long)t * 2 * G + d * G;
+            float r = sigmoid_f(x[g] + gh[g]);
+            float z = sigmoid_f(x[H + g] + gh[H + g]);
+            float n = tanhf(x[2 * H + g] + r * gh[2 * H + g]);
+            hn = (1.0f - z) * n + z * hs[g];
+            out[(long long)t * 2 * H + d * H + g] = hn;
+        }
+        __syncthreads();
+        if (g < H) hs[g] = hn;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_p embedding: lrelu_0.1((phone Wp^T + bp + emb_pitch[pitch]) * sqrt(H)); CTA per row
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_kernel(const float* __restrict__ phone, const int* __restrict__ pitch, const float* __restrict__ wp,
+             const float* __restrict__ bp, const float* __restrict__ emb_pitch, float* __restrict__ out, long long ldo,
+             int Cin, int H) {
+    extern __shared__ float xs[];
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < Cin; i += blockDim.x) xs[i] = phone[(long long)r * Cin + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int pi = pitch[r];
+    const float sc = sqrtf(float(H));
+    for (int h = warp; h < H; h += nw) {
+        const float* wr = wp + (long long)h * Cin;
+        float a = 0.f;
+        for (int k = lane; k < Cin; k += 32) a = fmaf(xs[k], __ldg(wr + k), a);
+        a = warp_sum(a);
+        if (lane == 0) {
+            float v = (a + bp[h] + emb_pitch[pi * H + h]) * sc;
+            out[(long long)r * ldo + h] = v > 0.f ? v : 0.1f * v;
+        }
+    }
+}
+
+__global__ void zp_kernel(const float* __restrict__ stats, float* __restrict__ out, long long ldo,
+                          const RunParams* __restrict__ rp, int R, int H) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= R * H) return;
+    const int r = e / H, c = e - r * H;
+    const float m = stats[(long long)r * 2 * H + c], lg = stats[(long long)r * 2 * H + H + c];
+    float nz = 0.f;
+    if (rp->noise_mode) nz = noise_gauss(noise_key(rp->noise_seed, rp->window, NOISE_KIND_Z), (uint64_t)e);
+    out[(long long)r * ldo + c] = m + expf(lg) * nz * 0.66666f;
+}
+
+__global__ void avg3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                            long long ld, float* __restrict__ out, long long ldo, float* __restrict__ raw, long long ldraw,
+                            int T, int C, float slope) {
+    const long long n = (long long)T * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        int ch = int(e % C);
+        long long t = e / C;
+        long long i = t * ld + ch;
+        float s = (a[i] + b[i] + c[i]) / 3.0f;
+        if (raw) raw[t * ldraw + ch] = s;
+        out[t * ldo + ch] = s > 0.f ? s : slope * s;
+    }
+}
+
+// conv_post: tanh(conv1d(C -> 1, k)); thread per output sample, weights in smem
+__global__ void __launch_bounds__(256)
+convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, int T, int C, int k) {
+    extern __shared__ float ws[];
+    const int n = k * C;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float4* p = reinterpret_cast<const float4*>(in + (long long)t * C);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = 0; j < n / 4; ++j) {
+        float4 v = __ldg(p + j);
+        a0 = fmaf(v.x, ws[4 * j + 0], a0); a1 = fmaf(v.y, ws[4 * j + 1], a1);
+        a2 = fmaf(v.z, ws[4 * j + 2], a2); a3 = fmaf(v.w, ws[4 * j + 3], a3);
+    }
+    out[t] = tanhf((a0 + a1) + (a2 + a3));
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ out, int T, int C,
+                                   int skip, int R, int row0) {
+    const long long n = (long long)R * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        int c = int(e % C), r = int(e / C);
+        int s = min((skip + r) / 2, T - 1) - row0;
+        out[e] = src[(long long)s * lds + c];
+    }
+}
+
+inline int grid_for(long long n, int block, int cap = 148 * 8) {
+    long long g = (n + block - 1) / block;
+    return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+size_t attn_smem(int T, int dim) { return sizeof(float) * (size_t(T) * (dim + 1) + size_t(T) * dim + ATT_WARPS * dim + size_t(ATT_WARPS) * T); }
+size_t relattn_smem(int T, int dim, int window) {
+    int nrel = 2 * window + 1;
+    return sizeof(float) * (2 * size_t(T) * (dim + 1) + size_t(T) * dim + size_t(nrel) * (dim + 1) + size_t(nrel) * dim + size_t(T) * T);
+}
+
+}  // namespace
+
+void init_kernel_attributes() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(relattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t s) {
+    const int wpb = 4;
+    layernorm_kernel<<<(o.rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(B.p<float>(o.X), o.ldx, B.p<float>(o.Y), o.ldy,
+                                                                  B.p<float>(o.gamma), B.p<float>(o.beta), o.rows, o.cols, o.eps);
+    return 1;
+}
+
+int launch_attn(const AttnOp& o, const DeviceBases& B, cudaStream_t s) {
+    dim3 grid(o.heads, (o.T + ATT_QB - 1) / ATT_QB);
+    attn_kernel<<<grid, ATT_WARPS * 32, attn_smem(o.T, o.dim), s>>>(B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T,
+                                                                    o.heads, o.dim);
+    return 1;
+}
+
+int launch_relattn(const RelAttnOp& o, const DeviceBases& B, cudaStream_t s) {
+    relattn_kernel<<<o.heads, 256, relattn_smem(o.T, o.dim, o.window), s>>>(B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
+                                                                            B.p<float>(o.rel_k), B.p<float>(o.rel_v), o.T, o.heads,
+                                                                            o.dim, o.window);
+    return 1;
+}
+
+int launch_conv0_stats(const Conv0StatsOp& o, const DeviceBases& B, cudaStream_t s) {
+    conv0_stats_kernel<<<(o.C + C0_CH - 1) / C0_CH, 256, 0, s>>>(B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats), o.T, o.C,
+                                                                 o.k, o.stride, o.eps);
+    return 1;
+}
+
+int launch_conv0_apply(const Conv0ApplyOp& o, const DeviceBases& B, cudaStream_t s) {
+    conv0_apply_kernel<<<(o.T + C0_TB - 1) / C0_TB, 256, 0, s>>>(B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats),
+                                                                 B.p<float>(o.gamma), B.p<float>(o.beta), B.p<float>(o.Y), o.T, o.C,
+                                                                 o.k, o.stride);
+    return 1;
+}
+
+int launch_avgpool(const AvgPoolOp& o, const DeviceBases& B, cudaStream_t s) {
+    long long n = (long long)(o.T / 2) * (o.F / 2) * o.C;
+    avgpool_kernel<<<grid_for(n, 256), 256, 0, s>>>(B.p<float>(o.in), o.ldin, B.p<float>(o.out), o.T, o.F, o.C);
+    return 1;
+}
+
+int launch_gru(const GruOp& o, const DeviceBases& B, cudaStream_t s) {
+    gru_kernel<<<2, 768, sizeof(float) * 4 * o.H, s>>>(B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out),
+                                                       o.T, o.H);
+    return 1;
+}
+
+int launch_embed(const EmbedOp& o, const DeviceBases& B, cudaStream_t s) {
+    embed_kernel<<<o.R, 256, sizeof(float) * o.Cin, s>>>(B.p<float>(o.phone), B.p<int>(o.pitch), B.p<float>(o.wp), B.p<float>(o.bp),
+                                                         B.p<float>(o.emb_pitch), B.p<float>(o.out), o.ldo, o.Cin, o.H);
+    return 1;
+}
+
+int launch_zp(const ZpOp& o, const DeviceBases& B, cudaStream_t s) {
+    zp_kernel<<<(o.R * o.H + 255) / 256, 256, 0, s>>>(B.p<float>(o.stats), B.p<float>(o.out), o.ldo, B.p<RunParams>(o.params), o.R, o.H);
+    return 1;
+}
+
+int launch_avg3(const Avg3Op& o, const DeviceBases& B, cudaStream_t s) {
+    avg3_kernel<<<grid_for((long long)o.T * o.C, 256), 256, 0, s>>>(B.p<float>(o.a), B.p<float>(o.b), B.p<float>(o.c), o.ld,
+                                                                    B.p<float>(o.out), o.ldo, B.p<float>(o.raw), o.ldraw, o.T, o.C,
+                                                                    o.slope);
+    return 1;
+}
+
+int launch_convpost(const ConvPostOp& o, const DeviceBases& B, cudaStream_t s) {
+    convpost_kernel<<<(o.T + 255) / 256, 256, sizeof(float) * o.k * o.C, s>>>(B.p<float>(o.in), B.p<float>(o.w), B.p<float>(o.out), o.T,
+                                                                              o.C, o.k);
+    return 1;
+}
+
+int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t s) {
+    gather_rows_kernel<<<grid_for((long long)o.R * o.C, 256), 256, 0, s>>>(B.p<float>(o.src), o.lds, B.p<float>(o.out), o.T, o.C,
+                                                                          o.skip, o.R, o.row0);
+    return 1;
+}
+
+}  // namespace rvc

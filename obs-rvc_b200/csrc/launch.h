@@ -1,0 +1,44 @@
+// launch.h - device launchers for the op descriptors of ops.h (implemented in kernels_*.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ops.h"
+
+namespace rvc {
+
+struct DeviceBases {
+    uint8_t* b[SP_COUNT] = {nullptr};
+    template <typename T> T* p(const Ref& r) const {
+        return r.null() ? nullptr : reinterpret_cast<T*>(b[r.space] + r.off);
+    }
+};
+
+// Each launcher enqueues exactly the kernels of one op on `stream` and returns how many kernels
+// it launched (0 for memset-only ops).  Errors are reported through cudaGetLastError by the caller.
+int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);
+int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_attn(const AttnOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_relattn(const RelAttnOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_conv0_stats(const Conv0StatsOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_conv0_apply(const Conv0ApplyOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_stftmel(const StftMelOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_avgpool(const AvgPoolOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_gru(const GruOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_f0decode(const F0DecodeOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_f0post(const F0PostOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_embed(const EmbedOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_zp(const ZpOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_sinegen(const SineGenOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_avg3(const Avg3Op& o, const DeviceBases& B, cudaStream_t stream);
+int launch_convpost(const ConvPostOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_knn_scan(const KnnScanOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_knn_blend(const KnnBlendOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t stream);
+
+// one-time per-process kernel attribute setup (dynamic shared memory opt-in)
+void init_kernel_attributes();
+
+}  // namespace rvc

@@ -130,11 +130,12 @@ struct ConvPostOp {  // tanh(conv1d(Cin->1, k)) on halo-padded channels-last inp
     Ref in; Ref w; Ref out; int32_t T = 0, C = 0, k = 0;
 };
 
-struct KnnDistOp {  // D[q,n] = sum_c (x[q,c]-index[n,c])^2 (fp32, fixed order)
-    Ref index; Ref queries; int64_t ldq = 0; Ref D; int32_t N = 0, C = 0, Q = 0;
+struct KnnScanOp {  // per-part top-k of D[q,n] = sum_c (x[q,c]-index[n,c])^2; part p owns rows p, p+parts, ...
+    Ref index; Ref queries; int64_t ldq = 0; Ref cand_d, cand_i;  // [Q][parts][k]
+    int32_t N = 0, C = 0, Q = 0, k = 0, parts = 0;
 };
-struct KnnSelectOp {  // k smallest per query, ascending, ties -> lowest row index
-    Ref D; Ref idx; Ref d2; int32_t N = 0, Q = 0, k = 0;
+struct KnnSelectOp {  // k smallest (d, idx) per query over parts*k candidates, ascending
+    Ref cand_d, cand_i; Ref idx; Ref d2; int32_t Q = 0, k = 0, parts = 0;
 };
 struct KnnBlendOp {  // out[Q,C] = rate * sum_i w_i index[idx_i] + (1-rate) x ; w = (1/d2)^2 normalised
     Ref index; Ref idx; Ref d2; Ref x; int64_t ldx = 0; Ref out; Ref params; int32_t C = 0, Q = 0, k = 0;
@@ -150,7 +151,7 @@ struct WaitOp { int32_t src_lane = 0, dst_lane = 0; };
 enum OpKind : int32_t {
     OP_GEMM, OP_LAYERNORM, OP_ATTN, OP_RELATTN, OP_CONV0_STATS, OP_CONV0_APPLY, OP_STFTMEL,
     OP_AVGPOOL, OP_GRU, OP_F0DECODE, OP_F0POST, OP_EMBED, OP_ZP, OP_SINEGEN, OP_AVG3,
-    OP_CONVPOST, OP_KNN_DIST, OP_KNN_SELECT, OP_KNN_BLEND, OP_GATHER_ROWS, OP_FILL, OP_WAIT
+    OP_CONVPOST, OP_KNN_SCAN, OP_KNN_SELECT, OP_KNN_BLEND, OP_GATHER_ROWS, OP_FILL, OP_WAIT
 };
 
 struct Op {
@@ -160,7 +161,7 @@ struct Op {
     // exactly one of these is meaningful, selected by `kind`
     GemmOp gemm; LayerNormOp ln; AttnOp attn; RelAttnOp relattn; Conv0StatsOp c0s; Conv0ApplyOp c0a;
     StftMelOp stft; AvgPoolOp pool; GruOp gru; F0DecodeOp f0d; F0PostOp f0p; EmbedOp embed; ZpOp zp;
-    SineGenOp sine; Avg3Op avg3; ConvPostOp cpost; KnnDistOp kd; KnnSelectOp ks; KnnBlendOp kb;
+    SineGenOp sine; Avg3Op avg3; ConvPostOp cpost; KnnScanOp kd; KnnSelectOp ks; KnnBlendOp kb;
     GatherRowsOp gather; FillOp fill; WaitOp wait;
 };
 
@@ -177,6 +178,7 @@ struct RunParams {
 
 static const int NOISE_KIND_Z = 1;
 static const int NOISE_KIND_SINE = 2;
+static const int KNN_PARTS = 148 * 8;  // one part per resident warp of the scan kernel
 
 // A named buffer of the plan (debug / result lookups).
 struct NamedBuf { std::string name; Ref ref; int64_t elems = 0; int32_t is_int = 0; };

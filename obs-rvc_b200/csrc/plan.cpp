@@ -6,6 +6,7 @@
 //   * halo rows/pixels are zeroed once when the work arena is created and every op preserves
 //     them (masked epilogues), so "same" padding costs nothing at run time;
 //   * every convolution is the implicit GEMM of ops.h over overlapping / segmented rows.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 
@@ -483,13 +484,15 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     if (kind == PLAN_KNN) {
         // queries staged in the audio buffer region by the caller: [Q, C]; results -> work
         const int Q = g.n16k, C = g.sf16k, k = g.return_length, Nrows = opt.index_rows;
-        if (Q <= 0 || C <= 0 || k <= 0 || k > 32 || Nrows < k) { err = "bad kNN shape"; return false; }
-        Ref D = b.alloc("knn_D", int64_t(Q) * Nrows);
+        if (Q <= 0 || C <= 0 || C % 4 != 0 || C > 1024 || k <= 0 || k > 16 || Nrows < k) { err = "bad kNN shape"; return false; }
+        const int parts = std::min(KNN_PARTS, Nrows);
+        Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
-        Op& a = b.add(OP_KNN_DIST, "knn_dist");
-        a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = plan.audio; a.kd.ldq = C; a.kd.D = D; a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q;
+        Op& a = b.add(OP_KNN_SCAN, "knn_scan");
+        a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = plan.audio; a.kd.ldq = C; a.kd.cand_d = cd; a.kd.cand_i = ci;
+        a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q; a.kd.k = k; a.kd.parts = parts;
         Op& s = b.add(OP_KNN_SELECT, "knn_select");
-        s.ks.D = D; s.ks.idx = idx; s.ks.d2 = d2; s.ks.N = Nrows; s.ks.Q = Q; s.ks.k = k;
+        s.ks.cand_d = cd; s.ks.cand_i = ci; s.ks.idx = idx; s.ks.d2 = d2; s.ks.Q = Q; s.ks.k = k; s.ks.parts = parts;
         plan.knn_q = Q;
         plan.work_bytes = b.work + 256;
         return b.ok;
@@ -554,15 +557,16 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     Ref src = x; int row0 = 0;
     if (opt.with_index) {
         const int k = opt.index_k, Nrows = opt.index_rows;
-        if (k <= 0 || k > 32 || Nrows < k) { err = "bad index / k"; return false; }
-        Ref D = b.alloc("knn_D", int64_t(Q) * Nrows);
+        if (k <= 0 || k > 16 || Nrows < k || C % 4 != 0 || C > 1024) { err = "bad index / k"; return false; }
+        const int parts = std::min(KNN_PARTS, Nrows);
+        Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
         Ref xb = b.alloc("knn_blend", int64_t(Q) * C);
-        Op& a = b.add(OP_KNN_DIST, "knn_dist");
-        a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = x.plus(int64_t(first) * C); a.kd.ldq = C; a.kd.D = D;
-        a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q;
+        Op& a = b.add(OP_KNN_SCAN, "knn_scan");
+        a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = x.plus(int64_t(first) * C); a.kd.ldq = C; a.kd.cand_d = cd;
+        a.kd.cand_i = ci; a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q; a.kd.k = k; a.kd.parts = parts;
         Op& s = b.add(OP_KNN_SELECT, "knn_select");
-        s.ks.D = D; s.ks.idx = idx; s.ks.d2 = d2; s.ks.N = Nrows; s.ks.Q = Q; s.ks.k = k;
+        s.ks.cand_d = cd; s.ks.cand_i = ci; s.ks.idx = idx; s.ks.d2 = d2; s.ks.Q = Q; s.ks.k = k; s.ks.parts = parts;
         Op& m = b.add(OP_KNN_BLEND, "knn_blend");
         m.kb.index = Ref{SP_IDX, 0}; m.kb.idx = idx; m.kb.d2 = d2; m.kb.x = x.plus(int64_t(first) * C); m.kb.ldx = C;
         m.kb.out = xb; m.kb.params = plan.params; m.kb.C = C; m.kb.Q = Q; m.kb.k = k;

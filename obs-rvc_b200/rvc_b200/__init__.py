@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's `rvc` crate public API over the C ABI.
+
+`RvcInfer` keeps the method set, argument meaning and error behaviour of `rvc::RvcInfer`
+(/root/reference/rvc/src/rvc.rs:18-220; exported by rvc/src/lib.rs:5) and of the adapter the
+OBS plugin calls (obs-rvc/src/rvcadapter.rs:33-67), but every call goes straight into
+`librvc_b200.so` (include/rvc_b200.h) - hand-written sm_100a CUDA, no ONNX Runtime, no PyTorch,
+no CPU fallback.  If the shared library or a CUDA device is missing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int32, c_size_t, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "librvc_b200.so")
+
+# rvc-common/src/enums.rs:3-28,32-39,97-103
+MODEL_V1, MODEL_V2 = 1, 2
+PITCH_RMVPE = 1
+
+
+class RvcInferError(Exception):
+    """rvc-common/src/errors.rs:1-20."""
+    code = -1
+
+
+class ModelNotLoaded(RvcInferError):
+    code = 1
+
+
+class ContentvecNotLoaded(RvcInferError):
+    code = 2
+
+
+class F0NotLoaded(RvcInferError):
+    code = 3
+
+
+class CudaError(RvcInferError):       # replaces RvcInferError::Ort
+    code = 4
+
+
+class BadShape(RvcInferError):        # RvcInferError::NdarrayShapeError / reference panics
+    code = 5
+
+
+class IoError(RvcInferError):
+    code = 6
+
+
+class InvalidArg(RvcInferError):
+    code = 7
+
+
+_ERRORS = {c.code: c for c in (ModelNotLoaded, ContentvecNotLoaded, F0NotLoaded, CudaError,
+                               BadShape, IoError, InvalidArg)}
+
+
+class Config(ctypes.Structure):
+    """`rvc_config` (include/rvc_b200.h)."""
+    _fields_ = [("device", c_int32), ("noise_mode", c_int32), ("noise_seed", c_uint64),
+                ("index_k", c_int32), ("upstream_pitch_shift", c_int32),
+                ("upstream_cents_window", c_int32), ("use_cuda_graph", c_int32),
+                ("debug_keep", c_int32), ("reserved", c_int32 * 7)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads librvc_b200.so; fails loudly when it has not been built (no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` (the engine has no CPU/PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.rvc_version.restype = c_char_p
+        L.rvc_last_error.restype = c_char_p
+        L.rvc_last_error.argtypes = [c_void_p]
+        L.rvc_last_create_error.restype = c_char_p
+        L.rvc_cuda_stream.restype = c_void_p
+        L.rvc_cuda_stream.argtypes = [c_void_p]
+        L.rvc_destroy.argtypes = [c_void_p]
+        L.rvc_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class RvcInfer:
+    """Drop-in for `rvc::RvcInfer`."""
+
+    def __init__(self, data_path: str, device: int = 0, noise_seed: int = 0, noise_mode: int = 1,
+                 index_k: int = 8, upstream_pitch_shift: bool = False,
+                 upstream_cents_window: bool = False, use_cuda_graph: bool = True):
+        """RvcInfer::new(data_path) - rvc.rs:30-44."""
+        L = lib()
+        cfg = Config()
+        L.rvc_config_default(byref(cfg))
+        cfg.device, cfg.noise_seed, cfg.noise_mode, cfg.index_k = device, noise_seed, noise_mode, index_k
+        cfg.upstream_pitch_shift = int(upstream_pitch_shift)
+        cfg.upstream_cents_window = int(upstream_cents_window)
+        cfg.use_cuda_graph = int(use_cuda_graph)
+        self._h = c_void_p()
+        rc = L.rvc_create(str(data_path).encode(), byref(cfg), byref(self._h))
+        if rc != 0:
+            raise _ERRORS.get(rc, RvcInferError)(L.rvc_last_create_error().decode())
+        self._L = L
+
+    # ------------------------------------------------------------------ plumbing
+    def _chk(self, rc):
+        if rc != 0:
+            raise _ERRORS.get(rc, RvcInferError)(self._L.rvc_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rvc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ------------------------------------------------------------------ loading
+    def load_contentvec(self, model_version: int = MODEL_V2):
+        """rvc.rs:46-54."""
+        self._chk(self._L.rvc_load_contentvec(self._h, c_int32(model_version)))
+
+    def load_f0(self, pitch_algorithm: int = PITCH_RMVPE):
+        """rvc.rs:62-75."""
+        self._chk(self._L.rvc_load_f0(self._h, c_int32(pitch_algorithm)))
+
+    def load_model(self, model_path: str):
+        """rvc.rs:56-60."""
+        self._chk(self._L.rvc_load_model(self._h, str(model_path).encode()))
+
+    def unload_model(self):
+        """rvc.rs:77-79."""
+        self._chk(self._L.rvc_unload_model(self._h))
+
+    def load_index(self, index_path: str, index_rate: float):
+        self._chk(self._L.rvc_load_index(self._h, str(index_path).encode(), c_float(index_rate)))
+
+    def set_index(self, rows, index_rate: float):
+        if rows is None:
+            self._chk(self._L.rvc_set_index(self._h, None, c_size_t(0), c_size_t(0), c_float(index_rate)))
+            return
+        rows = _f32(rows)
+        self._chk(self._L.rvc_set_index(self._h, rows.ctypes.data_as(c_void_p), c_size_t(rows.shape[0]),
+                                        c_size_t(rows.shape[1]), c_float(index_rate)))
+
+    def set_index_rate(self, index_rate: float):
+        self._chk(self._L.rvc_set_index_rate(self._h, c_float(index_rate)))
+
+    # ------------------------------------------------------------------ inference
+    def hubert(self, pcm) -> np.ndarray:
+        """rvc.rs:81-97 -> (1, C, T)."""
+        pcm = _f32(pcm)
+        cap = 1024 * (pcm.shape[0] // 320 + 2)
+        out = np.empty(cap, np.float32)
+        c, t = c_size_t(), c_size_t()
+        self._chk(self._L.rvc_hubert(self._h, pcm.ctypes.data_as(c_void_p), c_size_t(pcm.shape[0]),
+                                     out.ctypes.data_as(c_void_p), c_size_t(cap), byref(c), byref(t)))
+        return out[:c.value * t.value].reshape(1, c.value, t.value).copy()
+
+    def extract_feature(self, pcm) -> np.ndarray:
+        """rvc.rs:99-109 -> (1, 2T+1, C)."""
+        pcm = _f32(pcm)
+        cap = 1024 * (2 * (pcm.shape[0] // 320 + 2) + 1)
+        out = np.empty(cap, np.float32)
+        fr, c = c_size_t(), c_size_t()
+        self._chk(self._L.rvc_extract_feature(self._h, pcm.ctypes.data_as(c_void_p),
+                                              c_size_t(pcm.shape[0]), out.ctypes.data_as(c_void_p),
+                                              c_size_t(cap), byref(fr), byref(c)))
+        return out[:fr.value * c.value].reshape(1, fr.value, c.value).copy()
+
+    def pitch(self, pcm, pitch_shift: int, sample_frame_16k_size: int) -> np.ndarray:
+        """rvc.rs:111-131 -> f0[T] Hz."""
+        pcm = _f32(pcm)
+        out = np.empty(4096, np.float32)
+        n = c_size_t()
+        self._chk(self._L.rvc_pitch(self._h, pcm.ctypes.data_as(c_void_p), c_size_t(pcm.shape[0]),
+                                    c_int32(pitch_shift), c_size_t(sample_frame_16k_size),
+                                    out.ctypes.data_as(c_void_p), c_size_t(out.shape[0]), byref(n)))
+        return out[:n.value].copy()
+
+    def infer(self, pcm, sample_frame_16k_size: int, pitch_shift, skip_head: int,
+              return_length: int, out: np.ndarray | None = None) -> np.ndarray:
+        """rvc.rs:133-220 (`pitch_shift=None` -> 0, rvc.rs:163)."""
+        pcm = _f32(pcm)
+        if out is None:
+            out = np.empty(return_length * 480 + 16, np.float32)
+        n = c_size_t()
+        self._chk(self._L.rvc_infer(self._h, pcm.ctypes.data_as(c_void_p), c_size_t(pcm.shape[0]),
+                                    c_uint32(sample_frame_16k_size),
+                                    c_int32(0 if pitch_shift is None else int(pitch_shift)),
+                                    c_uint32(skip_head), c_uint32(return_length),
+                                    out.ctypes.data_as(c_void_p), c_size_t(out.shape[0]), byref(n)))
+        return out[:n.value]
+
+    def infer_ptr(self, pcm_ptr: int, n: int, sample_frame_16k_size: int, pitch_shift: int,
+                  skip_head: int, return_length: int, out_ptr: int, cap: int, device: bool) -> int:
+        """Raw-pointer form (pinned host or device memory) used by bench.py."""
+        ln = c_size_t()
+        fn = self._L.rvc_infer_dev if device else self._L.rvc_infer
+        self._chk(fn(self._h, c_void_p(pcm_ptr), c_size_t(n), c_uint32(sample_frame_16k_size),
+                     c_int32(pitch_shift), c_uint32(skip_head), c_uint32(return_length),
+                     c_void_p(out_ptr), c_size_t(cap), byref(ln)))
+        return ln.value
+
+    # ------------------------------------------------------------------ extras
+    def mel_extract(self, pcm) -> np.ndarray:
+        """rmvpe.rs:159-205 -> (128, T)."""
+        pcm = _f32(pcm)
+        cap = 128 * (pcm.shape[0] // 160 + 2)
+        out = np.empty(cap, np.float32)
+        t = c_size_t()
+        self._chk(self._L.rvc_mel_extract(self._h, pcm.ctypes.data_as(c_void_p), c_size_t(pcm.shape[0]),
+                                          out.ctypes.data_as(c_void_p), c_size_t(cap), byref(t)))
+        return out[:128 * t.value].reshape(128, t.value).copy()
+
+    def knn_search(self, queries, k: int):
+        q = _f32(queries)
+        d2 = np.empty((q.shape[0], k), np.float32)
+        idx = np.empty((q.shape[0], k), np.int32)
+        self._chk(self._L.rvc_knn_search(self._h, q.ctypes.data_as(c_void_p), c_size_t(q.shape[0]),
+                                         c_size_t(q.shape[1]), c_int32(k), d2.ctypes.data_as(c_void_p),
+                                         idx.ctypes.data_as(c_void_p)))
+        return d2, idx
+
+    def get_last(self, name: str, dtype=np.float32) -> np.ndarray:
+        nb = c_size_t()
+        self._chk(self._L.rvc_get_last(self._h, name.encode(), None, c_size_t(0), byref(nb)))
+        out = np.empty(nb.value // 4, dtype)
+        self._chk(self._L.rvc_get_last(self._h, name.encode(), out.ctypes.data_as(c_void_p),
+                                       c_size_t(nb.value), byref(nb)))
+        return out
+
+    def buffer_names(self):
+        nb = c_size_t()
+        self._chk(self._L.rvc_debug_list(self._h, None, c_size_t(0), byref(nb)))
+        buf = ctypes.create_string_buffer(nb.value + 1)
+        self._chk(self._L.rvc_debug_list(self._h, buf, c_size_t(nb.value + 1), byref(nb)))
+        return [s for s in buf.value.decode().split("\n") if s]
+
+    def plan_info(self) -> dict:
+        import json
+        buf = ctypes.create_string_buffer(1024)
+        nb = c_size_t()
+        self._chk(self._L.rvc_plan_info(self._h, buf, c_size_t(1024), byref(nb)))
+        return json.loads(buf.value.decode())
+
+    def reset_state(self):
+        self._chk(self._L.rvc_reset_state(self._h))
+
+    def sync(self):
+        self._chk(self._L.rvc_sync(self._h))
+
+    def cuda_stream(self) -> int:
+        return int(self._L.rvc_cuda_stream(self._h) or 0)
+
+    def kernel_launches(self) -> int:
+        n = c_uint64()
+        self._chk(self._L.rvc_kernel_launches(self._h, byref(n)))
+        return n.value

@@ -371,26 +371,35 @@ void run_convpost(const ConvPostOp& o, const Bases& B) {
     }
 }
 
-void run_knn_dist(const KnnDistOp& o, const Bases& B) {
-    const float* idx = P<float>(B, o.index); const float* q = P<float>(B, o.queries); float* D = P<float>(B, o.D);
-    parallel_for(o.N, [&](int n) {
+void run_knn_scan(const KnnScanOp& o, const Bases& B) {
+    const float* idx = P<float>(B, o.index); const float* q = P<float>(B, o.queries);
+    float* cd = P<float>(B, o.cand_d); int32_t* ci = P<int32_t>(B, o.cand_i);
+    parallel_for(o.parts, [&](int p) {
         for (int qi = 0; qi < o.Q; ++qi) {
-            double a = 0;
-            for (int c = 0; c < o.C; ++c) { double d = double(q[int64_t(qi) * o.ldq + c]) - idx[int64_t(n) * o.C + c]; a += d * d; }
-            D[int64_t(qi) * o.N + n] = float(a);
+            std::vector<std::pair<float, int32_t>> best;
+            for (int n = p; n < o.N; n += o.parts) {
+                double a = 0;
+                for (int c = 0; c < o.C; ++c) { double d = double(q[int64_t(qi) * o.ldq + c]) - idx[int64_t(n) * o.C + c]; a += d * d; }
+                best.emplace_back(float(a), n);
+            }
+            std::sort(best.begin(), best.end());
+            for (int j = 0; j < o.k; ++j) {
+                int64_t e = (int64_t(qi) * o.parts + p) * o.k + j;
+                if (j < int(best.size())) { cd[e] = best[j].first; ci[e] = best[j].second; } else { cd[e] = 3.4e38f; ci[e] = -1; }
+            }
         }
     });
 }
 
 void run_knn_select(const KnnSelectOp& o, const Bases& B) {
-    const float* D = P<float>(B, o.D); int32_t* idx = P<int32_t>(B, o.idx); float* d2 = P<float>(B, o.d2);
+    const float* cd = P<float>(B, o.cand_d); const int32_t* ci = P<int32_t>(B, o.cand_i);
+    int32_t* idx = P<int32_t>(B, o.idx); float* d2 = P<float>(B, o.d2);
+    const int M = o.parts * o.k;
     for (int q = 0; q < o.Q; ++q) {
-        std::vector<int32_t> ord(o.N);
-        for (int i = 0; i < o.N; ++i) ord[i] = i;
-        const float* d = D + int64_t(q) * o.N;
-        std::partial_sort(ord.begin(), ord.begin() + o.k, ord.end(),
-                          [&](int a, int b) { return d[a] < d[b] || (d[a] == d[b] && a < b); });
-        for (int i = 0; i < o.k; ++i) { idx[q * o.k + i] = ord[i]; d2[q * o.k + i] = d[ord[i]]; }
+        std::vector<std::pair<float, int32_t>> all;
+        for (int m = 0; m < M; ++m) if (ci[int64_t(q) * M + m] >= 0) all.emplace_back(cd[int64_t(q) * M + m], ci[int64_t(q) * M + m]);
+        std::sort(all.begin(), all.end());
+        for (int i = 0; i < o.k; ++i) { idx[q * o.k + i] = all[i].second; d2[q * o.k + i] = all[i].first; }
     }
 }
 
@@ -434,7 +443,7 @@ void run_op(const Op& op, const Bases& B) {
         case OP_SINEGEN: run_sinegen(op.sine, B); break;
         case OP_AVG3: run_avg3(op.avg3, B); break;
         case OP_CONVPOST: run_convpost(op.cpost, B); break;
-        case OP_KNN_DIST: run_knn_dist(op.kd, B); break;
+        case OP_KNN_SCAN: run_knn_scan(op.kd, B); break;
         case OP_KNN_SELECT: run_knn_select(op.ks, B); break;
         case OP_KNN_BLEND: run_knn_blend(op.kb, B); break;
         case OP_GATHER_ROWS: run_gather(op.gather, B); break;
