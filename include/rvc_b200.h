@@ -131,6 +131,13 @@ int rvc_sync(rvc_ctx* ctx);                        /* cudaStreamSynchronize(ctx 
 void* rvc_cuda_stream(rvc_ctx* ctx);               /* cudaStream_t of the context             */
 int rvc_kernel_launches(rvc_ctx* ctx, uint64_t* total); /* kernels launched by this context  */
 int rvc_plan_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes);
+/* device-side timing on the context stream (CUDA events; 8 slots) */
+int rvc_event_record(rvc_ctx* ctx, int slot);
+int rvc_event_elapsed_ms(rvc_ctx* ctx, int slot_a, int slot_b, float* ms);
+/* Replays every op of the last plan `iters` times back to back between CUDA events and returns a
+ * JSON array [{"name","kind","us","flops","wbytes","iobytes","grid"}] (measurement aid: per-op device
+ * time + algorithmic work; inputs are whatever the last run left in the work arena). */
+int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t* out_bytes);
 const char* rvc_version(void);
 
 #ifdef __cplusplus

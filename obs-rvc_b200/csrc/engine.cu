@@ -11,6 +11,7 @@
 // There is no CPU execution path: every op is a kernel launch and a missing device is an error.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -97,6 +98,7 @@ struct rvc_ctx {
     std::map<PlanKey, std::unique_ptr<PlanEntry>> plans;
     PlanEntry* last = nullptr;
     uint64_t window = 0, total_launches = 0;
+    cudaEvent_t timers[8] = {nullptr};
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -129,45 +131,51 @@ int upload(rvc_ctx* ctx, Model& m) {
     return RVC_OK;
 }
 
+int issue_one(rvc_ctx* ctx, const Op& op, const DeviceBases& B, cudaStream_t s, int* n) {
+    switch (op.kind) {
+        case OP_GEMM: *n += launch_gemm(op.gemm, B, s); break;
+        case OP_LAYERNORM: *n += launch_layernorm(op.ln, B, s); break;
+        case OP_ATTN: *n += launch_attn(op.attn, B, s); break;
+        case OP_RELATTN: *n += launch_relattn(op.relattn, B, s); break;
+        case OP_CONV0_STATS: *n += launch_conv0_stats(op.c0s, B, s); break;
+        case OP_CONV0_APPLY: *n += launch_conv0_apply(op.c0a, B, s); break;
+        case OP_STFTMEL: *n += launch_stftmel(op.stft, B, s); break;
+        case OP_AVGPOOL: *n += launch_avgpool(op.pool, B, s); break;
+        case OP_GRU: *n += launch_gru(op.gru, B, s); break;
+        case OP_F0DECODE: *n += launch_f0decode(op.f0d, B, s); break;
+        case OP_F0POST: *n += launch_f0post(op.f0p, B, s); break;
+        case OP_EMBED: *n += launch_embed(op.embed, B, s); break;
+        case OP_ZP: *n += launch_zp(op.zp, B, s); break;
+        case OP_SINEGEN: *n += launch_sinegen(op.sine, B, s); break;
+        case OP_AVG3: *n += launch_avg3(op.avg3, B, s); break;
+        case OP_CONVPOST: *n += launch_convpost(op.cpost, B, s); break;
+        case OP_KNN_SCAN: *n += launch_knn_scan(op.kd, B, s); break;
+        case OP_KNN_SELECT: *n += launch_knn_select(op.ks, B, s); break;
+        case OP_KNN_BLEND: *n += launch_knn_blend(op.kb, B, s); break;
+        case OP_GATHER_ROWS: *n += launch_gather_rows(op.gather, B, s); break;
+        case OP_FILL: CK(cudaMemsetAsync(B.p<uint8_t>(op.fill.dst), 0, op.fill.bytes, s)); break;
+        default: break;
+    }
+    return RVC_OK;
+}
+
 int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
     const DeviceBases B = ctx->bases(e);
     size_t ev = 0;
     int n = 0;
     for (const Op& op : e.plan.ops) {
-        cudaStream_t s = ctx->streams[op.lane];
-        switch (op.kind) {
-            case OP_GEMM: n += launch_gemm(op.gemm, B, s); break;
-            case OP_LAYERNORM: n += launch_layernorm(op.ln, B, s); break;
-            case OP_ATTN: n += launch_attn(op.attn, B, s); break;
-            case OP_RELATTN: n += launch_relattn(op.relattn, B, s); break;
-            case OP_CONV0_STATS: n += launch_conv0_stats(op.c0s, B, s); break;
-            case OP_CONV0_APPLY: n += launch_conv0_apply(op.c0a, B, s); break;
-            case OP_STFTMEL: n += launch_stftmel(op.stft, B, s); break;
-            case OP_AVGPOOL: n += launch_avgpool(op.pool, B, s); break;
-            case OP_GRU: n += launch_gru(op.gru, B, s); break;
-            case OP_F0DECODE: n += launch_f0decode(op.f0d, B, s); break;
-            case OP_F0POST: n += launch_f0post(op.f0p, B, s); break;
-            case OP_EMBED: n += launch_embed(op.embed, B, s); break;
-            case OP_ZP: n += launch_zp(op.zp, B, s); break;
-            case OP_SINEGEN: n += launch_sinegen(op.sine, B, s); break;
-            case OP_AVG3: n += launch_avg3(op.avg3, B, s); break;
-            case OP_CONVPOST: n += launch_convpost(op.cpost, B, s); break;
-            case OP_KNN_SCAN: n += launch_knn_scan(op.kd, B, s); break;
-            case OP_KNN_SELECT: n += launch_knn_select(op.ks, B, s); break;
-            case OP_KNN_BLEND: n += launch_knn_blend(op.kb, B, s); break;
-            case OP_GATHER_ROWS: n += launch_gather_rows(op.gather, B, s); break;
-            case OP_FILL: CK(cudaMemsetAsync(B.p<uint8_t>(op.fill.dst), 0, op.fill.bytes, s)); break;
-            case OP_WAIT: {
-                if (ev >= ctx->events.size()) {
-                    cudaEvent_t x; CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-                    ctx->events.push_back(x);
-                }
-                CK(cudaEventRecord(ctx->events[ev], ctx->streams[op.wait.src_lane]));
-                CK(cudaStreamWaitEvent(ctx->streams[op.wait.dst_lane], ctx->events[ev], 0));
-                ++ev;
-                break;
+        if (op.kind == OP_WAIT) {
+            if (ev >= ctx->events.size()) {
+                cudaEvent_t x; CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+                ctx->events.push_back(x);
             }
+            CK(cudaEventRecord(ctx->events[ev], ctx->streams[op.wait.src_lane]));
+            CK(cudaStreamWaitEvent(ctx->streams[op.wait.dst_lane], ctx->events[ev], 0));
+            ++ev;
+            continue;
         }
+        int rc = issue_one(ctx, op, B, ctx->streams[op.lane], &n);
+        if (rc != RVC_OK) return rc;
     }
     CK(cudaGetLastError());
     *launches = n;
@@ -336,6 +344,7 @@ void rvc_destroy(rvc_ctx* ctx) {
     ctx->plans.clear();
     ctx->cv.unload(); ctx->f0.unload(); ctx->syn.unload(); ctx->index.release(); ctx->state.release();
     for (auto ev : ctx->events) cudaEventDestroy(ev);
+    for (auto ev : ctx->timers) if (ev) cudaEventDestroy(ev);
     for (auto s : ctx->streams) if (s) cudaStreamDestroy(s);
     delete ctx;
 }
@@ -596,6 +605,73 @@ int rvc_plan_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) 
                           p.audio_len, p.knn_q, ctx->last->exec ? 1 : 0);
     if (out_bytes) *out_bytes = size_t(n);
     if (out && cap_bytes > 0) { size_t m = size_t(n) < cap_bytes - 1 ? size_t(n) : cap_bytes - 1; std::memcpy(out, buf, m); out[m] = 0; }
+    return RVC_OK;
+}
+
+int rvc_event_record(rvc_ctx* ctx, int slot) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (slot < 0 || slot >= 8) return ctx->fail(RVC_ERR_INVALID_ARG, "bad timer slot");
+    if (!ctx->timers[slot]) CK(cudaEventCreate(&ctx->timers[slot]));
+    CK(cudaEventRecord(ctx->timers[slot], ctx->streams[0]));
+    return RVC_OK;
+}
+
+int rvc_event_elapsed_ms(rvc_ctx* ctx, int a, int b, float* ms) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !ms || !ctx->timers[a] || !ctx->timers[b]) return ctx->fail(RVC_ERR_INVALID_ARG, "bad timer slot");
+    CK(cudaEventSynchronize(ctx->timers[b]));
+    CK(cudaEventElapsedTime(ms, ctx->timers[a], ctx->timers[b]));
+    return RVC_OK;
+}
+
+int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t* out_bytes) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->last || iters <= 0) return ctx->fail(RVC_ERR_INVALID_ARG, "nothing has run yet");
+    PlanEntry& e = *ctx->last;
+    ctx->sync_all();
+    const DeviceBases B = ctx->bases(e);
+    cudaStream_t s = ctx->streams[0];
+    cudaEvent_t t0, t1;
+    CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+    static const char* KN[] = {"gemm", "layernorm", "attn", "relattn", "conv0_stats", "conv0_apply", "stftmel", "avgpool", "gru",
+                               "f0decode", "f0post", "embed", "zp", "sinegen", "avg3", "convpost", "knn_scan", "knn_select",
+                               "knn_blend", "gather_rows", "fill", "wait"};
+    std::string js = "[";
+    bool first = true;
+    for (const Op& op : e.plan.ops) {
+        if (op.kind == OP_WAIT || op.kind == OP_FILL) continue;
+        if (op.kind == OP_F0POST) continue;  // stateful (rolls the pitch cache)
+        int n = 0;
+        issue_one(ctx, op, B, s, &n);  // warm
+        CK(cudaEventRecord(t0, s));
+        for (int i = 0; i < iters; ++i) issue_one(ctx, op, B, s, &n);
+        CK(cudaEventRecord(t1, s));
+        CK(cudaEventSynchronize(t1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, t0, t1));
+        double flops = 0, wbytes = 0, iobytes = 0; long long grid = 0;
+        if (op.kind == OP_GEMM) {
+            const GemmOp& g = op.gemm;
+            flops = 2.0 * g.M * double(g.N) * g.K * g.batch;
+            wbytes = 4.0 * double(g.N) * g.K * g.batch;
+            double arows = double(g.M) * std::min<double>(double(g.K), double(g.lda > 0 ? g.lda : g.K)) + g.K;
+            iobytes = 4.0 * (arows * g.batch + double(g.M) * g.N * g.batch * (1 + (g.R.null() ? 0 : 1) + (g.C2.null() ? 0 : 1)));
+            grid = g.M;
+        } else if (op.kind == OP_KNN_SCAN) {
+            flops = 3.0 * double(op.kd.N) * op.kd.C * op.kd.Q; wbytes = 4.0 * double(op.kd.N) * op.kd.C;
+        }
+        char buf[512];
+        std::snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"kind\": \"%s\", \"lane\": %d, \"us\": %.3f, \"flops\": %.0f, \"wbytes\": %.0f, \"iobytes\": %.0f, \"M\": %lld}",
+                      first ? "" : ", ", op.name.c_str(), KN[op.kind], op.lane, double(ms) * 1e3 / iters, flops, wbytes, iobytes, grid);
+        js += buf; first = false;
+    }
+    js += "]";
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    if (out_bytes) *out_bytes = js.size();
+    if (out && cap_bytes > 0) {
+        if (js.size() + 1 > cap_bytes) return ctx->fail(RVC_ERR_INVALID_ARG, "profile buffer too small");
+        std::memcpy(out, js.data(), js.size()); out[js.size()] = 0;
+    }
     return RVC_OK;
 }
 

@@ -263,6 +263,22 @@ class RvcInfer:
         self._chk(self._L.rvc_plan_info(self._h, buf, c_size_t(1024), byref(nb)))
         return json.loads(buf.value.decode())
 
+    def event_record(self, slot: int):
+        self._chk(self._L.rvc_event_record(self._h, c_int32(slot)))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = c_float()
+        self._chk(self._L.rvc_event_elapsed_ms(self._h, c_int32(a), c_int32(b), byref(ms)))
+        return ms.value
+
+    def profile_ops(self, iters: int = 20) -> list:
+        import json
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        nb = c_size_t()
+        self._chk(self._L.rvc_profile_ops(self._h, c_int32(iters), buf, c_size_t(cap), byref(nb)))
+        return json.loads(buf.value.decode())
+
     def reset_state(self):
         self._chk(self._L.rvc_reset_state(self._h))
 

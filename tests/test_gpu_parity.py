@@ -1,0 +1,234 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle on the same
+seeded inputs (bit-exact for F0 argmax / coarse pitch / kNN indices; waveform within 1e-3 RMS -
+BASELINE.json north_star).  Marked `gpu`: run on the B200 box (`pytest -m gpu`)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+WAVE_RMS_TOL = 1e-3      # north_star: output waveform within 1e-3 RMS
+FEATS_ABS_TOL = 2e-3     # rvc/src/tests/hubert.rs:18 `epsilon = 2e-3`
+
+
+@pytest.fixture(scope="module")
+def env():
+    import rvc_b200
+    from oracle import pipeline, weights
+    from oracle.weights import read_rvcw
+    root = os.path.join(tempfile.gettempdir(), "rvc_b200_data_seed7")
+    paths = weights.make_data_dir(root, seed=7, index_rows=40000)
+    index = read_rvcw(paths["index"])["big_npy"]
+    eng = rvc_b200.RvcInfer(root, noise_seed=0)
+    eng.load_contentvec(2); eng.load_f0(1); eng.load_model(paths["model"])
+    ora = pipeline.RvcInfer(root, noise_seed=0)
+    ora.load_contentvec(2); ora.load_f0(1); ora.load_model(paths["model"])
+    yield dict(eng=eng, ora=ora, paths=paths, index=index, pipeline=pipeline, rvc_b200=rvc_b200)
+    eng.close()
+
+
+def _rms(a):
+    return float(np.sqrt(np.mean(np.asarray(a, np.float64) ** 2)))
+
+
+def test_native_library_loaded(env):
+    """The product path is the CUDA .so, not a fallback."""
+    assert os.path.exists(env["rvc_b200"].LIB_PATH)
+    assert env["eng"].cuda_stream() != 0
+
+
+@pytest.mark.parametrize("src", ["synthetic", "input_wav2", "jfk"])
+def test_mel_extract(env, src):
+    """MelSpectrogram::mel_extract (rmvpe.rs:159-205) on synthetic and real audio."""
+    if src == "synthetic":
+        x = env["pipeline"].synthetic_pcm(4960, seed=3)
+    elif src == "input_wav2":
+        x = np.load(os.path.join(GOLDEN, "input_wav2.npy"))[-10080:]
+    else:
+        x = np.load(os.path.join(GOLDEN, "jfk_2p5s.npy"))[:4960]
+    got = env["eng"].mel_extract(x)
+    want = env["ora"].mel_extract(x)
+    assert got.shape == want.shape == (128, 1 + len(x) // 160)
+    # ln() amplifies error only where the band energy sits near the 1e-5 clamp: compare in the
+    # linear domain everywhere and in the log domain away from the clamp
+    assert np.abs(np.exp(got) - np.exp(want)).max() < 2e-5 * max(1.0, float(np.exp(want).max()))
+    assert np.abs(got - want)[want > -9].max() < 2e-3
+
+
+def test_hubert_geometry_and_values(env):
+    """rvc/src/tests/hubert.rs:10-19: 38240 samples -> (1, 239, 768); values vs the oracle at the
+    reference's own tolerance (2e-3 abs)."""
+    x = np.load(os.path.join(GOLDEN, "input_wav2.npy"))
+    h = env["eng"].hubert(x)
+    assert h.shape == (1, 768, 119)
+    want = env["ora"].hubert(x)
+    assert np.abs(h - want).max() < FEATS_ABS_TOL
+    f = env["eng"].extract_feature(x)
+    assert f.shape == (1, 239, 768)
+    assert np.abs(f - env["ora"].extract_feature(x)).max() < FEATS_ABS_TOL
+    np.testing.assert_array_equal(f[0, -1], f[0, -3])      # rvc.rs:101-108: last frame three times
+
+
+@pytest.mark.parametrize("shift,sf", [(13, 4800), (0, 2560), (-12, 2560)])
+def test_pitch(env, shift, sf):
+    """rvc/src/tests/pitch.rs:18-30 call shape (input_wav2.npy, 13, 4800); argmax bit-exact."""
+    x = np.load(os.path.join(GOLDEN, "input_wav2.npy"))
+    got = env["eng"].pitch(x, shift, sf)
+    want = env["ora"].pitch(x, shift, sf)
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(env["eng"].get_last("f0_argmax", np.int32), env["ora"].last["argmax"])
+    assert np.abs(got - want).max() <= 1e-3 * max(1.0, float(np.abs(want).max()))
+
+
+@pytest.mark.parametrize("geom_name,index_rate", [("BASELINE_GEOM", 0.0), ("BASELINE_GEOM", 0.5), ("DEFAULT_GEOM", 0.5)])
+def test_infer_stream(env, geom_name, index_rate):
+    """RvcInfer::infer (rvc.rs:133-220) over consecutive windows of one stream: pitch cache
+    continuity, retrieval, synthesizer."""
+    eng, ora = env["eng"], env["ora"]
+    g = getattr(env["pipeline"], geom_name)
+    eng.set_index(env["index"], index_rate)
+    ora.set_index(env["index"], index_rate)
+    eng.reset_state()
+    ora.cache.buf[:] = 0
+    ora.window = 0
+    nwin = 4
+    pcm = env["pipeline"].synthetic_pcm(g["n16k"] + g["sf16k"] * nwin, seed=1)
+    for w in range(nwin):
+        x = pcm[w * g["sf16k"]: w * g["sf16k"] + g["n16k"]]
+        got = eng.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+        want = ora.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"])
+        assert got.shape == want.shape == (g["return_length"] * 400,)
+        np.testing.assert_array_equal(eng.get_last("f0_argmax", np.int32), ora.last["argmax"])
+        np.testing.assert_array_equal(eng.get_last("pitch", np.int32), ora.last["pitch"])
+        if index_rate > 0:
+            np.testing.assert_array_equal(eng.get_last("knn_idx", np.int32).reshape(-1, 8), ora.last["knn_idx"])
+        assert np.abs(eng.get_last("phone").reshape(ora.last["phone"].shape) - ora.last["phone"]).max() < FEATS_ABS_TOL
+        err = _rms(got - want)
+        assert err < WAVE_RMS_TOL, f"window {w}: waveform RMS error {err}"
+        assert _rms(want) > 0.05          # the comparison is not vacuous
+    eng.set_index(None, 0.0)
+    ora.set_index(None, 0.0)
+
+
+def test_graph_replay_equals_eager(env):
+    """Call 1 runs eagerly, later calls replay the captured CUDA graph: same inputs, same bits."""
+    rb = env["rvc_b200"]
+    g = env["pipeline"].BASELINE_GEOM
+    x = env["pipeline"].synthetic_pcm(g["n16k"], seed=5)
+    outs = []
+    for use_graph in (False, True):
+        e = rb.RvcInfer(env["paths"]["data"], noise_seed=3, use_cuda_graph=use_graph)
+        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+        seq = []
+        for _ in range(3):
+            e.reset_state()
+            seq.append(e.infer(x, g["sf16k"], 0, g["skip_head"], g["return_length"]).copy())
+        assert e.plan_info()["graph"] == int(use_graph)
+        np.testing.assert_array_equal(seq[0], seq[1])
+        np.testing.assert_array_equal(seq[1], seq[2])
+        outs.append(seq[2])
+        e.close()
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
+def test_noise_modes_and_pitch_shift_quirk(env):
+    """noise_mode 0 = deterministic zeros; pitch shift is integer octaves (rvc.rs:121)."""
+    rb = env["rvc_b200"]
+    g = env["pipeline"].BASELINE_GEOM
+    x = env["pipeline"].synthetic_pcm(g["n16k"], seed=6)
+    e = rb.RvcInfer(env["paths"]["data"], noise_mode=0)
+    e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+    f7 = e.pitch(x, 7, g["sf16k"]); f0 = e.pitch(x, 0, g["sf16k"]); f12 = e.pitch(x, 12, g["sf16k"])
+    np.testing.assert_array_equal(f7, f0)
+    np.testing.assert_allclose(f12, 2.0 * f0, rtol=0, atol=0)
+    ora = env["pipeline"].RvcInfer(env["paths"]["data"])
+    ora.load_contentvec(2); ora.load_f0(1); ora.load_model(env["paths"]["model"])
+    ora.noise_enabled = False
+    got = e.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+    want = ora.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"])
+    assert _rms(got - want) < WAVE_RMS_TOL
+    e.close()
+
+
+def test_error_behaviour(env):
+    """rvc-common/src/errors.rs + SURVEY 8b 'Shape contract': errors instead of panics."""
+    rb = env["rvc_b200"]
+    g = env["pipeline"].BASELINE_GEOM
+    x = env["pipeline"].synthetic_pcm(g["n16k"], seed=7)
+    e = rb.RvcInfer(env["paths"]["data"])
+    with pytest.raises(rb.ModelNotLoaded):
+        e.infer(x, g["sf16k"], 0, g["skip_head"], g["return_length"])
+    with pytest.raises(rb.ContentvecNotLoaded):
+        e.hubert(x)
+    with pytest.raises(rb.F0NotLoaded):
+        e.pitch(x, 0, g["sf16k"])
+    with pytest.raises(rb.IoError):
+        e.load_model("/nonexistent/voice.rvcw")
+    e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+    with pytest.raises(rb.BadShape):          # skip_head + return_length > 2T+1 (rvc.rs:155 panics)
+        e.infer(x, g["sf16k"], 0, 220, 21)
+    with pytest.raises(rb.BadShape):          # input shorter than the f0 window (rmvpe.rs:257 panics)
+        e.pitch(x[:3000], 0, g["sf16k"])
+    e.unload_model()
+    with pytest.raises(rb.ModelNotLoaded):
+        e.infer(x, g["sf16k"], 0, g["skip_head"], g["return_length"])
+    e.close()
+    bad = rb.RvcInfer("/nonexistent-data-dir")
+    with pytest.raises(rb.IoError):
+        bad.load_contentvec(2)
+    bad.close()
+
+
+@pytest.mark.parametrize("n,c,q,k", [(40000, 768, 11, 8), (100000, 256, 128, 4), (5000, 256, 1, 8), (3000, 512, 40, 16)])
+def test_knn_search_exact(env, n, c, q, k):
+    """Brute-force L2 top-k indices bit-exact vs the float64 oracle (config-5 shape at reduced N)."""
+    from oracle import knn
+    from oracle.weights import synth_index
+    rb = env["rvc_b200"]
+    rows = synth_index(11, n, c)
+    rng = np.random.default_rng(5)
+    queries = (rows[rng.integers(0, n, q)] + rng.standard_normal((q, c)).astype(np.float32) * 0.2).astype(np.float32)
+    e = rb.RvcInfer(env["paths"]["data"], index_k=k)
+    e.set_index(rows, 0.0)
+    d2, idx = e.knn_search(queries, k)
+    wd, wi = knn.search(rows, queries, k)
+    np.testing.assert_array_equal(idx, wi)
+    assert np.abs(d2 - wd).max() <= 1e-4 * max(1.0, float(wd.max()))
+    e.close()
+
+
+def test_independent_streams_batch(env):
+    """streams shard with no shared state - two contexts on one GPU driven through
+    rvc_infer_batch give the same audio as each alone."""
+    import ctypes
+    rb = env["rvc_b200"]
+    g = env["pipeline"].BASELINE_GEOM
+    xs = [env["pipeline"].synthetic_pcm(g["n16k"], seed=20 + i) for i in range(2)]
+    solo = []
+    for i in range(2):
+        e = rb.RvcInfer(env["paths"]["data"], noise_seed=i)
+        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+        solo.append(e.infer(xs[i], g["sf16k"], 12, g["skip_head"], g["return_length"]).copy())
+        e.close()
+    es = []
+    for i in range(2):
+        e = rb.RvcInfer(env["paths"]["data"], noise_seed=i)
+        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+        es.append(e)
+    L = rb.lib()
+    n_out = g["return_length"] * 400
+    outs = [np.empty(n_out, np.float32) for _ in range(2)]
+    ctxs = (ctypes.c_void_p * 2)(*[e.handle for e in es])
+    pin = (ctypes.c_void_p * 2)(*[x.ctypes.data for x in xs])
+    pout = (ctypes.c_void_p * 2)(*[o.ctypes.data for o in outs])
+    ln = ctypes.c_size_t()
+    rc = L.rvc_infer_batch(ctxs, ctypes.c_size_t(2), pin, ctypes.c_size_t(g["n16k"]), ctypes.c_uint32(g["sf16k"]),
+                           ctypes.c_int32(12), ctypes.c_uint32(g["skip_head"]), ctypes.c_uint32(g["return_length"]),
+                           pout, ctypes.c_size_t(n_out), ctypes.byref(ln))
+    assert rc == 0 and ln.value == n_out
+    for i in range(2):
+        np.testing.assert_array_equal(outs[i], solo[i])
+        es[i].close()

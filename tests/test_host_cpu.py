@@ -1,0 +1,166 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/rvc_b200.h
+declares; the plan builder + weight packing, replayed by the test-only CPU interpreter, match the
+torch oracle; host mirror error mapping; oracle network bodies cross-checked against independent
+implementations (torch.nn.GRU, torchaudio HuBERT)."""
+import ctypes
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    return os.path.join(ROOT, "obs-rvc_b200", "librvc_b200.so")
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "rvc_b200.h")).read()
+    names = set(re.findall(r"\b(rvc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    L = ctypes.CDLL(built)
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in include/rvc_b200.h but not exported"
+    L.rvc_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.rvc_version()
+
+
+def test_create_fails_loudly_without_gpu(built):
+    """No CPU fallback: without a CUDA device the engine refuses to construct."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import rvc_b200
+    with pytest.raises(rvc_b200.CudaError):
+        rvc_b200.RvcInfer(tempfile.gettempdir())
+
+
+def test_config_struct_layout(built):
+    import rvc_b200
+    L = rvc_b200.lib()
+    cfg = rvc_b200.Config()
+    L.rvc_config_default(ctypes.byref(cfg))
+    assert (cfg.device, cfg.noise_mode, cfg.index_k, cfg.use_cuda_graph) == (0, 1, 8, 1)
+    assert ctypes.sizeof(rvc_b200.Config) == 64   # matches sizeof(rvc_config)
+
+
+@pytest.fixture(scope="session")
+def data():
+    from oracle import weights
+    root = os.path.join(tempfile.gettempdir(), "rvc_b200_data_seed7")
+    return weights.make_data_dir(root, seed=7, index_rows=40000)
+
+
+def test_plan_on_cpu_matches_oracle(built, data):
+    """Plan + packing + op semantics (shared with the CUDA engine) vs the torch oracle, two
+    consecutive BASELINE windows with retrieval: waveform RMS error < 1e-5, integers exact."""
+    import planexec
+    from oracle import pipeline
+    from oracle.weights import read_rvcw
+    idx = read_rvcw(data["index"])["big_npy"]
+    pe = planexec.PlanExec(data["data"])
+    pe.load(0, data["contentvec"]); pe.load(1, data["f0"]); pe.load(2, data["model"])
+    pe.set_index(idx, 0.5); pe.set_params(seed=0, noise_mode=1, index_k=8)
+    ora = pipeline.RvcInfer(data["data"], noise_seed=0)
+    ora.load_contentvec(2); ora.load_f0(1); ora.load_model(data["model"]); ora.set_index(idx, 0.5)
+    g = pipeline.BASELINE_GEOM
+    pcm = pipeline.synthetic_pcm(g["n16k"] + g["sf16k"] * 2)
+    for w in range(2):
+        x = pcm[w * g["sf16k"]: w * g["sf16k"] + g["n16k"]]
+        pe.run(planexec.PLAN_INFER, x, g["sf16k"], 12, g["skip_head"], g["return_length"])
+        want = ora.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"])
+        got = pe.get("audio")
+        assert np.sqrt(np.mean((got - want) ** 2)) < 1e-5
+        np.testing.assert_array_equal(pe.get("f0_argmax", np.int32), ora.last["argmax"])
+        np.testing.assert_array_equal(pe.get("pitch", np.int32), ora.last["pitch"])
+        np.testing.assert_array_equal(pe.get("knn_idx", np.int32).reshape(-1, 8), ora.last["knn_idx"])
+    d = pe.dims()
+    assert (d["hubert_T"], d["hubert_C"], d["f0_T"], d["audio_len"], d["knn_q"]) == (111, 768, 32, 8400, 11)
+    pe.close()
+
+
+def test_plan_shape_contract(built, data):
+    """SURVEY 8b shape contract: violations are plan errors, not crashes."""
+    import planexec
+    pe = planexec.PlanExec(data["data"])
+    pe.load(0, data["contentvec"]); pe.load(1, data["f0"]); pe.load(2, data["model"])
+    x = np.zeros(35840, np.float32)
+    with pytest.raises(RuntimeError):
+        pe.run(planexec.PLAN_INFER, x, 2560, 0, 220, 21)      # rvc.rs:155
+    with pytest.raises(RuntimeError):
+        pe.run(planexec.PLAN_PITCH, x[:3000], 2560, 0, 0, 0)  # rmvpe.rs:257
+    with pytest.raises(RuntimeError):
+        pe.run(planexec.PLAN_HUBERT, x[:100], 0, 0, 0, 0)
+    pe.close()
+
+
+def test_gru_matches_torch():
+    """oracle.nets.gru_direction vs torch.nn.GRU (pins the restated gate order)."""
+    import torch
+    from oracle import nets
+    torch.manual_seed(0)
+    gru = torch.nn.GRU(24, 16, batch_first=True, bidirectional=True)
+    x = torch.randn(9, 24)
+    with torch.no_grad():
+        want = gru(x[None])[0][0]
+        f = nets.gru_direction(x, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0, False)
+        b = nets.gru_direction(x, gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse,
+                               gru.bias_hh_l0_reverse, True)
+    assert torch.allclose(torch.cat([f, b], 1), want, atol=1e-6)
+
+
+def test_hubert_matches_torchaudio_structure():
+    """Independent structure check: oracle HuBERT == torchaudio.models.hubert_base with
+    the same weights copied over (frame geometry 35840 -> 111 and numerics)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import torch
+    from oracle import nets, weights
+    w = weights.synth_contentvec(3)
+    m = torchaudio.models.hubert_base().eval()
+    sd = m.state_dict()
+    tw = nets.to_torch(w)
+    mp = {}
+    for i in range(7):
+        mp[f"feature_extractor.conv_layers.{i}.conv.weight"] = tw[f"feature_extractor.conv_layers.{i}.0.weight"]
+    mp["feature_extractor.conv_layers.0.layer_norm.weight"] = tw["feature_extractor.conv_layers.0.2.weight"]
+    mp["feature_extractor.conv_layers.0.layer_norm.bias"] = tw["feature_extractor.conv_layers.0.2.bias"]
+    mp["encoder.feature_projection.layer_norm.weight"] = tw["layer_norm.weight"]
+    mp["encoder.feature_projection.layer_norm.bias"] = tw["layer_norm.bias"]
+    mp["encoder.feature_projection.projection.weight"] = tw["post_extract_proj.weight"]
+    mp["encoder.feature_projection.projection.bias"] = tw["post_extract_proj.bias"]
+    wv = tw["encoder.pos_conv.0.weight"]
+    mp["encoder.transformer.pos_conv_embed.conv.bias"] = tw["encoder.pos_conv.0.bias"]
+    mp["encoder.transformer.layer_norm.weight"] = tw["encoder.layer_norm.weight"]
+    mp["encoder.transformer.layer_norm.bias"] = tw["encoder.layer_norm.bias"]
+    for i in range(12):
+        s, d = f"encoder.layers.{i}.", f"encoder.transformer.layers.{i}."
+        for a, b in (("self_attn.q_proj", "attention.q_proj"), ("self_attn.k_proj", "attention.k_proj"),
+                     ("self_attn.v_proj", "attention.v_proj"), ("self_attn.out_proj", "attention.out_proj"),
+                     ("self_attn_layer_norm", "layer_norm"), ("fc1", "feed_forward.intermediate_dense"),
+                     ("fc2", "feed_forward.output_dense"), ("final_layer_norm", "final_layer_norm")):
+            mp[d + b + ".weight"] = tw[s + a + ".weight"]
+            mp[d + b + ".bias"] = tw[s + a + ".bias"]
+    # torchaudio keeps pos_conv under weight norm (dim=2): w = g * v / |v|; g = |v| makes w == v
+    g = wv.norm(dim=(0, 1), keepdim=True)
+    for k in sd:
+        if "pos_conv_embed.conv" not in k or k.endswith("bias"):
+            continue
+        if k.endswith("original0") or k.endswith("weight_g"):
+            mp[k] = g
+        elif k.endswith("original1") or k.endswith("weight_v"):
+            mp[k] = wv
+    missing = [k for k in sd if k not in mp]
+    assert not missing, missing
+    m.load_state_dict(mp)
+    x = torch.from_numpy(np.random.default_rng(0).standard_normal(35840).astype(np.float32) * 0.1)
+    with torch.no_grad():
+        want = m.extract_features(x[None])[0][-1][0]
+    got = nets.hubert_forward(tw, x)
+    assert got.shape == want.shape == (111, 768)
+    assert float((got - want).abs().max()) < 2e-4
