@@ -1,0 +1,47 @@
+// gemm_sched.h - plan-time choice of the GEMM kernel variant and split-K factor (host-only).
+//
+// At batch 1 most contractions of the path are small-M (4..111 rows) against multi-megabyte
+// weight matrices: they are bound by how fast the weights stream out of HBM, which needs (a) a
+// CTA count that is a multiple of the 148 SMs and (b) several k-tiles of loads in flight per
+// CTA.  The v2 kernel (kernels_gemm2.cu) therefore splits K across CTAs; partial tiles go to a
+// per-op scratch area and the last CTA to arrive on a tile reduces them in a fixed order and
+// applies the epilogue (deterministic, one launch).
+#pragma once
+#include <algorithm>
+
+#include "ops.h"
+
+namespace rvc {
+
+struct GemmSched {
+    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM64/BN128
+    int bm = 0, bn = 0, splitk = 1, tiles = 0;
+};
+
+constexpr int GEMM2_BK = 32;
+constexpr int NUM_SMS = 148;
+
+inline GemmSched gemm_schedule(const GemmOp& g) {
+    GemmSched s;
+    const bool aligned = g.A.off % 16 == 0 && g.W.off % 16 == 0 && g.lda % 4 == 0 && g.seg_len % 4 == 0 &&
+                         g.seg_stride % 4 == 0 && g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
+    if (!aligned || g.K < 64) return s;  // tiny / oddly aligned contractions stay on the v1 kernel
+    if (g.M <= 8) { s.variant = 1; s.bm = 8; s.bn = 256; }
+    else if (g.M <= 16) { s.variant = 2; s.bm = 16; s.bn = 128; }
+    else if (g.M <= 256) { s.variant = 3; s.bm = 32; s.bn = 64; }
+    else { s.variant = 4; s.bm = 64; s.bn = 128; }
+    // narrow outputs: do not waste a 256/128-wide tile on a 32..64-column problem
+    if (s.variant == 1 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
+    if (s.variant == 2 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
+    if (s.variant == 4 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
+    const int tm = (g.M + s.bm - 1) / s.bm, tn = (g.N + s.bn - 1) / s.bn;
+    s.tiles = tm * tn * g.batch;
+    const int nkt = (g.K + GEMM2_BK - 1) / GEMM2_BK;
+    int want = (2 * NUM_SMS + s.tiles - 1) / s.tiles;          // ~2 CTAs per SM in total
+    int maxsplit = std::max(1, nkt / 4);                        // at least 4 k-tiles per split
+    s.splitk = std::max(1, std::min(std::min(want, maxsplit), 64));
+    if (g.out_mode != OUT_PLAIN && false) s.splitk = 1;
+    return s;
+}
+
+}  // namespace rvc

@@ -12,6 +12,7 @@
 // k-major shared layout gives LDS.128 operand fetches.
 #include <cstdio>
 
+#include "gemm_common.cuh"
 #include "launch.h"
 
 namespace rvc {
@@ -20,35 +21,7 @@ namespace {
 
 constexpr int BK = 16;
 
-struct GemmParams {
-    const float* A; long long lda; int seg_len; long long seg_stride;
-    const float* W; long long ldw;
-    const float* bias;
-    float* C; long long ldc;
-    float* C2; long long ldc2; int act2;
-    const float* R; long long ldr;
-    int M, N, K, act;
-    float alpha;
-    int mask_period, mask_valid;
-    long long sA, sW, sBias, sC, sR;
-    int out_mode, om_a, om_b, om_c, om_d;
-    int vec_store;
-};
-
-__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
-
-__device__ __forceinline__ float apply_act(int act, float v) {
-    switch (act) {
-        case ACT_GELU: return gelu_f(v);
-        case ACT_RELU: return fmaxf(v, 0.0f);
-        case ACT_LRELU01: return v > 0.0f ? v : 0.1f * v;
-        case ACT_LRELU001: return v > 0.0f ? v : 0.01f * v;
-        case ACT_SIGMOID: return sigmoid_f(v);
-        case ACT_TANH: return tanhf(v);
-        default: return v;
-    }
-}
+using namespace gemmk;
 
 // loads 4 consecutive k of one row (zero beyond the row / K range)
 template <bool VEC>
@@ -276,16 +249,11 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 }  // namespace
 
+int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);  // kernels_gemm2.cu
+
 int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
-    GemmParams p;
-    p.A = B.p<float>(g.A); p.lda = g.lda; p.seg_len = g.seg_len; p.seg_stride = g.seg_stride;
-    p.W = B.p<float>(g.W); p.ldw = g.ldw; p.bias = B.p<float>(g.bias);
-    p.C = B.p<float>(g.C); p.ldc = g.ldc; p.C2 = B.p<float>(g.C2); p.ldc2 = g.ldc2; p.act2 = g.act2;
-    p.R = B.p<float>(g.R); p.ldr = g.ldr;
-    p.M = g.M; p.N = g.N; p.K = g.K; p.act = g.act; p.alpha = g.alpha;
-    p.mask_period = g.mask_period; p.mask_valid = g.mask_valid;
-    p.sA = g.sA; p.sW = g.sW; p.sBias = g.sBias; p.sC = g.sC; p.sR = g.sR;
-    p.out_mode = g.out_mode; p.om_a = g.om_a; p.om_b = g.om_b; p.om_c = g.om_c; p.om_d = g.om_d;
+    if (g.sched_variant > 0) return launch_gemm_v2(g, B, stream);
+    GemmParams p = make_params(g, B);
     const bool vec = al16(p.A) && al16(p.W) && g.lda % 4 == 0 && g.seg_len % 4 == 0 && g.seg_stride % 4 == 0 &&
                      g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
     p.vec_store = (g.out_mode == OUT_PLAIN && g.act != ACT_GATE && al16(p.C) && g.ldc % 4 == 0 && g.sC % 4 == 0 &&

@@ -401,6 +401,7 @@ void init_kernel_attributes() {
     done = true;
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(relattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    init_gemm_v2_attributes();
 }
 
 int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t s) {

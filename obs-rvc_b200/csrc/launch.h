@@ -40,5 +40,6 @@ int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t
 
 // one-time per-process kernel attribute setup (dynamic shared memory opt-in)
 void init_kernel_attributes();
+void init_gemm_v2_attributes();
 
 }  // namespace rvc

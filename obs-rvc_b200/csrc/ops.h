@@ -56,6 +56,9 @@ struct GemmOp {
     int32_t mask_period = 0, mask_valid = 0;  // rows with (m % period) >= valid write 0
     int32_t batch = 1; int64_t sA = 0, sW = 0, sBias = 0, sC = 0, sR = 0;  // element strides
     int32_t out_mode = OUT_PLAIN; int32_t om_a = 0, om_b = 0, om_c = 0, om_d = 0;
+    // kernel schedule chosen at plan time (gemm_sched.h): 0 = v1 tile kernel, >0 = v2 cp.async
+    // split-K variant; scratch[splitk][batch][M][N] partial tiles + one arrival counter per tile
+    int32_t sched_variant = 0, splitk = 1; Ref scratch, counters;
 };
 
 struct LayerNormOp {  // y = (x-mean)/sqrt(var+eps)*gamma+beta over `cols`, biased variance

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 
+#include "gemm_sched.h"
 #include "model.h"
 
 namespace rvc {
@@ -166,9 +167,15 @@ int64_t interior(const Map2d& m) { return (int64_t(m.F + 2) + 1) * m.C; }
 
 void conv3x3(PB& b, const Packed* P, const std::string& name, const std::string& wname, const Map2d& in,
              int cout, Ref dst_interior, int64_t ld_dst, int act, Ref R, int64_t ldr) {
-    GemmOp& g = b.gemm(name, in.base, in.C, 3 * in.C, int64_t(in.F + 2) * in.C, b.w(P, SP_F0, wname + ".w"),
-                       9 * in.C, b.w(P, SP_F0, wname + ".b"), dst_interior, ld_dst, in.T * (in.F + 2), cout,
-                       9 * in.C, act);
+    Ref A = in.base, Wt = b.w(P, SP_F0, wname + ".w");
+    int K = 9 * in.C;
+    if (in.T == 1) {
+        // a single time row: kernel rows dt=0 and dt=2 only ever see the zero halo, so only the
+        // middle third of every filter is streamed (3x less weight traffic at the U-Net bottleneck)
+        A = in.base.plus(int64_t(in.F + 2) * in.C); Wt = Wt.plus(3 * in.C); K = 3 * in.C;
+    }
+    GemmOp& g = b.gemm(name, A, in.C, 3 * in.C, int64_t(in.F + 2) * in.C, Wt, 9 * in.C, b.w(P, SP_F0, wname + ".b"),
+                       dst_interior, ld_dst, in.T * (in.F + 2), cout, K, act);
     g.mask_period = in.F + 2; g.mask_valid = in.F; g.R = R; g.ldr = ldr;
 }
 
@@ -466,6 +473,20 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
     return audio;
 }
 
+// chooses the kernel variant / split-K factor of every GEMM and allocates its scratch
+void schedule_gemms(PB& b) {
+    for (Op& op : b.plan.ops) {
+        if (op.kind != OP_GEMM) continue;
+        GemmOp& g = op.gemm;
+        GemmSched s = gemm_schedule(g);
+        g.sched_variant = s.variant; g.splitk = s.splitk;
+        if (s.variant > 0 && s.splitk > 1) {
+            g.scratch = b.alloc("", int64_t(s.splitk) * g.batch * g.M * g.N);
+            g.counters = b.alloc("", s.tiles, true);
+        }
+    }
+}
+
 }  // namespace
 
 bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const Packed* cv, const CvInfo* cvi,
@@ -494,6 +515,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         Op& s = b.add(OP_KNN_SELECT, "knn_select");
         s.ks.cand_d = cd; s.ks.cand_i = ci; s.ks.idx = idx; s.ks.d2 = d2; s.ks.Q = Q; s.ks.k = k; s.ks.parts = parts;
         plan.knn_q = Q;
+        schedule_gemms(b);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -502,6 +524,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         if (N < 1024) { err = "input shorter than one FFT frame"; return false; }
         F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm, N, plan.params, true, 0);
         plan.f0_T = o.T;
+        schedule_gemms(b);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -516,6 +539,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
             op.gather.C = cvi->out_dim; op.gather.skip = 0; op.gather.R = 2 * T + 1;
             if (int64_t(2 * T + 1) * cvi->out_dim > StateLayout::AUDIO_CAP) b.fail("feature too large");
         }
+        schedule_gemms(b);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -526,6 +550,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     if (kind == PLAN_PITCH) {
         F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
         plan.f0_T = o.T;
+        schedule_gemms(b);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -594,6 +619,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     if (audio_len > StateLayout::AUDIO_CAP) { err = "output too long"; return false; }
     build_synth(b, syn, *syi, phone, pitch, pitchf, plan.params, plan.audio, R, ml);
     plan.audio_len = audio_len;
+    schedule_gemms(b);
     plan.work_bytes = b.work + 256;
     return b.ok;
 }
