@@ -39,14 +39,19 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
         for (int j = 0; j < KK; ++j) { ld[g][j] = FLT_MAX; li[g][j] = -1; }
 
     const float4* qs4 = reinterpret_cast<const float4*>(qs);
-    for (int n = part; n < N; n += parts) {
+    float4 y[CV], yn[CV];
+    auto load_row = [&](float4* dst, int n) {
         const float4* row = reinterpret_cast<const float4*>(index + (long long)n * C);
-        float4 y[CV];
 #pragma unroll
         for (int i = 0; i < CV; ++i) {
             int c4 = lane + i * 32;
-            y[i] = c4 < C4 ? __ldg(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[i] = c4 < C4 ? __ldcs(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // streamed once: evict-first
         }
+    };
+    if (part < N) load_row(y, part);
+    for (int n = part; n < N; n += parts) {
+        const bool more = n + parts < N;
+        if (more) load_row(yn, n + parts);  // next row in flight while this one is reduced
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             float v[QN];
@@ -92,6 +97,10 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
                     }
                 }
             }
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < CV; ++i) y[i] = yn[i];
         }
     }
     if (lane < QN) {

@@ -1,10 +1,14 @@
 // kernels_misc.cu - the non-GEMM device ops of the plan (normalisation, attention, GRU, glue).
 // All arithmetic is fp32 with the same formulas as the reference path's oracle; reductions use
 // warp shuffles; every kernel is latency-sized for one audio window.
+#include <cooperative_groups.h>
+
 #include <cfloat>
 
 #include "launch.h"
 #include "noise.h"
+
+namespace cg = cooperative_groups;
 
 namespace rvc {
 
@@ -260,45 +264,61 @@ __global__ void avgpool_kernel(const float* __restrict__ in, long long ldin, flo
 }
 
 // ------------------------------------------------------------------------------------------
-// Bidirectional GRU (H=256): one CTA per direction, thread g owns gate row g of W_hh
+// Bidirectional GRU (H=256).  The recurrence is latency-bound (T sequential steps), so W_hh is
+// made register-resident: one thread-block cluster of 8 CTAs per direction, CTA r owns hidden
+// units [32r, 32r+32) = 96 gate rows x 256, 32 weights per thread (768 threads).  Every step each
+// CTA computes its 32 new h values and pushes them into all 8 peers' shared memory over DSMEM;
+// one cluster barrier per step replaces a trip through L2.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(768)
-gru_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t, const float* __restrict__ bhh,
-           float* __restrict__ out, int T, int H) {
-    extern __shared__ float sm[];
-    float* hs = sm;          // [H]
-    float* gh = hs + H;      // [3H]
-    const int d = blockIdx.x, g = threadIdx.x, G = 3 * H;
-    const float* wt = whh_t + (long long)d * H * G;
-    const float bg = g < G ? bhh[d * G + g] : 0.f;
-    if (g < H) hs[g] = 0.f;
-    __syncthreads();
+constexpr int GRU_CL = 8, GRU_H = 256, GRU_UNITS = GRU_H / GRU_CL;  // 32 hidden units per CTA
+
+__global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(768)
+gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t, const float* __restrict__ bhh,
+                   float* __restrict__ out, int T) {
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int H = GRU_H, G = 3 * GRU_H;
+    __shared__ __align__(16) float hbuf[2][H];
+    __shared__ float gh[3 * GRU_UNITS];
+    const int rank = int(cluster.block_rank()), d = blockIdx.x / GRU_CL, tid = threadIdx.x;
+    const int row_local = tid >> 3, part = tid & 7;            // 96 rows x 8 k-slices
+    const int gate = row_local / GRU_UNITS, ju = row_local % GRU_UNITS;
+    const int g = gate * H + rank * GRU_UNITS + ju;            // global gate row
+    float w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = whh_t[((long long)d * H + (i * 8 + part)) * G + g];
+    const float bg = bhh[d * G + g];
+    if (tid < H) { hbuf[0][tid] = 0.f; hbuf[1][tid] = 0.f; }
+    cluster.sync();
     for (int s = 0; s < T; ++s) {
-        const int t = d == 0 ? s : T - 1 - s;
-        if (g < G) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < H; k += 4) {
-                a0 = fmaf(__ldg(wt + (long long)(k + 0) * G + g), hs[k + 0], a0);
-                a1 = fmaf(__ldg(wt + (long long)(k + 1) * G + g), hs[k + 1], a1);
-                a2 = fmaf(__ldg(wt + (long long)(k + 2) * G + g), hs[k + 2], a2);
-                a3 = fmaf(__ldg(wt + (long long)(k + 3) * G + g), hs[k + 3], a3);
-            }
-            gh[g] = bg + ((a0 + a1) + (a2 + a3));
+        const int t = d == 0 ? s : T - 1 - s, cur = s & 1;
+        float xr = 0.f, xz = 0.f, xn = 0.f;
+        if (tid < GRU_UNITS) {
+            const float* x = gi + (long long)t * 2 * G + d * G + rank * GRU_UNITS + tid;
+            xr = x[0]; xz = x[H]; xn = x[2 * H];
         }
-        __syncthreads();
-        float hn = 0.f;
-        if (g < H) {
-            const float* x = gi + (long long)t * 2 * G + d * G;
-            float r = sigmoid_f(x[g] + gh[g]);
-            float z = sigmoid_f(x[H + g] + gh[H + g]);
-            float n = tanhf(x[2 * H + g] + r * gh[2 * H + g]);
-            hn = (1.0f - z) * n + z * hs[g];
-            out[(long long)t * 2 * H + d * H + g] = hn;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            a0 = fmaf(w[i], hbuf[cur][i * 8 + part], a0);
+            a1 = fmaf(w[i + 1], hbuf[cur][(i + 1) * 8 + part], a1);
         }
+        float a = a0 + a1;
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (part == 0) gh[row_local] = a + bg;
         __syncthreads();
-        if (g < H) hs[g] = hn;
-        __syncthreads();
+        if (tid < GRU_UNITS) {
+            const int j = rank * GRU_UNITS + tid;
+            const float r = sigmoid_f(xr + gh[tid]);
+            const float z = sigmoid_f(xz + gh[GRU_UNITS + tid]);
+            const float n = tanhf(xn + r * gh[2 * GRU_UNITS + tid]);
+            const float hn = (1.0f - z) * n + z * hbuf[cur][j];
+            out[(long long)t * 2 * H + d * H + j] = hn;
+#pragma unroll
+            for (int peer = 0; peer < GRU_CL; ++peer) cluster.map_shared_rank(&hbuf[cur ^ 1][0], peer)[j] = hn;
+        }
+        cluster.sync();
     }
 }
 
@@ -445,8 +465,8 @@ int launch_avgpool(const AvgPoolOp& o, const DeviceBases& B, cudaStream_t s) {
 }
 
 int launch_gru(const GruOp& o, const DeviceBases& B, cudaStream_t s) {
-    gru_kernel<<<2, 768, sizeof(float) * 4 * o.H, s>>>(B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out),
-                                                       o.T, o.H);
+    // H is fixed by the RMVPE architecture (BiGRU(384, 256)); validated when the model is packed
+    gru_cluster_kernel<<<2 * GRU_CL, 768, 0, s>>>(B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out), o.T);
     return 1;
 }
 

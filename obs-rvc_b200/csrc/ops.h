@@ -181,7 +181,7 @@ struct RunParams {
 
 static const int NOISE_KIND_Z = 1;
 static const int NOISE_KIND_SINE = 2;
-static const int KNN_PARTS = 148 * 8;  // one part per resident warp of the scan kernel
+static const int KNN_PARTS = 148 * 16;  // one part per warp; 2 CTAs of 8 warps per SM
 
 // A named buffer of the plan (debug / result lookups).
 struct NamedBuf { std::string name; Ref ref; int64_t elems = 0; int32_t is_int = 0; };

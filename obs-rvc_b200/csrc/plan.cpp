@@ -392,10 +392,13 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
     b.alias("sy.har", har, L);
     Ref sine_dbg = b.alloc("sy.sine", L);
     {
+        // the sine source only needs pitchf: it runs on lane 1 while enc_p / flow occupy lane 0
+        if (multi_lane) { b.wait(0, 1); b.lane = 1; }
         Op& op = b.add(OP_SINEGEN, "sy.sine");
         op.sine.pitchf = pitchf; op.sine.out = har; op.sine.sine_dbg = sine_dbg; op.sine.params = params;
         op.sine.R = R; op.sine.upp = upp; op.sine.sr = float(info.sr); op.sine.lin_w = info.lin_w;
         op.sine.lin_b = info.lin_b;
+        b.lane = 0;
     }
     static const int RATES[4] = {10, 10, 2, 2}, UK[4] = {16, 16, 4, 4}, RK[3] = {3, 7, 11}, RD[3] = {1, 3, 5};
     // conv_pre (+ cond(g) folded into the bias); lrelu'd copy feeds ups[0] (1 halo row)
@@ -406,6 +409,7 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
                            7 * H, ACT_NONE);
         g.C2 = upin_pad.plus(512); g.ldc2 = 512; g.act2 = ACT_LRELU01;
     }
+    if (multi_lane) b.wait(1, 0);  // har is consumed by the noise convs
     int Tin = R, cin = 512;
     for (int i = 0; i < 4; ++i) {
         const int u = RATES[i], k = UK[i], p = (k - u) / 2, cout = cin / 2, Tout = Tin * u;
