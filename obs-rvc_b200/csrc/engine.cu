@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -38,8 +39,9 @@ struct DevBuf {
 struct Model {
     Packed packed;  // offsets kept; host copy dropped after upload
     DevBuf dev;
+    int64_t hilo_stride = 0;  // bytes from the fp32 arena to its tf32 hi copy (and again to lo); 0 = none
     bool loaded = false;
-    void unload() { dev.release(); packed = Packed{}; loaded = false; }
+    void unload() { dev.release(); packed = Packed{}; loaded = false; hilo_stride = 0; }
 };
 
 struct PlanKey {
@@ -99,6 +101,7 @@ struct rvc_ctx {
     PlanEntry* last = nullptr;
     uint64_t window = 0, total_launches = 0;
     cudaEvent_t timers[8] = {nullptr};
+    bool allow_umma = true;
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -111,6 +114,7 @@ struct rvc_ctx {
         DeviceBases B;
         B.b[SP_CV] = cv.dev.d; B.b[SP_F0] = f0.dev.d; B.b[SP_SYN] = syn.dev.d; B.b[SP_IDX] = index.d;
         B.b[SP_WORK] = e.work.d; B.b[SP_STATE] = state.d;
+        B.hilo_stride[SP_CV] = cv.hilo_stride; B.hilo_stride[SP_SYN] = syn.hilo_stride;
         return B;
     }
 };
@@ -119,12 +123,18 @@ namespace {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call); } while (0)
 
-int upload(rvc_ctx* ctx, Model& m) {
-    size_t bytes = m.packed.host.size() * sizeof(float);
+int upload(rvc_ctx* ctx, Model& m, bool with_hilo) {
+    size_t bytes = (m.packed.host.size() * sizeof(float) + 1023) & ~size_t(1023);
     m.dev.release();
-    CK(cudaMalloc(&m.dev.d, bytes + 256));
+    CK(cudaMalloc(&m.dev.d, bytes * (with_hilo ? 3 : 1) + 256));
     m.dev.bytes = bytes;
-    CK(cudaMemcpy(m.dev.d, m.packed.host.data(), bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.dev.d, m.packed.host.data(), m.packed.host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (with_hilo) {
+        // tf32 hi / lo copies of the whole arena for the tcgen05 3xTF32 GEMMs (kernels_umma.cu)
+        launch_split_hilo(reinterpret_cast<const float*>(m.dev.d), reinterpret_cast<float*>(m.dev.d + bytes),
+                          reinterpret_cast<float*>(m.dev.d + 2 * bytes), m.packed.host.size(), ctx->streams[0]);
+        m.hilo_stride = int64_t(bytes);
+    }
     CK(cudaDeviceSynchronize());
     std::vector<float>().swap(m.packed.host);
     m.loaded = true;
@@ -189,6 +199,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     PlanOptions opt;
     opt.index_k = ctx->cfg.index_k; opt.upstream_cents_window = ctx->cfg.upstream_cents_window;
     opt.with_index = key.with_index || kind == PLAN_KNN; opt.index_rows = ctx->index_rows; opt.multi_lane = true;
+    opt.allow_umma = ctx->allow_umma;
     auto e = std::make_unique<PlanEntry>();
     std::string err;
     if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.packed : nullptr,
@@ -310,6 +321,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     if (cfg) ctx->cfg = *cfg; else rvc_config_default(&ctx->cfg);
     if (ctx->cfg.index_k <= 0 || ctx->cfg.index_k > 16) { g_create_error = "index_k must be in [1,16]"; return RVC_ERR_INVALID_ARG; }
     ctx->data_path = data_path;
+    { const char* ev = getenv("RVC_UMMA"); ctx->allow_umma = !(ev && ev[0] == '0'); }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) {
@@ -358,7 +370,7 @@ int rvc_load_contentvec(rvc_ctx* ctx, int32_t model_version) {
     if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
     ctx->drop_plans(); ctx->cv.unload();
     if (!pack_contentvec(f, ctx->cv.packed, ctx->cvi, err)) return ctx->fail(RVC_ERR_IO, err);
-    return upload(ctx, ctx->cv);
+    return upload(ctx, ctx->cv, ctx->allow_umma);
 }
 
 int rvc_load_f0(rvc_ctx* ctx, int32_t pitch_algorithm) {
@@ -369,7 +381,7 @@ int rvc_load_f0(rvc_ctx* ctx, int32_t pitch_algorithm) {
     if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
     ctx->drop_plans(); ctx->f0.unload();
     if (!pack_rmvpe(f, ctx->f0.packed, ctx->f0i, err)) return ctx->fail(RVC_ERR_IO, err);
-    return upload(ctx, ctx->f0);
+    return upload(ctx, ctx->f0, false);
 }
 
 int rvc_load_model(rvc_ctx* ctx, const char* model_path) {
@@ -379,7 +391,7 @@ int rvc_load_model(rvc_ctx* ctx, const char* model_path) {
     if (!f.load(model_path, err)) return ctx->fail(RVC_ERR_IO, err);
     ctx->drop_plans(); ctx->syn.unload();
     if (!pack_synth(f, ctx->syn.packed, ctx->syi, err)) return ctx->fail(RVC_ERR_IO, err);
-    return upload(ctx, ctx->syn);
+    return upload(ctx, ctx->syn, ctx->allow_umma);
 }
 
 int rvc_unload_model(rvc_ctx* ctx) {

@@ -37,6 +37,43 @@ __device__ __forceinline__ float apply_act(int act, float v) {
     }
 }
 
+// final accumulator -> output element (bias, activation, residual, masks, scatter modes); mirrors the
+// scalar interpreter in oracle/plan_exec/cpu_exec.cpp
+__device__ __forceinline__ void epilogue_elem(const GemmParams& p, const float* __restrict__ bias, float* C, float* C2,
+                                              const float* R, int m, int n, float acc, float acc_partner) {
+    const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
+    if (p.act == ACT_GATE) {
+        if (n & 1) return;
+        const float v0 = fmaf(p.alpha, acc, bias ? __ldg(bias + n) : 0.f);
+        const float v1 = fmaf(p.alpha, acc_partner, bias ? __ldg(bias + n + 1) : 0.f);
+        float g = tanhf(v0) * sigmoid_f(v1);
+        const int col = n >> 1;
+        if (R) g += R[(long long)m * p.ldr + col];
+        if (masked) g = 0.f;
+        C[(long long)m * p.ldc + col] = g;
+        if (C2) C2[(long long)m * p.ldc2 + col] = masked ? 0.f : apply_act(p.act2, g);
+        return;
+    }
+    float v = apply_act(p.act, fmaf(p.alpha, acc, bias ? __ldg(bias + n) : 0.f));
+    if (p.out_mode == OUT_PLAIN) {
+        if (R) v += R[(long long)m * p.ldr + n];
+        if (masked) v = 0.f;
+        C[(long long)m * p.ldc + n] = v;
+        if (C2) C2[(long long)m * p.ldc2 + n] = masked ? 0.f : apply_act(p.act2, v);
+    } else if (p.out_mode == OUT_PIXSHUF2) {
+        const int qt = m / p.om_a, qf = m - qt * p.om_a;
+        if (qf >= p.om_a - 2) return;
+        const int ph = n / p.om_b, co = n - ph * p.om_b, rt = ph >> 1, rf = ph & 1;
+        C[((long long)(2 * qt + rt) * p.om_c + (2 * qf + rf)) * p.ldc + co] = masked ? 0.f : v;
+    } else {  // OUT_CONVT1D
+        const int r = n / p.om_b, co = n - r * p.om_b;
+        const int o = m * p.om_a + r - p.om_c;
+        if (o < 0 || o >= p.om_d) return;
+        C[(long long)o * p.ldc + co] = v;
+        if (C2) C2[(long long)o * p.ldc2 + co] = apply_act(p.act2, v);
+    }
+}
+
 inline GemmParams make_params(const GemmOp& g, const DeviceBases& B) {
     GemmParams p;
     p.A = B.p<float>(g.A); p.lda = g.lda; p.seg_len = g.seg_len; p.seg_stride = g.seg_stride;

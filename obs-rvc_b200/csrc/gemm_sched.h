@@ -14,18 +14,37 @@
 namespace rvc {
 
 struct GemmSched {
-    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM64/BN128
+    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM64/BN128 (v2);
+                      // 5/6/7: tcgen05 3xTF32 kernel (kernels_umma.cu) with BN = 128/64/32
     int bm = 0, bn = 0, splitk = 1, tiles = 0;
 };
 
 constexpr int GEMM2_BK = 32;
 constexpr int NUM_SMS = 148;
 
-inline GemmSched gemm_schedule(const GemmOp& g) {
+inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     GemmSched s;
     const bool aligned = g.A.off % 16 == 0 && g.W.off % 16 == 0 && g.lda % 4 == 0 && g.seg_len % 4 == 0 &&
                          g.seg_stride % 4 == 0 && g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
     if (!aligned || g.K < 64) return s;  // tiny / oddly aligned contractions stay on the v1 kernel
+    // tensor-core path: dense contractions of ContentVec / synthesizer with at least half a 128-row tile;
+    // RMVPE (SP_F0) stays on exact-fp32 CUDA cores (its 360-bin argmax is a bit-exact parity item)
+    const bool contiguous = g.seg_len >= g.K;
+    if (allow_umma && (g.W.space == SP_CV || g.W.space == SP_SYN) && g.M >= 64 && g.N % 16 == 0 && g.N >= 32 &&
+        (contiguous || (g.seg_len % 32 == 0 && g.K % g.seg_len == 0)) && g.K >= 96) {
+        const int tm = (g.M + 127) / 128;
+        const int nkb = (g.K + 31) / 32;
+        int bn = 128;
+        if (g.N <= 32) bn = 32;
+        else if (g.N <= 64 || tm * ((g.N + 127) / 128) * g.batch < NUM_SMS) bn = 64;
+        s.variant = bn == 128 ? 5 : (bn == 64 ? 6 : 7);
+        s.bm = 128; s.bn = bn;
+        s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
+        const int want = (NUM_SMS + s.tiles - 1) / s.tiles;     // 1 CTA per SM (smem-limited)
+        const int maxsplit = std::max(1, nkb / 4);
+        s.splitk = std::max(1, std::min(std::min(want, maxsplit), 32));
+        return s;
+    }
     if (g.M <= 8) { s.variant = 1; s.bm = 8; s.bn = 256; }
     else if (g.M <= 16) { s.variant = 2; s.bm = 16; s.bn = 128; }
     else if (g.M <= 256) { s.variant = 3; s.bm = 32; s.bn = 64; }

@@ -252,7 +252,12 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);  // kernels_gemm2.cu
 
 int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
-    if (g.sched_variant > 0) return launch_gemm_v2(g, B, stream);
+    if (g.sched_variant >= 5) {
+        if (launch_gemm_umma(g, B, stream)) return 1;
+        // tensor maps unavailable: exact CUDA-core kernel below (no split-K scratch needed)
+    } else if (g.sched_variant > 0) {
+        return launch_gemm_v2(g, B, stream);
+    }
     GemmParams p = make_params(g, B);
     const bool vec = al16(p.A) && al16(p.W) && g.lda % 4 == 0 && g.seg_len % 4 == 0 && g.seg_stride % 4 == 0 &&
                      g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;

@@ -402,6 +402,14 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, long long lds,
     }
 }
 
+__global__ void split_hilo_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[i] = h; lo[i] = v - h;
+    }
+}
+
 inline int grid_for(long long n, int block, int cap = 148 * 8) {
     long long g = (n + block - 1) / block;
     return int(g < 1 ? 1 : (g > cap ? cap : g));
@@ -422,6 +430,11 @@ void init_kernel_attributes() {
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(relattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     init_gemm_v2_attributes();
+    init_umma_attributes();
+}
+
+void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n, cudaStream_t stream) {
+    split_hilo_kernel<<<148 * 8, 256, 0, stream>>>(src, dst_hi, dst_lo, n);
 }
 
 int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t s) {

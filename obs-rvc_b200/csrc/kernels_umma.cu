@@ -1,0 +1,390 @@
+// kernels_umma.cu - tcgen05 / TMEM / TMA implicit GEMM for the dense contractions (sm_100a).
+//
+// Serves the FLOP-heavy GEMMs of the path (ContentVec conv stem + transformer, pos-conv, HiFiGAN
+// convs / transposed convs): CUDA-core fp32 tops out near 25 TFLOP/s on B200, the 5th-gen tensor
+// cores do not.  Parity demands fp32-grade results (F0/kNN bit-exact decisions downstream, 1e-3
+// waveform RMS), so the kernel runs the 3xTF32 error-compensated scheme:
+//     A = A_hi + A_lo,  W = W_hi + W_lo   (hi = fp32 with the 13 low mantissa bits cleared)
+//     D += A_hi.W_hi + A_lo.W_hi + A_hi.W_lo        (dropped term ~2^-22 relative)
+// W_hi / W_lo are precomputed once per model and live in HBM next to the fp32 weights; A_hi / A_lo
+// are produced in shared memory by the (otherwise idle) epilogue warps from the fp32 tile that TMA
+// delivered.  Accumulation is fp32 in TMEM.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer - cp.async.bulk.tensor loads of A (4-D map: the segmented / overlapping
+//              im2col rows of ops.h), W_hi, W_lo into a 3-4 stage SWIZZLE_128B ring, mbarrier tx;
+//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=BN, K=8),
+//              tcgen05.commit releases smem stages / publishes the accumulator;
+//   warps 2-5: hi/lo split of each A stage (generic -> async proxy fence), then the epilogue:
+//              tcgen05.ld 32 lanes x 16 columns, optional split-K (partials to scratch, last CTA per
+//              tile reduces in fixed order), bias / activation / residual / masks / scatter modes.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "gemm_common.cuh"
+#include "gemm_sched.h"
+#include "launch.h"
+
+namespace rvc {
+
+namespace {
+
+using namespace gemmk;
+
+constexpr int UM_BM = 128;
+constexpr int UM_BK = 32;                 // floats per k-block = 128 B = one swizzle row
+constexpr int UM_A_BYTES = UM_BM * 128;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1ll << 28)) __trap();  // a broken pipeline must fail loudly, never hang the GPU
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);   // start address            bits [0,14)
+    d |= uint64_t(1) << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= uint64_t(1024 >> 4) << 32;               // stride byte offset: 8 rows x 128 B   bits [32,46)
+    d |= uint64_t(1) << 46;                       // descriptor version (Blackwell)
+    d |= uint64_t(2) << 61;                       // layout type SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN, int PASSES>
+struct UmmaCfg {
+    static constexpr int W_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = (UM_A_BYTES + W_BYTES) * (PASSES == 3 ? 2 : 1);
+    static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > 6 ? 6 : (196 * 1024 / STAGE_BYTES);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmWlo, GemmParams p) {
+    using Cfg = UmmaCfg<BN, PASSES>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    auto stageA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+    auto stageAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES; };
+    auto stageW = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES * (PASSES == 3 ? 2 : 1); };
+    auto stageWlo = [&](int s) { return stageW(s) + Cfg::W_BYTES; };
+
+    const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
+    const int z = blockIdx.z % p.splitk, bz = blockIdx.z / p.splitk;
+    const int nkb_total = (p.K + UM_BK - 1) / UM_BK;
+    const int kb0 = z * p.kt_per_split, kb1 = min(nkb_total, kb0 + p.kt_per_split);
+    const int nkb = max(0, kb1 - kb0);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 128); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(uint32_t(Cfg::TMEM_COLS)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                mbar_expect_tx(&bar_full[s], UM_A_BYTES + Cfg::W_BYTES * (PASSES == 3 ? 2 : 1));
+                const int kk = (kb0 + i) * UM_BK;
+                const int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
+                tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);
+                tma_load_3d(&tmW, stageW(s), &bar_full[s], kk, n0, bz);
+                if (PASSES == 3) tma_load_3d(&tmWlo, stageWlo(s), &bar_full[s], kk, n0, bz);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(UM_BM >> 4) << 24);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&bar_full[s], ph);
+                if (PASSES == 3) mbar_wait(&bar_conv[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(stageA(s)), a_lo = smem_u32(stageAlo(s));
+                const uint32_t w_hi = smem_u32(stageW(s)), w_lo = smem_u32(stageWlo(s));
+#pragma unroll
+                for (int ks = 0; ks < UM_BK / 8; ++ks) {
+                    const uint32_t off = ks * 32;  // 8 tf32 = 32 B along K inside the swizzle atom
+                    umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(w_hi + off), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                    if (PASSES == 3) {
+                        umma_tf32(tmem_base, umma_desc(a_lo + off), umma_desc(w_hi + off), idesc, 1u);
+                        umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(w_lo + off), idesc, 1u);
+                    }
+                }
+                umma_commit(&bar_empty[s]);  // smem stage reusable once these MMAs have read it
+            }
+            if (nkb > 0) umma_commit(&bar_acc); else mbar_arrive(&bar_acc);
+        }
+    } else {
+        // ===== converter + epilogue warps (128 threads) =====
+        const int ct = tid - 64;
+        if (PASSES == 3) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&bar_full[s], ph);
+                float4* a = reinterpret_cast<float4*>(stageA(s));
+                float4* lo = reinterpret_cast<float4*>(stageAlo(s));
+#pragma unroll
+                for (int j = 0; j < UM_A_BYTES / 16 / 128; ++j) {
+                    const int e = ct + j * 128;
+                    const float4 v = a[e];
+                    float4 h;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    a[e] = h;
+                    lo[e] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
+                mbar_arrive(&bar_conv[s]);
+            }
+        }
+        mbar_wait(&bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int m = m0 + q * 32 + lane;
+        const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+        const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
+        float* C = p.C + bz * p.sC;
+        float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
+        const float* R = p.R ? p.R + bz * p.sR : nullptr;
+        bool finalize = true;
+        if (p.splitk > 1) {
+            float* part = p.scratch + ((long long)(bz * p.splitk + z) * p.M) * p.N;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                if (nkb > 0) tmem_ld16(trow + c0, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+                if (m < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < p.N) __stcg(part + (long long)m * p.N + n, v[j]);
+                    }
+                }
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (ct == 0) {
+                const int tile = (bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                const unsigned ticket = atomicAdd(p.counters + tile, 1u);
+                s_last = (ticket == unsigned(p.splitk - 1)) ? 1 : 0;
+                if (s_last) p.counters[tile] = 0;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            finalize = s_last != 0;
+            if (finalize) __threadfence();
+        }
+        if (finalize) {
+            const float* base = p.splitk > 1 ? p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N : nullptr;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                if (p.splitk > 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        float s = 0.f;
+                        if (m < p.M && n < p.N)
+                            for (int zz = 0; zz < p.splitk; ++zz) s += __ldcg(base + ((long long)zz * p.M + m) * p.N + n);
+                        v[j] = s;
+                    }
+                } else {
+                    tmem_ld16(trow + c0, v);
+                }
+                if (m < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < p.N) epilogue_elem(p, bias, C, C2, R, m, n, v[j], v[j ^ 1]);
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(Cfg::TMEM_COLS)) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool encode(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<float*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, int PASSES>
+bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const float* w_hi, const float* w_lo, cudaStream_t s) {
+    using Cfg = UmmaCfg<BN, PASSES>;
+    CUtensorMap tmA, tmW, tmWlo;
+    const int nseg = (g.seg_len >= g.K) ? 1 : g.K / g.seg_len;
+    const int seg_len = nseg == 1 ? g.K : g.seg_len;
+    const cuuint64_t big = cuuint64_t(1) << 36;  // stride of a size-1 dimension (any multiple of 16)
+    {
+        cuuint64_t dims[4] = {cuuint64_t(seg_len), cuuint64_t(nseg), cuuint64_t(g.M), cuuint64_t(g.batch)};
+        cuuint64_t str[3] = {nseg > 1 ? cuuint64_t(g.seg_stride) * 4 : big, cuuint64_t(g.lda) * 4, g.batch > 1 ? cuuint64_t(g.sA) * 4 : big};
+        cuuint32_t box[4] = {UM_BK, 1, UM_BM, 1};
+        if (!encode(&tmA, p.A, 4, dims, str, box)) return false;
+    }
+    {
+        cuuint64_t dims[3] = {cuuint64_t(g.K), cuuint64_t(g.N), cuuint64_t(g.batch)};
+        cuuint64_t str[2] = {cuuint64_t(g.ldw) * 4, g.batch > 1 ? cuuint64_t(g.sW) * 4 : big};
+        cuuint32_t box[3] = {UM_BK, cuuint32_t(BN), 1};
+        if (!encode(&tmW, w_hi, 3, dims, str, box)) return false;
+        if (!encode(&tmWlo, w_lo, 3, dims, str, box)) return false;
+    }
+    const int nkb = (g.K + UM_BK - 1) / UM_BK;
+    p.kt_per_split = (nkb + g.splitk - 1) / g.splitk;
+    p.seg_len = seg_len;
+    auto kern = umma_gemm_kernel<BN, PASSES>;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + UM_BM - 1) / UM_BM, g.batch * g.splitk);
+    kern<<<grid, 192, Cfg::SMEM_BYTES, s>>>(tmA, tmW, tmWlo, p);
+    return true;
+}
+
+int g_umma_passes = 3;
+
+}  // namespace
+
+void init_umma_attributes() {
+    cudaFuncSetAttribute(umma_gemm_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 3>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 3>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 3>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 1>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 1>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 1>::SMEM_BYTES);
+    const char* e = getenv("RVC_UMMA_PASSES");
+    if (e && e[0] == '1') g_umma_passes = 1;
+}
+
+// returns 0 when the tensor maps could not be encoded (caller falls back to the CUDA-core kernel)
+int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
+    const int64_t hl = B.hilo_stride[g.W.space];
+    if (hl <= 0) return 0;
+    GemmParams p = gemmk::make_params(g, B);
+    const float* w_hi = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + hl);
+    const float* w_lo = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + 2 * hl);
+    const int bn = g.sched_variant == 5 ? 128 : (g.sched_variant == 6 ? 64 : 32);
+    bool ok;
+    if (g_umma_passes == 3) {
+        ok = bn == 128 ? launch_umma_cfg<128, 3>(g, p, w_hi, w_lo, stream)
+           : bn == 64 ? launch_umma_cfg<64, 3>(g, p, w_hi, w_lo, stream) : launch_umma_cfg<32, 3>(g, p, w_hi, w_lo, stream);
+    } else {
+        ok = bn == 128 ? launch_umma_cfg<128, 1>(g, p, p.W, p.W, stream)
+           : bn == 64 ? launch_umma_cfg<64, 1>(g, p, p.W, p.W, stream) : launch_umma_cfg<32, 1>(g, p, p.W, p.W, stream);
+    }
+    return ok ? 1 : 0;
+}
+
+}  // namespace rvc

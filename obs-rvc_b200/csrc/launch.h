@@ -10,6 +10,8 @@ namespace rvc {
 
 struct DeviceBases {
     uint8_t* b[SP_COUNT] = {nullptr};
+    // byte distance from the fp32 weights of a space to their tf32 "hi" copy (and again to "lo"); 0 = none
+    int64_t hilo_stride[SP_COUNT] = {0};
     template <typename T> T* p(const Ref& r) const {
         return r.null() ? nullptr : reinterpret_cast<T*>(b[r.space] + r.off);
     }
@@ -41,5 +43,10 @@ int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t
 // one-time per-process kernel attribute setup (dynamic shared memory opt-in)
 void init_kernel_attributes();
 void init_gemm_v2_attributes();
+void init_umma_attributes();
+// tcgen05 path; returns 0 if the TMA descriptors cannot be built (caller falls back)
+int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);
+// dst_hi[i] = src[i] with the 13 low mantissa bits cleared, dst_lo[i] = src[i] - dst_hi[i]
+void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n, cudaStream_t stream);
 
 }  // namespace rvc

@@ -63,6 +63,7 @@ struct PlanOptions {
     int32_t upstream_cents_window = 0;
     bool with_index = false; int32_t index_rows = 0;
     bool multi_lane = true;  // independent branches on separate stream lanes
+    bool allow_umma = true;  // dense GEMMs on the tcgen05 3xTF32 kernel (needs hi/lo weight copies)
 };
 
 struct Plan {

@@ -23,6 +23,7 @@ struct PB {
     bool ok = true;
     int64_t work = 0;
     int lane = 0;
+    bool allow_umma = true;
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
 
@@ -482,7 +483,7 @@ void schedule_gemms(PB& b) {
     for (Op& op : b.plan.ops) {
         if (op.kind != OP_GEMM) continue;
         GemmOp& g = op.gemm;
-        GemmSched s = gemm_schedule(g);
+        GemmSched s = gemm_schedule(g, b.allow_umma);
         g.sched_variant = s.variant; g.splitk = s.splitk;
         if (s.variant > 0 && s.splitk > 1) {
             g.scratch = b.alloc("", int64_t(s.splitk) * g.batch * g.M * g.N);
@@ -498,6 +499,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
                 std::string& err) {
     plan = Plan{};
     PB b{plan, err};
+    b.allow_umma = opt.allow_umma;
     plan.params = Ref{SP_STATE, StateLayout::off_params};
     plan.cache = Ref{SP_STATE, StateLayout::off_cache};
     plan.pcm = Ref{SP_STATE, StateLayout::off_pcm};

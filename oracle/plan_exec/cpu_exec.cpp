@@ -461,6 +461,7 @@ struct Exec {
     Plan plan;
     RunParams rp{};
     int index_k = 8;
+    bool allow_umma = true;
     Exec() : state(StateLayout::bytes, 0) { rp.uppower = 1.f; rp.noise_mode = 1; }
     Bases bases() {
         Bases B;
@@ -507,7 +508,7 @@ void pe_set_params(void* h, uint64_t seed, int noise_mode, int index_k) {
 int pe_run(void* h, int kind, const float* pcm, int n, int sf16k, int pitch_shift, int skip_head, int return_length) {
     Exec* e = static_cast<Exec*>(h);
     Geometry g{n, sf16k, skip_head, return_length};
-    PlanOptions opt; opt.index_k = e->index_k; opt.with_index = e->index_rows > 0; opt.index_rows = e->index_rows;
+    PlanOptions opt; opt.index_k = e->index_k; opt.allow_umma = e->allow_umma; opt.with_index = e->index_rows > 0; opt.index_rows = e->index_rows;
     if (!build_plan(PlanKind(kind), g, opt, e->has_cv ? &e->cv : nullptr, &e->cvi, e->has_f0 ? &e->f0 : nullptr, &e->f0i,
                     e->has_syn ? &e->syn : nullptr, &e->syi, e->plan, e->err)) return 1;
     e->work.assign(size_t(e->plan.work_bytes), 0);
