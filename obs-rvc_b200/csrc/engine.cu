@@ -687,4 +687,17 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
     return RVC_OK;
 }
 
+int rvc_debug_umma_timing(rvc_ctx* ctx, const char* op_name, long long* out16) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->last) return RVC_ERR_INVALID_ARG;
+    ctx->sync_all();
+    const DeviceBases B = ctx->bases(*ctx->last);
+    for (const Op& op : ctx->last->plan.ops) {
+        if (op.name == op_name) { int n = 0; issue_one(ctx, op, B, ctx->streams[0], &n); issue_one(ctx, op, B, ctx->streams[0], &n); break; }
+    }
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    rvc::umma_debug_read(out16);
+    return RVC_OK;
+}
+
 }  // extern "C"

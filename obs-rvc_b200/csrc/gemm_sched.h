@@ -42,7 +42,9 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
         s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
         const int want = (NUM_SMS + s.tiles - 1) / s.tiles;     // 1 CTA per SM (smem-limited)
         const int maxsplit = std::max(1, nkb / 4);
-        s.splitk = std::max(1, std::min(std::min(want, maxsplit), 32));
+        // split-K group = one thread-block cluster (partials reduced over DSMEM): power of two <= 8
+        s.splitk = 1;
+        while (s.splitk * 2 <= std::min(std::min(want, maxsplit), 8)) s.splitk *= 2;
         return s;
     }
     if (g.M <= 8) { s.variant = 1; s.bm = 8; s.bn = 256; }

@@ -18,6 +18,7 @@
 //   warps 2-5: hi/lo split of each A stage (generic -> async proxy fence), then the epilogue:
 //              tcgen05.ld 32 lanes x 16 columns, optional split-K (partials to scratch, last CTA per
 //              tile reduces in fixed order), bias / activation / residual / masks / scatter modes.
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -26,6 +27,8 @@
 #include "gemm_common.cuh"
 #include "gemm_sched.h"
 #include "launch.h"
+
+namespace cg = cooperative_groups;
 
 namespace rvc {
 
@@ -36,6 +39,8 @@ using namespace gemmk;
 constexpr int UM_BM = 128;
 constexpr int UM_BK = 32;                 // floats per k-block = 128 B = one swizzle row
 constexpr int UM_A_BYTES = UM_BM * 128;   // 16 KB
+constexpr int UM_THREADS = 384;           // 12 warps: TMA, MMA, 4 convert/TMEM-drain warps, 6 extra store warps
+constexpr int UM_WARPS = UM_THREADS / 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -110,6 +115,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ long long g_umma_dbg[16];
+#define UMMA_DBG(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_umma_dbg[i] = clock64(); } while (0)
+
 template <int BN, int PASSES>
 struct UmmaCfg {
     static constexpr int W_BYTES = BN * 128;
@@ -120,15 +128,15 @@ struct UmmaCfg {
 };
 
 template <int BN, int PASSES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(UM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmWlo, GemmParams p) {
     using Cfg = UmmaCfg<BN, PASSES>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int CT_LD = BN + 4;  // staging tile row stride (words): float4-aligned, conflict-free
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_conv[STAGES], bar_empty[STAGES], bar_acc;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,11 +151,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int kb0 = z * p.kt_per_split, kb1 = min(nkb_total, kb0 + p.kt_per_split);
     const int nkb = max(0, kb1 - kb0);
 
+    if (tid == 0) UMMA_DBG(0);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
         if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 128); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 1); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -159,6 +168,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
+    if (tid == 0) UMMA_DBG(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -173,6 +183,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_3d(&tmW, stageW(s), &bar_full[s], kk, n0, bz);
                 if (PASSES == 3) tma_load_3d(&tmWlo, stageWlo(s), &bar_full[s], kk, n0, bz);
             }
+            UMMA_DBG(2);
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -181,7 +192,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
                 mbar_wait(&bar_full[s], ph);
+                if (i == 0) UMMA_DBG(3);
                 if (PASSES == 3) mbar_wait(&bar_conv[s], ph);
+                if (i == 0) UMMA_DBG(4);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_u32(stageA(s)), a_lo = smem_u32(stageAlo(s));
                 const uint32_t w_hi = smem_u32(stageW(s)), w_lo = smem_u32(stageWlo(s));
@@ -197,99 +210,140 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_commit(&bar_empty[s]);  // smem stage reusable once these MMAs have read it
             }
             if (nkb > 0) umma_commit(&bar_acc); else mbar_arrive(&bar_acc);
+            UMMA_DBG(5);
         }
-    } else {
-        // ===== converter + epilogue warps (128 threads) =====
+    } else if (warp < 6) {
+        // ===== converter + TMEM-drain warps (128 threads) =====
         const int ct = tid - 64;
         if (PASSES == 3) {
-            for (int i = 0; i < nkb; ++i) {
+            // hi/lo split of the A tile: k-block i belongs to converter warp i % 4, so up to four stages are
+            // converted concurrently (each warp streams a whole 16 KB stage: latency, not bandwidth, bound)
+            const int cw = warp - 2;
+            for (int i = cw; i < nkb; i += 4) {
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
                 mbar_wait(&bar_full[s], ph);
                 float4* a = reinterpret_cast<float4*>(stageA(s));
                 float4* lo = reinterpret_cast<float4*>(stageAlo(s));
+#pragma unroll 1
+                for (int b = 0; b < UM_A_BYTES / 16 / 32; b += 8) {
+                    float4 v[8];
 #pragma unroll
-                for (int j = 0; j < UM_A_BYTES / 16 / 128; ++j) {
-                    const int e = ct + j * 128;
-                    const float4 v = a[e];
-                    float4 h;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                    a[e] = h;
-                    lo[e] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                    for (int j = 0; j < 8; ++j) v[j] = a[(b + j) * 32 + lane];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 h;
+                        h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
+                        h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
+                        h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
+                        h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
+                        a[(b + j) * 32 + lane] = h;
+                        lo[(b + j) * 32 + lane] = make_float4(v[j].x - h.x, v[j].y - h.y, v[j].z - h.z, v[j].w - h.w);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
-                mbar_arrive(&bar_conv[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_conv[s]);
             }
         }
+        if (ct == 0) UMMA_DBG(6);
         mbar_wait(&bar_acc, 0);
+        if (ct == 0) UMMA_DBG(7);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // accumulator: TMEM (one row per lane) -> padded fp32 staging tile in the now idle pipeline smem
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-        const int m = m0 + q * 32 + lane;
+        const int row = q * 32 + lane;
         const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+        float* ct_row = reinterpret_cast<float*>(smem) + row * CT_LD;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16];
+            if (nkb > 0) tmem_ld16(trow + c0, v);
+            else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(ct_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (ct == 0) UMMA_DBG(11);
+    }
+    // ---- staged tile -> global: lanes along N (coalesced); split-K partial tiles are reduced across the
+    //      cluster through distributed shared memory, each CTA finishing 128/splitk rows ----
+    if (tid == 0) UMMA_DBG(8);
+    if (p.splitk > 1) cg::this_cluster().sync(); else __syncthreads();
+    if (tid == 64) UMMA_DBG(12);
+    {
         const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
         float* C = p.C + bz * p.sC;
         float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
         const float* R = p.R ? p.R + bz * p.sR : nullptr;
-        bool finalize = true;
-        if (p.splitk > 1) {
-            float* part = p.scratch + ((long long)(bz * p.splitk + z) * p.M) * p.N;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                if (nkb > 0) tmem_ld16(trow + c0, v);
-                else {
+        const float* Ct = reinterpret_cast<const float*>(smem);
+        const int rows_per = UM_BM / p.splitk;
+        const int r_begin = z * rows_per, r_end = r_begin + rows_per;
+        const bool gate = p.act == ACT_GATE;
+        const float* peers[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                }
-                if (m < p.M) {
+        for (int zz = 0; zz < 8; ++zz)
+            peers[zz] = (p.splitk > 1 && zz < p.splitk) ? cg::this_cluster().map_shared_rank(Ct, zz) : Ct;
+        if (p.vec_store) {
+            // fast path (plain row-major output, no gate): float4 per lane, BN/4 lanes per row
+            constexpr int LPR = BN / 4, RPI = 32 / LPR;
+            const int sub = lane / LPR, c4 = (lane % LPR) * 4, n = n0 + c4;
+            const bool ncol = n < p.N;  // N % 4 == 0 on this path
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias && ncol) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            for (int row = r_begin + warp * RPI + sub; row < r_end; row += UM_WARPS * RPI) {
+                const int m = m0 + row;
+                if (m >= p.M || !ncol) continue;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c0 + j;
-                        if (n < p.N) __stcg(part + (long long)m * p.N + n, v[j]);
+                for (int zz = 0; zz < 8; ++zz) {
+                    if (zz < p.splitk) {
+                        const float4 t = *reinterpret_cast<const float4*>(peers[zz] + row * CT_LD + c4);
+                        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
                     }
+                }
+                float4 v;
+                v.x = apply_act(p.act, fmaf(p.alpha, a.x, bv.x)); v.y = apply_act(p.act, fmaf(p.alpha, a.y, bv.y));
+                v.z = apply_act(p.act, fmaf(p.alpha, a.z, bv.z)); v.w = apply_act(p.act, fmaf(p.alpha, a.w, bv.w));
+                if (R) {
+                    const float4 r = *reinterpret_cast<const float4*>(R + (long long)m * p.ldr + n);
+                    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                }
+                const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
+                if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(C + (long long)m * p.ldc + n) = v;
+                if (C2) {
+                    float4 w;
+                    w.x = masked ? 0.f : apply_act(p.act2, v.x); w.y = masked ? 0.f : apply_act(p.act2, v.y);
+                    w.z = masked ? 0.f : apply_act(p.act2, v.z); w.w = masked ? 0.f : apply_act(p.act2, v.w);
+                    *reinterpret_cast<float4*>(C2 + (long long)m * p.ldc2 + n) = w;
                 }
             }
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (ct == 0) {
-                const int tile = (bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-                const unsigned ticket = atomicAdd(p.counters + tile, 1u);
-                s_last = (ticket == unsigned(p.splitk - 1)) ? 1 : 0;
-                if (s_last) p.counters[tile] = 0;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            finalize = s_last != 0;
-            if (finalize) __threadfence();
-        }
-        if (finalize) {
-            const float* base = p.splitk > 1 ? p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N : nullptr;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                if (p.splitk > 1) {
+        } else {
+            for (int row = r_begin + warp; row < r_end; row += UM_WARPS) {
+                const int m = m0 + row;
+                if (m >= p.M) break;
+                for (int col = lane; col < BN; col += 32) {
+                    const int n = n0 + col;
+                    float v = 0.f, vp = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c0 + j;
-                        float s = 0.f;
-                        if (m < p.M && n < p.N)
-                            for (int zz = 0; zz < p.splitk; ++zz) s += __ldcg(base + ((long long)zz * p.M + m) * p.N + n);
-                        v[j] = s;
+                    for (int zz = 0; zz < 8; ++zz) {
+                        if (zz < p.splitk) {
+                            v += peers[zz][row * CT_LD + col];
+                            if (gate) vp += peers[zz][row * CT_LD + (col ^ 1)];
+                        }
                     }
-                } else {
-                    tmem_ld16(trow + c0, v);
-                }
-                if (m < p.M) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c0 + j;
-                        if (n < p.N) epilogue_elem(p, bias, C, C2, R, m, n, v[j], v[j ^ 1]);
-                    }
+                    if (n < p.N) epilogue_elem(p, bias, C, C2, R, m, n, v, vp);
                 }
             }
         }
     }
+    if (tid == 64) UMMA_DBG(13);
+    if (p.splitk > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's staging tile
+    if (tid == 64) UMMA_DBG(9);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (tid == 0) UMMA_DBG(10);
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(Cfg::TMEM_COLS)) : "memory");
     }
@@ -347,9 +401,21 @@ bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const float* w_hi, const fl
     const int nkb = (g.K + UM_BK - 1) / UM_BK;
     p.kt_per_split = (nkb + g.splitk - 1) / g.splitk;
     p.seg_len = seg_len;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    p.vec_store = (g.out_mode == OUT_PLAIN && g.act != ACT_GATE && g.N % 4 == 0 && al16(p.C) && g.ldc % 4 == 0 && g.sC % 4 == 0 &&
+                   (!p.C2 || (al16(p.C2) && g.ldc2 % 4 == 0)) && (!p.R || (al16(p.R) && g.ldr % 4 == 0 && g.sR % 4 == 0)) &&
+                   (!p.bias || (al16(p.bias) && g.sBias % 4 == 0))) ? 1 : 0;
     auto kern = umma_gemm_kernel<BN, PASSES>;
-    dim3 grid((g.N + BN - 1) / BN, (g.M + UM_BM - 1) / UM_BM, g.batch * g.splitk);
-    kern<<<grid, 192, Cfg::SMEM_BYTES, s>>>(tmA, tmW, tmWlo, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + UM_BM - 1) / UM_BM, g.batch * g.splitk);
+    cfg.blockDim = dim3(UM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K group = one thread-block cluster along z
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = unsigned(g.splitk);
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmWlo, p) != cudaSuccess) return false;
     return true;
 }
 
@@ -367,6 +433,8 @@ void init_umma_attributes() {
     const char* e = getenv("RVC_UMMA_PASSES");
     if (e && e[0] == '1') g_umma_passes = 1;
 }
+
+void umma_debug_read(long long* out) { cudaMemcpyFromSymbol(out, g_umma_dbg, sizeof(long long) * 16); }
 
 // returns 0 when the tensor maps could not be encoded (caller falls back to the CUDA-core kernel)
 int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {

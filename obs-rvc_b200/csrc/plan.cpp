@@ -485,7 +485,7 @@ void schedule_gemms(PB& b) {
         GemmOp& g = op.gemm;
         GemmSched s = gemm_schedule(g, b.allow_umma);
         g.sched_variant = s.variant; g.splitk = s.splitk;
-        if (s.variant > 0 && s.splitk > 1) {
+        if (s.variant > 0 && s.variant < 5 && s.splitk > 1) {  // v2 only: the tcgen05 kernel reduces over DSMEM
             g.scratch = b.alloc("", int64_t(s.splitk) * g.batch * g.M * g.N);
             g.counters = b.alloc("", s.tiles, true);
         }
