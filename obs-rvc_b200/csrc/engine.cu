@@ -654,13 +654,22 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
         if (op.kind == OP_WAIT || op.kind == OP_FILL) continue;
         if (op.kind == OP_F0POST) continue;  // stateful (rolls the pitch cache)
         int n = 0;
-        issue_one(ctx, op, B, s, &n);  // warm
-        CK(cudaEventRecord(t0, s));
+        issue_one(ctx, op, B, s, &n);  // warm (also sets kernel attributes outside capture)
+        CK(cudaStreamSynchronize(s));
+        // `iters` launches captured into one graph: device time without host launch overhead
+        cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+        CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         for (int i = 0; i < iters; ++i) issue_one(ctx, op, B, s, &n);
+        CK(cudaStreamEndCapture(s, &g));
+        CK(cudaGraphInstantiate(&ge, g, 0));
+        CK(cudaGraphLaunch(ge, s));  // warm replay
+        CK(cudaEventRecord(t0, s));
+        CK(cudaGraphLaunch(ge, s));
         CK(cudaEventRecord(t1, s));
         CK(cudaEventSynchronize(t1));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, t0, t1));
+        cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
         double flops = 0, wbytes = 0, iobytes = 0; long long grid = 0;
         if (op.kind == OP_GEMM) {
             const GemmOp& g = op.gemm;
@@ -693,10 +702,11 @@ int rvc_debug_umma_timing(rvc_ctx* ctx, const char* op_name, long long* out16) {
     ctx->sync_all();
     const DeviceBases B = ctx->bases(*ctx->last);
     for (const Op& op : ctx->last->plan.ops) {
-        if (op.name == op_name) { int n = 0; issue_one(ctx, op, B, ctx->streams[0], &n); issue_one(ctx, op, B, ctx->streams[0], &n); break; }
+        std::string want(op_name); if (want.size() > 3 && want.substr(want.size() - 3) == "@v2") want = want.substr(0, want.size() - 3);
+        if (op.name == want) { int n = 0; issue_one(ctx, op, B, ctx->streams[0], &n); issue_one(ctx, op, B, ctx->streams[0], &n); break; }
     }
     CK(cudaStreamSynchronize(ctx->streams[0]));
-    rvc::umma_debug_read(out16);
+    if (std::string(op_name).find("@v2") != std::string::npos) rvc::v2_debug_read(out16); else rvc::umma_debug_read(out16);
     return RVC_OK;
 }
 

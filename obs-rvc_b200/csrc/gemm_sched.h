@@ -50,11 +50,10 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     if (g.M <= 8) { s.variant = 1; s.bm = 8; s.bn = 256; }
     else if (g.M <= 16) { s.variant = 2; s.bm = 16; s.bn = 128; }
     else if (g.M <= 256) { s.variant = 3; s.bm = 32; s.bn = 64; }
-    else { s.variant = 4; s.bm = 64; s.bn = 128; }
+    else { s.variant = 3; s.bm = 32; s.bn = 64; }
     // narrow outputs: do not waste a 256/128-wide tile on a 32..64-column problem
     if (s.variant == 1 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
     if (s.variant == 2 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
-    if (s.variant == 4 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
     const int tm = (g.M + s.bm - 1) / s.bm, tn = (g.N + s.bn - 1) / s.bn;
     s.tiles = tm * tn * g.batch;
     const int nkt = (g.K + GEMM2_BK - 1) / GEMM2_BK;

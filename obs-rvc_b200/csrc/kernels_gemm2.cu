@@ -32,18 +32,27 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, i
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int TM, int WM, int WN, int TN, int STAGES>
+__device__ long long g_v2_dbg[16];
+#define V2_DBG(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) g_v2_dbg[i] = clock64(); } while (0)
+
+// BM x BN output tile, 8 warps.  Inside a k-tile (BK = 32 = 8 k-quads) warp w owns k-quad w and
+// accumulates the WHOLE tile for it (lane <-> column, BM rows x BN/32 columns = 64 accumulators):
+// per k-tile a warp issues BM broadcast LDS.128 + BN/32 conflict-free LDS.128 for 4*64 FMAs, i.e. the
+// tile runs at the FMA rate instead of the shared-memory wavefront rate even at one CTA per SM.
+// The eight per-warp partial tiles are summed through shared memory in fixed warp order.
+template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
-    constexpr int BM = TM * WM, BN = 32 * TN * WN;
-    static_assert(WM * WN == 8, "8 warps");
+    constexpr int TN = BN / 32;
+    static_assert(BM * TN == 64, "64 accumulators per thread");
     constexpr int STAGE_FLOATS = (BM + BN) * LDS2;
     constexpr int CHUNKS = (BM + BN) * (BK2 / 4);          // 16-byte chunks per stage
     constexpr int CPT = (CHUNKS + 255) / 256;              // chunks per thread
+    constexpr int RS = 256 / BN > 0 ? 256 / BN : 1;        // row stride of the final thread->output map
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_last;
 
+    V2_DBG(0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp / WN, wn = warp % WN;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int z = blockIdx.z % p.splitk, bz = blockIdx.z / p.splitk;
     const float* __restrict__ A = p.A + bz * p.sA;
@@ -51,6 +60,7 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
     const int nkt_total = (p.K + BK2 - 1) / BK2;
     const int kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split);
     const int nkt = max(0, kt1 - kt0);
+    const bool contiguous = p.seg_len >= p.K;
 
     // per-thread chunk descriptors (row base pointers are k-invariant)
     const float* cbase[CPT]; int ckc[CPT]; int cdst[CPT]; bool cisA[CPT], cvalid[CPT];
@@ -80,7 +90,7 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
             const float* src = p.W;  // any valid address when zero-filling
             int bytes = 0;
             if (cbase[i] && kk < p.K) {
-                if (cisA[i]) {
+                if (cisA[i] && !contiguous) {
                     const int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
                     src = cbase[i] + (long long)seg * p.seg_stride + within;
                 } else {
@@ -92,9 +102,10 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         }
     };
 
-    float acc[TM][TN];
+    V2_DBG(1);
+    float acc[BM][TN];
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+    for (int i = 0; i < BM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
@@ -103,50 +114,64 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         if (s < nkt) load_stage(s, kt0 + s);
         cp_async_commit();
     }
+    V2_DBG(2);
     for (int kt = 0; kt < nkt; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
+        if (kt == 0) V2_DBG(3);
+        if (kt == 1) V2_DBG(4);
         if (kt + STAGES - 1 < nkt) load_stage((kt + STAGES - 1) % STAGES, kt0 + kt + STAGES - 1);
         cp_async_commit();
-        const float* As = smem + (kt % STAGES) * STAGE_FLOATS + (wm * TM) * LDS2;
-        const float* Ws = smem + (kt % STAGES) * STAGE_FLOATS + (BM + wn * 32 * TN + lane) * LDS2;
+        const float* As = smem + (kt % STAGES) * STAGE_FLOATS + warp * 4;
+        const float* Ws = smem + (kt % STAGES) * STAGE_FLOATS + (BM + lane) * LDS2 + warp * 4;
+        float4 b[TN];
 #pragma unroll
-        for (int kq = 0; kq < BK2 / 4; ++kq) {
-            float4 b[TN];
+        for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Ws + j * 32 * LDS2);
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Ws + j * 32 * LDS2 + kq * 4);
+        for (int i = 0; i < BM; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(As + i * LDS2);
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                const float4 a = *reinterpret_cast<const float4*>(As + i * LDS2 + kq * 4);
-#pragma unroll
-                for (int j = 0; j < TN; ++j) {
-                    acc[i][j] = fmaf(a.x, b[j].x, acc[i][j]);
-                    acc[i][j] = fmaf(a.y, b[j].y, acc[i][j]);
-                    acc[i][j] = fmaf(a.z, b[j].z, acc[i][j]);
-                    acc[i][j] = fmaf(a.w, b[j].w, acc[i][j]);
-                }
+            for (int j = 0; j < TN; ++j) {
+                acc[i][j] = fmaf(a.x, b[j].x, acc[i][j]);
+                acc[i][j] = fmaf(a.y, b[j].y, acc[i][j]);
+                acc[i][j] = fmaf(a.z, b[j].z, acc[i][j]);
+                acc[i][j] = fmaf(a.w, b[j].w, acc[i][j]);
             }
         }
     }
     cp_async_wait<0>();
+    __syncthreads();  // every warp is done with the stage buffers: reuse them for the partial tiles
+    V2_DBG(5);
+    float* red = smem;  // [8 warps][BM][BN]
+#pragma unroll
+    for (int i = 0; i < BM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) red[(warp * BM + i) * BN + j * 32 + lane] = acc[i][j];
+    __syncthreads();
+    // final map: thread t owns column t % BN and 8 rows (stride RS): coalesced along N
+    const int col = tid % BN, r0 = tid / BN;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = r0 + i * RS;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[(w * BM + row) * BN + col];
+        v[i] = s;
+    }
 
     const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
     float* C = p.C + bz * p.sC;
     float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
     const float* R = p.R ? p.R + bz * p.sR : nullptr;
-    const int mbase = m0 + wm * TM, nbase = n0 + wn * 32 * TN + lane;
+    const int n = n0 + col;
 
     if (p.splitk > 1) {
         float* part = p.scratch + ((long long)(bz * p.splitk + z) * p.M) * p.N;
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            const int m = mbase + i;
-            if (m >= p.M) continue;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int n = nbase + j * 32;
-                if (n < p.N) __stcg(part + (long long)m * p.N + n, acc[i][j]);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + r0 + i * RS;
+            if (m < p.M && n < p.N) __stcg(part + (long long)m * p.N + n, v[i]);
         }
         __threadfence();
         __syncthreads();
@@ -157,39 +182,64 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
             if (s_last) p.counters[tile] = 0;  // self-cleaning for the next launch / graph replay
         }
         __syncthreads();
+        V2_DBG(6);
         if (!s_last) return;
         __threadfence();
         const float* base = p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N;
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            const int m = mbase + i;
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int zz = 0; zz < p.splitk; ++zz) {
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int n = nbase + j * 32;
-                float s = 0.f;
-                if (m < p.M && n < p.N)
-                    for (int zz = 0; zz < p.splitk; ++zz) s += __ldcg(base + ((long long)zz * p.M + m) * p.N + n);
-                acc[i][j] = s;
+            for (int i = 0; i < 8; ++i) {  // 8 independent loads in flight per thread
+                const int m = m0 + r0 + i * RS;
+                if (m < p.M && n < p.N) v[i] += __ldcg(base + ((long long)zz * p.M + m) * p.N + n);
             }
         }
     }
+    // epilogue: residual values are fetched up front (R may alias C for in-place accumulation, which
+    // would otherwise serialise every load behind the previous store)
+    const bool plain = p.out_mode == OUT_PLAIN;
+    const bool gate = p.act == ACT_GATE;
+    float rv[8];
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int m = mbase + i;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + r0 + i * RS;
+        const int rc = gate ? (n >> 1) : n;
+        rv[i] = (R && plain && m < p.M && n < p.N && !(gate && (n & 1))) ? R[(long long)m * p.ldr + rc] : 0.f;
+    }
+    const float bn_ = (bias && n < p.N) ? __ldg(bias + n) : 0.f;
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-            const int n = nbase + j * 32;
-            const float partner = __shfl_xor_sync(0xffffffffu, acc[i][j], 1);
-            if (m < p.M && n < p.N) epilogue_elem(p, bias, C, C2, R, m, n, acc[i][j], partner);
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + r0 + i * RS;
+        const float partner = __shfl_xor_sync(0xffffffffu, v[i], 1);
+        if (m >= p.M || n >= p.N) continue;
+        if (plain && !gate) {
+            float o = apply_act(p.act, fmaf(p.alpha, v[i], bn_)) + rv[i];
+            const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
+            if (masked) o = 0.f;
+            C[(long long)m * p.ldc + n] = o;
+            if (C2) C2[(long long)m * p.ldc2 + n] = masked ? 0.f : apply_act(p.act2, o);
+        } else if (plain && gate) {
+            if (n & 1) continue;
+            const float v1 = fmaf(p.alpha, partner, bias ? __ldg(bias + n + 1) : 0.f);
+            float o = tanhf(fmaf(p.alpha, v[i], bn_)) * sigmoid_f(v1) + rv[i];
+            const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
+            if (masked) o = 0.f;
+            C[(long long)m * p.ldc + (n >> 1)] = o;
+            if (C2) C2[(long long)m * p.ldc2 + (n >> 1)] = masked ? 0.f : apply_act(p.act2, o);
+        } else {
+            epilogue_elem(p, bias, C, C2, nullptr, m, n, v[i], partner);
         }
     }
+    V2_DBG(7);
 }
 
-template <int TM, int WM, int WN, int TN, int STAGES>
+template <int BM, int BN, int STAGES>
 void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
-    constexpr int BM = TM * WM, BN = 32 * TN * WN;
-    constexpr size_t smem = sizeof(float) * size_t(STAGES) * (BM + BN) * LDS2;
-    auto kern = gemm_v2_kernel<TM, WM, WN, TN, STAGES>;
+    constexpr size_t stage_bytes = sizeof(float) * size_t(STAGES) * (BM + BN) * LDS2;
+    constexpr size_t red_bytes = sizeof(float) * 8 * BM * BN;
+    constexpr size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
+    auto kern = gemm_v2_kernel<BM, BN, STAGES>;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
     const int nkt = (g.K + BK2 - 1) / BK2;
@@ -203,20 +253,20 @@ void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
 int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
     GemmParams p = gemmk::make_params(g, B);
     switch (g.sched_variant) {
-        case 1: launch_v2<8, 1, 8, 1, 3>(g, p, stream); break;
-        case 2: launch_v2<8, 2, 4, 1, 4>(g, p, stream); break;
-        case 3: launch_v2<8, 4, 2, 1, 4>(g, p, stream); break;
-        default: launch_v2<16, 4, 2, 2, 3>(g, p, stream); break;
+        case 1: launch_v2<8, 256, 3>(g, p, stream); break;
+        case 2: launch_v2<16, 128, 4>(g, p, stream); break;
+        default: launch_v2<32, 64, 4>(g, p, stream); break;
     }
     return 1;
 }
 
+void v2_debug_read(long long* out) { cudaMemcpyFromSymbol(out, g_v2_dbg, sizeof(long long) * 16); }
+
 // instantiates every variant's attribute once, outside stream capture
 void init_gemm_v2_attributes() {
-    cudaFuncSetAttribute(gemm_v2_kernel<8, 1, 8, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 3 * (8 + 256) * LDS2));
-    cudaFuncSetAttribute(gemm_v2_kernel<8, 2, 4, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 4 * (16 + 128) * LDS2));
-    cudaFuncSetAttribute(gemm_v2_kernel<8, 4, 2, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 4 * (32 + 64) * LDS2));
-    cudaFuncSetAttribute(gemm_v2_kernel<16, 4, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 3 * (64 + 128) * LDS2));
+    cudaFuncSetAttribute(gemm_v2_kernel<8, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 3 * (8 + 256) * LDS2));
+    cudaFuncSetAttribute(gemm_v2_kernel<16, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 4 * (16 + 128) * LDS2));
+    cudaFuncSetAttribute(gemm_v2_kernel<32, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
 }
 
 }  // namespace rvc

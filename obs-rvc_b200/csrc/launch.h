@@ -44,7 +44,8 @@ int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t
 void init_kernel_attributes();
 void init_gemm_v2_attributes();
 void init_umma_attributes();
-void umma_debug_read(long long* out);  // phase timestamps of the last tcgen05 GEMM CTA (0,0,0)
+void umma_debug_read(long long* out);
+void v2_debug_read(long long* out);  // phase timestamps of the last tcgen05 GEMM CTA (0,0,0)
 // tcgen05 path; returns 0 if the TMA descriptors cannot be built (caller falls back)
 int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);
 // dst_hi[i] = src[i] with the 13 low mantissa bits cleared, dst_lo[i] = src[i] - dst_hi[i]
