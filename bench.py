@@ -38,6 +38,16 @@ WORKLOAD = ("configs[1]: single stream batch=1, ContentVec-768 + RMVPE + 40k x 7
             "rate 0.5) + NSF-HiFiGAN 40k; 35840-sample window advanced by 2560")
 
 
+def shard_streams(n_streams: int, rank: int, world: int):
+    """Stream s lives on rank s mod world for its whole life (its pitch cache is device state)."""
+    return [s for s in range(n_streams) if s % world == rank]
+
+
+def aggregate_throughput(steps: int, world: int, max_seconds: float) -> float:
+    """Whole-job windows/s: every rank processed `steps` windows; time = MAX over ranks."""
+    return world * steps / max_seconds
+
+
 def data_dir():
     from oracle import weights
     root = os.path.join(tempfile.gettempdir(), "rvc_b200_data_seed7")
@@ -206,7 +216,7 @@ def main():
         dev_ms_max = float(t.item())
     else:
         dev_ms_max = dev_ms
-    value = world * args.steps / (dev_ms_max * 1e-3)
+    value = aggregate_throughput(args.steps, world, dev_ms_max * 1e-3)
 
     # ---- e2e: host buffers through the C ABI call, one window in flight -------------------------
     eng.reset_state()
@@ -229,7 +239,7 @@ def main():
         e2e_s = float(t.item())
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    e2e = world * args.steps / e2e_s
+    e2e = aggregate_throughput(args.steps, world, e2e_s)
 
     # ---- roofline of the dominant kernel (rank 0): per-op device times via CUDA events ----------
     roof = None

@@ -127,15 +127,24 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         float4 b[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Ws + j * 32 * LDS2);
+        // rows in groups of RG: the RG broadcast loads are issued together and the FMAs are ordered
+        // so that consecutive instructions hit different accumulators (FMA latency 4 is covered)
+        constexpr int RG = BM >= 8 ? 8 : BM;
 #pragma unroll
-        for (int i = 0; i < BM; ++i) {
-            const float4 a = *reinterpret_cast<const float4*>(As + i * LDS2);
+        for (int i0 = 0; i0 < BM; i0 += RG) {
+            float4 a[RG];
+#pragma unroll
+            for (int r = 0; r < RG; ++r) a[r] = *reinterpret_cast<const float4*>(As + (i0 + r) * LDS2);
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                acc[i][j] = fmaf(a.x, b[j].x, acc[i][j]);
-                acc[i][j] = fmaf(a.y, b[j].y, acc[i][j]);
-                acc[i][j] = fmaf(a.z, b[j].z, acc[i][j]);
-                acc[i][j] = fmaf(a.w, b[j].w, acc[i][j]);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].x, b[j].x, acc[i0 + r][j]);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].y, b[j].y, acc[i0 + r][j]);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].z, b[j].z, acc[i0 + r][j]);
+#pragma unroll
+                for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].w, b[j].w, acc[i0 + r][j]);
             }
         }
     }

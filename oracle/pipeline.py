@@ -130,12 +130,13 @@ class RvcInfer:
         first = min(skip_head // 2, T - 1)
         last = min((skip_head + return_length - 1) // 2, T - 1)
         if self.index is not None and self.index_rate > 0.0 and return_length > 0:
-            blended, d2, ix = knn.blend(self.index, raw[first:last + 1], self.index_k,
-                                        self.index_rate)
+            queries = raw[first:last + 1].copy()
+            blended, d2, ix = knn.blend(self.index, queries, self.index_k, self.index_rate)
             raw = raw.copy()
             raw[first:last + 1] = blended
             self.last["knn_idx"] = ix
             self.last["knn_d2"] = d2
+            self.last["knn_q"] = queries
         feats = dsp.extend_feature_2x(raw)
         phone = feats[skip_head:skip_head + return_length]             # rvc.rs:155
         shift = 0 if pitch_shift is None else int(pitch_shift)         # rvc.rs:163
