@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="also dump per-op device times to gpurun_out/")
+    ap.add_argument("--streams", type=int, default=8,
+                    help="supplementary: independent live streams per GPU sharing one set of weights (configs[3]); 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,6 +243,45 @@ def main():
     sampler.join(timeout=2)
     e2e = aggregate_throughput(args.steps, world, e2e_s)
 
+    # ---- supplementary: S independent streams on this GPU (configs[3] shape: 8 per GPU), weights shared --
+    multi = None
+    if args.streams > 1:
+        engs = [eng]
+        for i in range(1, args.streams):
+            e2 = rvc_b200.RvcInfer(paths["data"], device=local_rank, noise_seed=rank * 1000 + i)
+            e2.load_contentvec(2); e2.load_f0(1); e2.load_model(paths["model"]); e2.load_index(paths["index"], 0.5)
+            engs.append(e2)
+        outs = [torch.empty(out_len, dtype=torch.float32, device=dev) for _ in engs]
+        ksteps = max(20, args.steps // 4)
+
+        def step_all(i):
+            for e_, o_ in zip(engs, outs):
+                e_.infer_ptr(pcm_dev.data_ptr() + 4 * (i % total) * sf, n16k, sf, 12, skip, R, o_.data_ptr(), out_len, True)
+
+        for i in range(5):
+            step_all(i)
+        for e_ in engs:
+            e_.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            step_all(5 + i)
+        for e_ in engs:
+            e_.sync()
+        torch.cuda.synchronize(dev)
+        ms_t = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([ms_t], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_t = float(t.item())
+        multi = {"streams_per_gpu": args.streams, "value": world * args.streams * ksteps / ms_t, "unit": UNIT,
+                 "ms_per_round": ms_t / ksteps * 1e3,
+                 "timing": "host wall clock around K rounds of S async windows, device synchronised on both sides"}
+        for e_ in engs[1:]:
+            e_.close()
+
     # ---- roofline of the dominant kernel (rank 0): per-op device times via CUDA events ----------
     roof = None
     prof = None
@@ -285,6 +326,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n16k * 4, "d2h_bytes_per_step": out_len * 4},
             "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_b,
+            "multi_stream": multi,
         }
         print(json.dumps(line))
     eng.close()

@@ -16,8 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/stat.h>
+
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -36,13 +39,44 @@ struct DevBuf {
     void release() { if (d) cudaFree(d); d = nullptr; bytes = 0; }
 };
 
-struct Model {
+// Immutable weights of one model file, resident in HBM.  Shared (by path) between all contexts of a
+// process on the same device: independent streams replicate state, never weights.
+struct ModelData {
     Packed packed;  // offsets kept; host copy dropped after upload
     DevBuf dev;
     int64_t hilo_stride = 0;  // bytes from the fp32 arena to its tf32 hi copy (and again to lo); 0 = none
-    bool loaded = false;
-    void unload() { dev.release(); packed = Packed{}; loaded = false; hilo_stride = 0; }
+    CvInfo cvi; F0Info f0i; SynInfo syi;
+    int rows = 0, cols = 0;   // retrieval index only
+    ~ModelData() { dev.release(); }
 };
+
+struct Model {
+    std::shared_ptr<ModelData> d;
+    bool loaded = false;
+    Packed& packed_ref() { return d->packed; }
+    void unload() { d.reset(); loaded = false; }
+};
+
+std::mutex g_model_mu;
+std::map<std::string, std::weak_ptr<ModelData>> g_model_cache;
+
+std::string model_key(int device, const std::string& path, bool hilo) {
+    struct stat st{};
+    long long sz = 0, mt = 0;
+    if (stat(path.c_str(), &st) == 0) { sz = (long long)st.st_size; mt = (long long)st.st_mtime; }
+    return std::to_string(device) + "|" + path + "|" + std::to_string(sz) + "|" + std::to_string(mt) + (hilo ? "|hilo" : "");
+}
+
+std::shared_ptr<ModelData> cache_lookup(const std::string& key) {
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    auto it = g_model_cache.find(key);
+    if (it == g_model_cache.end()) return nullptr;
+    return it->second.lock();
+}
+void cache_store(const std::string& key, const std::shared_ptr<ModelData>& d) {
+    std::lock_guard<std::mutex> lk(g_model_mu);
+    g_model_cache[key] = d;
+}
 
 struct PlanKey {
     int kind; Geometry g; int with_index; int index_rows; int k;
@@ -95,7 +129,7 @@ struct rvc_ctx {
     std::vector<cudaEvent_t> events;
     Model cv, f0, syn;
     CvInfo cvi; F0Info f0i; SynInfo syi;
-    DevBuf index; int index_rows = 0, index_c = 0; float index_rate = 0.f;
+    Model index; int index_rows = 0, index_c = 0; float index_rate = 0.f;
     DevBuf state;
     std::map<PlanKey, std::unique_ptr<PlanEntry>> plans;
     PlanEntry* last = nullptr;
@@ -112,9 +146,10 @@ struct rvc_ctx {
     void sync_all() { for (auto s : streams) if (s) cudaStreamSynchronize(s); }
     DeviceBases bases(const PlanEntry& e) const {
         DeviceBases B;
-        B.b[SP_CV] = cv.dev.d; B.b[SP_F0] = f0.dev.d; B.b[SP_SYN] = syn.dev.d; B.b[SP_IDX] = index.d;
+        B.b[SP_CV] = cv.d ? cv.d->dev.d : nullptr; B.b[SP_F0] = f0.d ? f0.d->dev.d : nullptr;
+        B.b[SP_SYN] = syn.d ? syn.d->dev.d : nullptr; B.b[SP_IDX] = index.d ? index.d->dev.d : nullptr;
         B.b[SP_WORK] = e.work.d; B.b[SP_STATE] = state.d;
-        B.hilo_stride[SP_CV] = cv.hilo_stride; B.hilo_stride[SP_SYN] = syn.hilo_stride;
+        B.hilo_stride[SP_CV] = cv.d ? cv.d->hilo_stride : 0; B.hilo_stride[SP_SYN] = syn.d ? syn.d->hilo_stride : 0;
         return B;
     }
 };
@@ -123,7 +158,7 @@ namespace {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call); } while (0)
 
-int upload(rvc_ctx* ctx, Model& m, bool with_hilo) {
+int upload(rvc_ctx* ctx, ModelData& m, bool with_hilo) {
     size_t bytes = (m.packed.host.size() * sizeof(float) + 1023) & ~size_t(1023);
     m.dev.release();
     CK(cudaMalloc(&m.dev.d, bytes * (with_hilo ? 3 : 1) + 256));
@@ -137,7 +172,6 @@ int upload(rvc_ctx* ctx, Model& m, bool with_hilo) {
     }
     CK(cudaDeviceSynchronize());
     std::vector<float>().swap(m.packed.host);
-    m.loaded = true;
     return RVC_OK;
 }
 
@@ -193,7 +227,7 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
 }
 
 int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
-    PlanKey key{int(kind), g, (ctx->index.d && kind == PLAN_INFER) ? 1 : 0, ctx->index_rows, ctx->cfg.index_k};
+    PlanKey key{int(kind), g, (ctx->index.loaded && kind == PLAN_INFER) ? 1 : 0, ctx->index_rows, ctx->cfg.index_k};
     auto it = ctx->plans.find(key);
     if (it != ctx->plans.end()) { *out = it->second.get(); return RVC_OK; }
     PlanOptions opt;
@@ -202,8 +236,8 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     opt.allow_umma = ctx->allow_umma;
     auto e = std::make_unique<PlanEntry>();
     std::string err;
-    if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.packed : nullptr,
-                    &ctx->f0i, ctx->syn.loaded ? &ctx->syn.packed : nullptr, &ctx->syi, e->plan, err))
+    if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.d->packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.d->packed : nullptr,
+                    &ctx->f0i, ctx->syn.loaded ? &ctx->syn.d->packed : nullptr, &ctx->syi, e->plan, err))
         return ctx->fail(RVC_ERR_BAD_SHAPE, err);
     if (e->plan.n_lanes > MAX_LANES) return ctx->fail(RVC_ERR_INVALID_ARG, "too many lanes");
     CK(cudaMalloc(&e->work.d, size_t(e->plan.work_bytes)));
@@ -354,7 +388,7 @@ void rvc_destroy(rvc_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     ctx->sync_all();
     ctx->plans.clear();
-    ctx->cv.unload(); ctx->f0.unload(); ctx->syn.unload(); ctx->index.release(); ctx->state.release();
+    ctx->cv.unload(); ctx->f0.unload(); ctx->syn.unload(); ctx->index.unload(); ctx->state.release();
     for (auto ev : ctx->events) cudaEventDestroy(ev);
     for (auto ev : ctx->timers) if (ev) cudaEventDestroy(ev);
     for (auto s : ctx->streams) if (s) cudaStreamDestroy(s);
@@ -366,32 +400,56 @@ int rvc_load_contentvec(rvc_ctx* ctx, int32_t model_version) {
     if (model_version != RVC_MODEL_V1 && model_version != RVC_MODEL_V2) model_version = RVC_MODEL_V2;  // enums.rs:42-49
     const int c = model_version == RVC_MODEL_V1 ? 256 : 768, l = model_version == RVC_MODEL_V1 ? 9 : 12;   // enums.rs:9-23
     std::string path = ctx->data_path + "/contentvec/vec-" + std::to_string(c) + "-layer-" + std::to_string(l) + ".rvcw";
-    RvcwFile f; std::string err;
-    if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
+    const std::string key = model_key(ctx->cfg.device, path, ctx->allow_umma);
+    std::shared_ptr<ModelData> d = cache_lookup(key);
+    if (!d) {
+        RvcwFile f; std::string err;
+        if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
+        d = std::make_shared<ModelData>();
+        if (!pack_contentvec(f, d->packed, d->cvi, err)) return ctx->fail(RVC_ERR_IO, err);
+        rc = upload(ctx, *d, ctx->allow_umma); if (rc) return rc;
+        cache_store(key, d);
+    }
     ctx->drop_plans(); ctx->cv.unload();
-    if (!pack_contentvec(f, ctx->cv.packed, ctx->cvi, err)) return ctx->fail(RVC_ERR_IO, err);
-    return upload(ctx, ctx->cv, ctx->allow_umma);
+    ctx->cv.d = d; ctx->cv.loaded = true; ctx->cvi = d->cvi;
+    return RVC_OK;
 }
 
 int rvc_load_f0(rvc_ctx* ctx, int32_t pitch_algorithm) {
     int rc = enter(ctx); if (rc) return rc;
     (void)pitch_algorithm;  // enums.rs:106-113: every value maps to Rmvpe
     std::string path = ctx->data_path + "/f0/rmvpe.rvcw";
-    RvcwFile f; std::string err;
-    if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
+    const std::string key = model_key(ctx->cfg.device, path, false);
+    std::shared_ptr<ModelData> d = cache_lookup(key);
+    if (!d) {
+        RvcwFile f; std::string err;
+        if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
+        d = std::make_shared<ModelData>();
+        if (!pack_rmvpe(f, d->packed, d->f0i, err)) return ctx->fail(RVC_ERR_IO, err);
+        rc = upload(ctx, *d, false); if (rc) return rc;
+        cache_store(key, d);
+    }
     ctx->drop_plans(); ctx->f0.unload();
-    if (!pack_rmvpe(f, ctx->f0.packed, ctx->f0i, err)) return ctx->fail(RVC_ERR_IO, err);
-    return upload(ctx, ctx->f0, false);
+    ctx->f0.d = d; ctx->f0.loaded = true; ctx->f0i = d->f0i;
+    return RVC_OK;
 }
 
 int rvc_load_model(rvc_ctx* ctx, const char* model_path) {
     int rc = enter(ctx); if (rc) return rc;
     if (!model_path) return ctx->fail(RVC_ERR_INVALID_ARG, "null path");
-    RvcwFile f; std::string err;
-    if (!f.load(model_path, err)) return ctx->fail(RVC_ERR_IO, err);
+    const std::string key = model_key(ctx->cfg.device, model_path, ctx->allow_umma);
+    std::shared_ptr<ModelData> d = cache_lookup(key);
+    if (!d) {
+        RvcwFile f; std::string err;
+        if (!f.load(model_path, err)) return ctx->fail(RVC_ERR_IO, err);
+        d = std::make_shared<ModelData>();
+        if (!pack_synth(f, d->packed, d->syi, err)) return ctx->fail(RVC_ERR_IO, err);
+        rc = upload(ctx, *d, ctx->allow_umma); if (rc) return rc;
+        cache_store(key, d);
+    }
     ctx->drop_plans(); ctx->syn.unload();
-    if (!pack_synth(f, ctx->syn.packed, ctx->syi, err)) return ctx->fail(RVC_ERR_IO, err);
-    return upload(ctx, ctx->syn, ctx->allow_umma);
+    ctx->syn.d = d; ctx->syn.loaded = true; ctx->syi = d->syi;
+    return RVC_OK;
 }
 
 int rvc_unload_model(rvc_ctx* ctx) {
@@ -400,28 +458,50 @@ int rvc_unload_model(rvc_ctx* ctx) {
     return RVC_OK;
 }
 
+static int attach_index(rvc_ctx* ctx, const std::shared_ptr<ModelData>& d, float index_rate) {
+    ctx->drop_plans(); ctx->index.unload();
+    ctx->index.d = d; ctx->index.loaded = true; ctx->index_rows = d->rows; ctx->index_c = d->cols; ctx->index_rate = index_rate;
+    return RVC_OK;
+}
+
+static int upload_index(rvc_ctx* ctx, const float* rows, size_t n, size_t c, std::shared_ptr<ModelData>& out) {
+    if (c % 4 != 0 || c > 1024 || n > 0x7fffffffull || n < size_t(ctx->cfg.index_k))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "index must be N x C with C % 4 == 0, C <= 1024, N >= k");
+    out = std::make_shared<ModelData>();
+    CK(cudaMalloc(&out->dev.d, n * c * sizeof(float)));
+    out->dev.bytes = n * c * sizeof(float);
+    CK(cudaMemcpy(out->dev.d, rows, out->dev.bytes, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());
+    out->rows = int(n); out->cols = int(c);
+    return RVC_OK;
+}
+
 int rvc_set_index(rvc_ctx* ctx, const float* rows, size_t n, size_t c, float index_rate) {
     int rc = enter(ctx); if (rc) return rc;
-    ctx->drop_plans(); ctx->index.release(); ctx->index_rows = 0; ctx->index_c = 0;
     ctx->index_rate = index_rate;
-    if (!rows || n == 0) return RVC_OK;  // clears the index
-    if (c % 4 != 0 || c > 1024 || n > 0x7fffffffull || n < size_t(ctx->cfg.index_k)) return ctx->fail(RVC_ERR_BAD_SHAPE, "index must be N x C with C % 4 == 0, C <= 1024, N >= k");
-    CK(cudaMalloc(&ctx->index.d, n * c * sizeof(float)));
-    ctx->index.bytes = n * c * sizeof(float);
-    CK(cudaMemcpy(ctx->index.d, rows, ctx->index.bytes, cudaMemcpyHostToDevice));
-    CK(cudaDeviceSynchronize());
-    ctx->index_rows = int(n); ctx->index_c = int(c);
-    return RVC_OK;
+    if (!rows || n == 0) {  // clears the index
+        ctx->drop_plans(); ctx->index.unload(); ctx->index_rows = 0; ctx->index_c = 0;
+        return RVC_OK;
+    }
+    std::shared_ptr<ModelData> d;
+    rc = upload_index(ctx, rows, n, c, d); if (rc) return rc;
+    return attach_index(ctx, d, index_rate);
 }
 
 int rvc_load_index(rvc_ctx* ctx, const char* index_path, float index_rate) {
     int rc = enter(ctx); if (rc) return rc;
     if (!index_path) return ctx->fail(RVC_ERR_INVALID_ARG, "null path");
-    RvcwFile f; std::string err;
-    if (!f.load(index_path, err)) return ctx->fail(RVC_ERR_IO, err);
-    const HostTensor* t = f.find("big_npy");
-    if (!t || t->dtype != 0 || t->shape.size() != 2) return ctx->fail(RVC_ERR_IO, "index file has no big_npy [N,C] tensor");
-    return rvc_set_index(ctx, t->f(), size_t(t->shape[0]), size_t(t->shape[1]), index_rate);
+    const std::string key = model_key(ctx->cfg.device, index_path, false) + "|index";
+    std::shared_ptr<ModelData> d = cache_lookup(key);
+    if (!d) {
+        RvcwFile f; std::string err;
+        if (!f.load(index_path, err)) return ctx->fail(RVC_ERR_IO, err);
+        const HostTensor* t = f.find("big_npy");
+        if (!t || t->dtype != 0 || t->shape.size() != 2) return ctx->fail(RVC_ERR_IO, "index file has no big_npy [N,C] tensor");
+        rc = upload_index(ctx, t->f(), size_t(t->shape[0]), size_t(t->shape[1]), d); if (rc) return rc;
+        cache_store(key, d);
+    }
+    return attach_index(ctx, d, index_rate);
 }
 
 int rvc_set_index_rate(rvc_ctx* ctx, float index_rate) {
@@ -543,7 +623,7 @@ int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t
 
 int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32_t k, float* d2, int32_t* idx) {
     int rc = enter(ctx); if (rc) return rc;
-    if (!ctx->index.d) return ctx->fail(RVC_ERR_INVALID_ARG, "no index loaded");
+    if (!ctx->index.loaded) return ctx->fail(RVC_ERR_INVALID_ARG, "no index loaded");
     if (!queries || !d2 || !idx || q == 0 || c != size_t(ctx->index_c) || k <= 0 || k > 16 || q * c > size_t(StateLayout::AUDIO_CAP))
         return ctx->fail(RVC_ERR_BAD_SHAPE, "bad kNN query shape");
     PlanEntry* e = nullptr;
