@@ -27,8 +27,11 @@
 #include "../../include/rvc_b200.h"
 #include "launch.h"
 #include "model.h"
+#include "pdl.cuh"
 
 using namespace rvc;
+
+namespace rvc { bool g_use_pdl = false; }  // measured: no gain on this path (profiles/README), opt-in with RVC_PDL=1
 
 namespace {
 
@@ -108,10 +111,12 @@ constexpr int MAX_LANES = 4;
 
 __global__ void set_params_kernel(RunParams* p, float uppower, float index_rate, unsigned long long seed,
                                   unsigned long long window, int noise_mode) {
+    pdl_enter();
     p->uppower = uppower; p->index_rate = index_rate; p->noise_seed = seed; p->window = window; p->noise_mode = noise_mode;
 }
 
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    pdl_enter();
     __shared__ float tile[32][33];
     int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += 8) if (r0 + i < rows && c < cols) tile[i][threadIdx.x] = in[(long long)(r0 + i) * cols + c];
@@ -279,8 +284,9 @@ int set_params(rvc_ctx* ctx, int32_t pitch_shift) {
     float up;
     if (ctx->cfg.upstream_pitch_shift) up = std::pow(2.0f, float(pitch_shift) / 12.0f);
     else up = std::ldexp(1.0f, pitch_shift / 12);  // 2.0f32.powi(pitch_shift / 12): i32 division (rvc.rs:121)
-    set_params_kernel<<<1, 1, 0, ctx->streams[0]>>>(reinterpret_cast<RunParams*>(ctx->state.d + StateLayout::off_params), up,
-                                                    ctx->index_rate, ctx->cfg.noise_seed, ctx->window, ctx->cfg.noise_mode);
+    launch_k(set_params_kernel, dim3(1), dim3(1), size_t(0), ctx->streams[0],
+             reinterpret_cast<RunParams*>(ctx->state.d + StateLayout::off_params), up, ctx->index_rate,
+             (unsigned long long)ctx->cfg.noise_seed, (unsigned long long)ctx->window, ctx->cfg.noise_mode);
     ctx->total_launches++;
     return RVC_OK;
 }
@@ -356,6 +362,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     if (ctx->cfg.index_k <= 0 || ctx->cfg.index_k > 16) { g_create_error = "index_k must be in [1,16]"; return RVC_ERR_INVALID_ARG; }
     ctx->data_path = data_path;
     { const char* ev = getenv("RVC_UMMA"); ctx->allow_umma = !(ev && ev[0] == '0'); }
+    { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) {
@@ -555,7 +562,7 @@ int rvc_hubert(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap,
     const NamedBuf* nb = e->plan.find("cv.out");
     const float* src = reinterpret_cast<const float*>(e->work.d + nb->ref.off);
     dim3 grid((C + 31) / 32, (T + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, s>>>(src, state_audio(ctx), T, C);  // (T,C) -> (C,T) as rvc.rs:96
+    launch_k(transpose_kernel, grid, block, size_t(0), s, src, state_audio(ctx), T, C);  // (T,C) -> (C,T) as rvc.rs:96
     ctx->total_launches++;
     CK(cudaMemcpyAsync(out, state_audio(ctx), size_t(T) * C * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -613,7 +620,7 @@ int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t
     rc = run_plan(ctx, *e); if (rc) return rc;
     const NamedBuf* nb = e->plan.find("mel");
     dim3 grid(4, (T + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const float*>(e->work.d + nb->ref.off), state_audio(ctx), T, 128);
+    launch_k(transpose_kernel, grid, block, size_t(0), s, reinterpret_cast<const float*>(e->work.d + nb->ref.off), state_audio(ctx), T, 128);
     ctx->total_launches++;
     CK(cudaMemcpyAsync(out, state_audio(ctx), size_t(T) * 128 * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -750,8 +757,9 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, t0, t1));
         cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
-        double flops = 0, wbytes = 0, iobytes = 0; long long grid = 0;
+        double flops = 0, wbytes = 0, iobytes = 0; long long grid = 0; int variant = -1, splitk = 1;
         if (op.kind == OP_GEMM) {
+            variant = op.gemm.sched_variant; splitk = op.gemm.splitk;
             const GemmOp& g = op.gemm;
             flops = 2.0 * g.M * double(g.N) * g.K * g.batch;
             wbytes = 4.0 * double(g.N) * g.K * g.batch;
@@ -762,8 +770,8 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
             flops = 3.0 * double(op.kd.N) * op.kd.C * op.kd.Q; wbytes = 4.0 * double(op.kd.N) * op.kd.C;
         }
         char buf[512];
-        std::snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"kind\": \"%s\", \"lane\": %d, \"us\": %.3f, \"flops\": %.0f, \"wbytes\": %.0f, \"iobytes\": %.0f, \"M\": %lld}",
-                      first ? "" : ", ", op.name.c_str(), KN[op.kind], op.lane, double(ms) * 1e3 / iters, flops, wbytes, iobytes, grid);
+        std::snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"kind\": \"%s\", \"lane\": %d, \"us\": %.3f, \"flops\": %.0f, \"wbytes\": %.0f, \"iobytes\": %.0f, \"M\": %lld, \"variant\": %d, \"splitk\": %d}",
+                      first ? "" : ", ", op.name.c_str(), KN[op.kind], op.lane, double(ms) * 1e3 / iters, flops, wbytes, iobytes, grid, variant, splitk);
         js += buf; first = false;
     }
     js += "]";

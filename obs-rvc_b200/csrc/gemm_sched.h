@@ -59,7 +59,8 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     const int nkt = (g.K + GEMM2_BK - 1) / GEMM2_BK;
     int want = (2 * NUM_SMS + s.tiles - 1) / s.tiles;          // ~2 CTAs per SM in total
     int maxsplit = std::max(1, nkt / 4);                        // at least 4 k-tiles per split
-    s.splitk = std::max(1, std::min(std::min(want, maxsplit), 64));
+    // every extra split costs a partial-tile round trip through L2 in the last CTA: keep the group small
+    s.splitk = std::max(1, std::min(std::min(want, maxsplit), 8));
     if (g.out_mode != OUT_PLAIN && false) s.splitk = 1;
     return s;
 }

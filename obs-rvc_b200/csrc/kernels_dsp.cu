@@ -4,6 +4,7 @@
 #include <cfloat>
 
 #include "launch.h"
+#include "pdl.cuh"
 #include "noise.h"
 
 namespace rvc {
@@ -21,6 +22,7 @@ stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restric
                     const int* __restrict__ band_start, const int* __restrict__ band_count,
                     const int* __restrict__ band_off, const float* __restrict__ band_w, float* __restrict__ mel,
                     float* __restrict__ out2, long long out2_pitch, float scale, float shift, float clamp) {
+    pdl_enter();
     __shared__ float2 buf[1024];
     __shared__ float2 tw[512];
     __shared__ float mag[513];
@@ -70,6 +72,7 @@ stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restric
 __global__ void __launch_bounds__(128)
 f0_decode_kernel(const float* __restrict__ sal, float* __restrict__ f0, int* __restrict__ argmax,
                  const RunParams* __restrict__ rp, int bins, float threshold, int upstream_window) {
+    pdl_enter();
     const int t = blockIdx.x, tid = threadIdx.x;
     const float* s = sal + (long long)t * bins;
     float bv = -FLT_MAX; int bi = 0x7fffffff;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(1024)
 f0_post_kernel(const float* __restrict__ f0, float* __restrict__ cache, int* __restrict__ pitch,
                float* __restrict__ pitchf, int pitch_len, int shift, int hubert_length, int skip_head,
                int return_length, int n, float mel_min, float mel_max) {
+    pdl_enter();
     const int i = threadIdx.x;
     float keep = 0.f;
     if (i + shift < n) keep = cache[i + shift];
@@ -140,6 +144,7 @@ f0_post_kernel(const float* __restrict__ f0, float* __restrict__ cache, int* __r
 __global__ void __launch_bounds__(1024)
 sinegen_kernel(const float* __restrict__ f0, float* __restrict__ out, float* __restrict__ dbg,
                const RunParams* __restrict__ rp, int T, int upp, float sr, float lin_w, float lin_b) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smraw[];
     double* part = reinterpret_cast<double*>(smraw);        // [1024] chunk sums -> exclusive offsets
     float* rad = reinterpret_cast<float*>(part + 1024);     // [T]
@@ -208,27 +213,27 @@ sinegen_kernel(const float* __restrict__ f0, float* __restrict__ out, float* __r
 }  // namespace
 
 int launch_stftmel(const StftMelOp& o, const DeviceBases& B, cudaStream_t s) {
-    stft_mel_log_kernel<<<o.T, 256, 0, s>>>(B.p<float>(o.pcm), o.L, B.p<float>(o.window), B.p<int>(o.band_start),
+    launch_k(stft_mel_log_kernel, dim3(o.T), dim3(256), size_t(0), s, B.p<float>(o.pcm), o.L, B.p<float>(o.window), B.p<int>(o.band_start),
                                             B.p<int>(o.band_count), B.p<int>(o.band_off), B.p<float>(o.band_w), B.p<float>(o.mel),
                                             B.p<float>(o.out2), o.out2_pitch, o.scale, o.shift, o.clamp);
     return 1;
 }
 
 int launch_f0decode(const F0DecodeOp& o, const DeviceBases& B, cudaStream_t s) {
-    f0_decode_kernel<<<o.T, 128, 0, s>>>(B.p<float>(o.salience), B.p<float>(o.f0), B.p<int>(o.argmax), B.p<RunParams>(o.params),
+    launch_k(f0_decode_kernel, dim3(o.T), dim3(128), size_t(0), s, B.p<float>(o.salience), B.p<float>(o.f0), B.p<int>(o.argmax), B.p<RunParams>(o.params),
                                          o.bins, o.threshold, o.upstream_window);
     return 1;
 }
 
 int launch_f0post(const F0PostOp& o, const DeviceBases& B, cudaStream_t s) {
-    f0_post_kernel<<<1, 1024, 0, s>>>(B.p<float>(o.f0), B.p<float>(o.cache), B.p<int>(o.pitch), B.p<float>(o.pitchf), o.pitch_len,
+    launch_k(f0_post_kernel, dim3(1), dim3(1024), size_t(0), s, B.p<float>(o.f0), B.p<float>(o.cache), B.p<int>(o.pitch), B.p<float>(o.pitchf), o.pitch_len,
                                       o.shift, o.hubert_length, o.skip_head, o.return_length, o.cache_len, o.mel_min, o.mel_max);
     return 1;
 }
 
 int launch_sinegen(const SineGenOp& o, const DeviceBases& B, cudaStream_t s) {
     size_t smem = sizeof(double) * 1024 + sizeof(float) * 2 * o.R;
-    sinegen_kernel<<<1, 1024, smem, s>>>(B.p<float>(o.pitchf), B.p<float>(o.out), B.p<float>(o.sine_dbg), B.p<RunParams>(o.params),
+    launch_k(sinegen_kernel, dim3(1), dim3(1024), size_t(smem), s, B.p<float>(o.pitchf), B.p<float>(o.out), B.p<float>(o.sine_dbg), B.p<RunParams>(o.params),
                                          o.R, o.upp, o.sr, o.lin_w, o.lin_b);
     return 1;
 }

@@ -14,6 +14,7 @@
 
 #include "gemm_common.cuh"
 #include "launch.h"
+#include "pdl.cuh"
 
 namespace rvc {
 
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
     __shared__ __align__(16) float As[2][BK][BM];
     __shared__ __align__(16) float Ws[2][BK][BN];
 
+    pdl_enter();
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -241,8 +243,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
 template <int BM, int BN, int TM, int TN>
 void launch_cfg(const GemmParams& p, int batch, bool vec, cudaStream_t s) {
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
-    if (vec) gemm_f32_kernel<BM, BN, TM, TN, true><<<grid, 256, 0, s>>>(p);
-    else gemm_f32_kernel<BM, BN, TM, TN, false><<<grid, 256, 0, s>>>(p);
+    if (vec) launch_k(gemm_f32_kernel<BM, BN, TM, TN, true>, grid, dim3(256), size_t(0), s, p);
+    else launch_k(gemm_f32_kernel<BM, BN, TM, TN, false>, grid, dim3(256), size_t(0), s, p);
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

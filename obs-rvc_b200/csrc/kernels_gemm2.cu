@@ -15,6 +15,7 @@
 #include "gemm_common.cuh"
 #include "gemm_sched.h"
 #include "launch.h"
+#include "pdl.cuh"
 
 namespace rvc {
 
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_last;
 
+    pdl_launch_dependents();
     V2_DBG(0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         }
     };
 
+    pdl_wait();  // everything above is index math on kernel parameters only
     V2_DBG(1);
     float acc[BM][TN];
 #pragma unroll
@@ -197,12 +200,21 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         const float* base = p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N;
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        for (int zz = 0; zz < p.splitk; ++zz) {
+        // partials are summed in z order; 4 splits x 8 rows = 32 independent L2 loads in flight per thread
+        for (int zz0 = 0; zz0 < p.splitk; zz0 += 4) {
+            float t[4][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {  // 8 independent loads in flight per thread
-                const int m = m0 + r0 + i * RS;
-                if (m < p.M && n < p.N) v[i] += __ldcg(base + ((long long)zz * p.M + m) * p.N + n);
-            }
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = m0 + r0 + i * RS;
+                    t[u][i] = (zz0 + u < p.splitk && m < p.M && n < p.N)
+                                  ? __ldcg(base + ((long long)(zz0 + u) * p.M + m) * p.N + n) : 0.f;
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += t[u][i];
         }
     }
     // epilogue: residual values are fetched up front (R may alias C for in-place accumulation, which
@@ -254,7 +266,7 @@ void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
     const int nkt = (g.K + BK2 - 1) / BK2;
     p.kt_per_split = (nkt + g.splitk - 1) / g.splitk;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch * g.splitk);
-    kern<<<grid, 256, smem, s>>>(p);
+    launch_k(kern, grid, dim3(256), smem, s, p);
 }
 
 }  // namespace

@@ -12,6 +12,7 @@
 #include <climits>
 
 #include "launch.h"
+#include "pdl.cuh"
 
 namespace rvc {
 
@@ -21,6 +22,7 @@ template <int CV, int QN, int G, int KK>
 __global__ void __launch_bounds__(256)
 knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __restrict__ queries, long long ldq, int Q,
                 float* __restrict__ cand_d, int* __restrict__ cand_i, int parts, int k) {
+    pdl_enter();
     extern __shared__ __align__(16) float qs[];  // [G*QN][C], zero padded
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C4 = C >> 2;
@@ -123,6 +125,7 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
 __global__ void __launch_bounds__(256)
 knn_select_kernel(const float* __restrict__ cand_d, const int* __restrict__ cand_i, int* __restrict__ idx,
                   float* __restrict__ d2, int M, int k) {
+    pdl_enter();
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* cd = cand_d + (long long)q * M;
     const int* ci = cand_i + (long long)q * M;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(256)
 knn_blend_kernel(const float* __restrict__ index, const int* __restrict__ idx, const float* __restrict__ d2,
                  const float* __restrict__ x, long long ldx, float* __restrict__ out, const RunParams* __restrict__ rp,
                  int C, int k) {
+    pdl_enter();
     const int q = blockIdx.x;
     __shared__ float w[32]; __shared__ int id[32];
     if (threadIdx.x == 0) {
@@ -180,7 +184,7 @@ void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaS
     size_t smem = sizeof(float) * size_t(G) * QN * o.C;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-    kern<<<(o.parts + 7) / 8, 256, smem, s>>>(B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
+    launch_k(kern, dim3((o.parts + 7) / 8), dim3(256), smem, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
                                               B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k,
                                               B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
 }
@@ -215,12 +219,12 @@ int launch_knn_scan(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
 }
 
 int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t s) {
-    knn_select_kernel<<<o.Q, 256, 0, s>>>(B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx), B.p<float>(o.d2), o.parts * o.k, o.k);
+    launch_k(knn_select_kernel, dim3(o.Q), dim3(256), size_t(0), s, B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx), B.p<float>(o.d2), o.parts * o.k, o.k);
     return 1;
 }
 
 int launch_knn_blend(const KnnBlendOp& o, const DeviceBases& B, cudaStream_t s) {
-    knn_blend_kernel<<<o.Q, 256, 0, s>>>(B.p<float>(o.index), B.p<int>(o.idx), B.p<float>(o.d2), B.p<float>(o.x), o.ldx, B.p<float>(o.out),
+    launch_k(knn_blend_kernel, dim3(o.Q), dim3(256), size_t(0), s, B.p<float>(o.index), B.p<int>(o.idx), B.p<float>(o.d2), B.p<float>(o.x), o.ldx, B.p<float>(o.out),
                                          B.p<RunParams>(o.params), o.C, o.k);
     return 1;
 }

@@ -6,6 +6,7 @@
 #include <cfloat>
 
 #include "launch.h"
+#include "pdl.cuh"
 #include "noise.h"
 
 namespace cg = cooperative_groups;
@@ -40,6 +41,7 @@ constexpr int LN_MAXV = 32;  // up to 1024 columns
 __global__ void layernorm_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int cols,
                                  float eps) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
     const float* x = X + (long long)warp * ldx;
@@ -75,6 +77,7 @@ constexpr int ATT_QB = 16, ATT_WARPS = 8;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo, int T, int heads, int dim) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int h = blockIdx.x, q0 = blockIdx.y * ATT_QB;
     const int HD = heads * dim, dk = dim + 1;
@@ -120,6 +123,7 @@ attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out
 __global__ void __launch_bounds__(256)
 relattn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo,
                const float* __restrict__ rel_k, const float* __restrict__ rel_v, int T, int heads, int dim, int window) {
+    pdl_enter();
     extern __shared__ float sm[];
     const int h = blockIdx.x, HD = heads * dim, dk = dim + 1, nrel = 2 * window + 1;
     float* Qs = sm;                          // [T][dim+1]
@@ -183,6 +187,7 @@ constexpr int C0_CH = 4;  // channels per CTA in the stats pass
 __global__ void __launch_bounds__(256)
 conv0_stats_kernel(const float* __restrict__ pcm, const float* __restrict__ w, float* __restrict__ stats, int T, int C,
                    int k, int stride, float eps) {
+    pdl_enter();
     const int c0 = blockIdx.x * C0_CH;
     float wr[C0_CH][10];
 #pragma unroll
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(256)
 conv0_apply_kernel(const float* __restrict__ pcm, const float* __restrict__ w, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, int T, int C,
                    int k, int stride) {
+    pdl_enter();
     __shared__ float xs[C0_TB * 5 + 16];
     const int t0 = blockIdx.x * C0_TB;
     const int nx = (min(C0_TB, T - t0) - 1) * stride + k;
@@ -251,6 +257,7 @@ conv0_apply_kernel(const float* __restrict__ pcm, const float* __restrict__ w, c
 // 2x2 average pool on halo-padded NHWC
 // ------------------------------------------------------------------------------------------
 __global__ void avgpool_kernel(const float* __restrict__ in, long long ldin, float* __restrict__ out, int T, int F, int C) {
+    pdl_enter();
     const int To = T / 2, Fo = F / 2;
     const long long n = (long long)To * Fo * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -275,6 +282,7 @@ constexpr int GRU_CL = 8, GRU_H = 256, GRU_UNITS = GRU_H / GRU_CL;  // 32 hidden
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(768)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t, const float* __restrict__ bhh,
                    float* __restrict__ out, int T) {
+    pdl_enter();
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int H = GRU_H, G = 3 * GRU_H;
     __shared__ __align__(16) float hbuf[2][H];
@@ -329,6 +337,7 @@ __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ phone, const int* __restrict__ pitch, const float* __restrict__ wp,
              const float* __restrict__ bp, const float* __restrict__ emb_pitch, float* __restrict__ out, long long ldo,
              int Cin, int H) {
+    pdl_enter();
     extern __shared__ float xs[];
     const int r = blockIdx.x;
     for (int i = threadIdx.x; i < Cin; i += blockDim.x) xs[i] = phone[(long long)r * Cin + i];
@@ -350,6 +359,7 @@ embed_kernel(const float* __restrict__ phone, const int* __restrict__ pitch, con
 
 __global__ void zp_kernel(const float* __restrict__ stats, float* __restrict__ out, long long ldo,
                           const RunParams* __restrict__ rp, int R, int H) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= R * H) return;
     const int r = e / H, c = e - r * H;
@@ -362,6 +372,7 @@ __global__ void zp_kernel(const float* __restrict__ stats, float* __restrict__ o
 __global__ void avg3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                             long long ld, float* __restrict__ out, long long ldo, float* __restrict__ raw, long long ldraw,
                             int T, int C, float slope) {
+    pdl_enter();
     const long long n = (long long)T * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         int ch = int(e % C);
@@ -376,6 +387,7 @@ __global__ void avg3_kernel(const float* __restrict__ a, const float* __restrict
 // conv_post: tanh(conv1d(C -> 1, k)); thread per output sample, weights in smem
 __global__ void __launch_bounds__(256)
 convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, int T, int C, int k) {
+    pdl_enter();
     extern __shared__ float ws[];
     const int n = k * C;
     for (int i = threadIdx.x; i < n; i += blockDim.x) ws[i] = w[i];
@@ -394,6 +406,7 @@ convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ out, int T, int C,
                                    int skip, int R, int row0) {
+    pdl_enter();
     const long long n = (long long)R * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         int c = int(e % C), r = int(e / C);
@@ -403,6 +416,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, long long lds,
 }
 
 __global__ void split_hilo_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+    pdl_enter();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float v = src[i];
         const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -434,38 +448,38 @@ void init_kernel_attributes() {
 }
 
 void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n, cudaStream_t stream) {
-    split_hilo_kernel<<<148 * 8, 256, 0, stream>>>(src, dst_hi, dst_lo, n);
+    launch_k(split_hilo_kernel, dim3(148 * 8), dim3(256), size_t(0), stream, src, dst_hi, dst_lo, n);
 }
 
 int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t s) {
     const int wpb = 4;
-    layernorm_kernel<<<(o.rows + wpb - 1) / wpb, wpb * 32, 0, s>>>(B.p<float>(o.X), o.ldx, B.p<float>(o.Y), o.ldy,
+    launch_k(layernorm_kernel, dim3((o.rows + wpb - 1) / wpb), dim3(wpb * 32), size_t(0), s, B.p<float>(o.X), o.ldx, B.p<float>(o.Y), o.ldy,
                                                                   B.p<float>(o.gamma), B.p<float>(o.beta), o.rows, o.cols, o.eps);
     return 1;
 }
 
 int launch_attn(const AttnOp& o, const DeviceBases& B, cudaStream_t s) {
     dim3 grid(o.heads, (o.T + ATT_QB - 1) / ATT_QB);
-    attn_kernel<<<grid, ATT_WARPS * 32, attn_smem(o.T, o.dim), s>>>(B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T,
+    launch_k(attn_kernel, grid, dim3(ATT_WARPS * 32), attn_smem(o.T, o.dim), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T,
                                                                     o.heads, o.dim);
     return 1;
 }
 
 int launch_relattn(const RelAttnOp& o, const DeviceBases& B, cudaStream_t s) {
-    relattn_kernel<<<o.heads, 256, relattn_smem(o.T, o.dim, o.window), s>>>(B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
+    launch_k(relattn_kernel, dim3(o.heads), dim3(256), relattn_smem(o.T, o.dim, o.window), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
                                                                             B.p<float>(o.rel_k), B.p<float>(o.rel_v), o.T, o.heads,
                                                                             o.dim, o.window);
     return 1;
 }
 
 int launch_conv0_stats(const Conv0StatsOp& o, const DeviceBases& B, cudaStream_t s) {
-    conv0_stats_kernel<<<(o.C + C0_CH - 1) / C0_CH, 256, 0, s>>>(B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats), o.T, o.C,
+    launch_k(conv0_stats_kernel, dim3((o.C + C0_CH - 1) / C0_CH), dim3(256), size_t(0), s, B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats), o.T, o.C,
                                                                  o.k, o.stride, o.eps);
     return 1;
 }
 
 int launch_conv0_apply(const Conv0ApplyOp& o, const DeviceBases& B, cudaStream_t s) {
-    conv0_apply_kernel<<<(o.T + C0_TB - 1) / C0_TB, 256, 0, s>>>(B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats),
+    launch_k(conv0_apply_kernel, dim3((o.T + C0_TB - 1) / C0_TB), dim3(256), size_t(0), s, B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats),
                                                                  B.p<float>(o.gamma), B.p<float>(o.beta), B.p<float>(o.Y), o.T, o.C,
                                                                  o.k, o.stride);
     return 1;
@@ -473,42 +487,42 @@ int launch_conv0_apply(const Conv0ApplyOp& o, const DeviceBases& B, cudaStream_t
 
 int launch_avgpool(const AvgPoolOp& o, const DeviceBases& B, cudaStream_t s) {
     long long n = (long long)(o.T / 2) * (o.F / 2) * o.C;
-    avgpool_kernel<<<grid_for(n, 256), 256, 0, s>>>(B.p<float>(o.in), o.ldin, B.p<float>(o.out), o.T, o.F, o.C);
+    launch_k(avgpool_kernel, dim3(grid_for(n, 256)), dim3(256), size_t(0), s, B.p<float>(o.in), o.ldin, B.p<float>(o.out), o.T, o.F, o.C);
     return 1;
 }
 
 int launch_gru(const GruOp& o, const DeviceBases& B, cudaStream_t s) {
     // H is fixed by the RMVPE architecture (BiGRU(384, 256)); validated when the model is packed
-    gru_cluster_kernel<<<2 * GRU_CL, 768, 0, s>>>(B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out), o.T);
+    launch_k(gru_cluster_kernel, dim3(2 * GRU_CL), dim3(768), size_t(0), s, B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out), o.T);
     return 1;
 }
 
 int launch_embed(const EmbedOp& o, const DeviceBases& B, cudaStream_t s) {
-    embed_kernel<<<o.R, 256, sizeof(float) * o.Cin, s>>>(B.p<float>(o.phone), B.p<int>(o.pitch), B.p<float>(o.wp), B.p<float>(o.bp),
+    launch_k(embed_kernel, dim3(o.R), dim3(256), size_t(sizeof(float) * o.Cin), s, B.p<float>(o.phone), B.p<int>(o.pitch), B.p<float>(o.wp), B.p<float>(o.bp),
                                                          B.p<float>(o.emb_pitch), B.p<float>(o.out), o.ldo, o.Cin, o.H);
     return 1;
 }
 
 int launch_zp(const ZpOp& o, const DeviceBases& B, cudaStream_t s) {
-    zp_kernel<<<(o.R * o.H + 255) / 256, 256, 0, s>>>(B.p<float>(o.stats), B.p<float>(o.out), o.ldo, B.p<RunParams>(o.params), o.R, o.H);
+    launch_k(zp_kernel, dim3((o.R * o.H + 255) / 256), dim3(256), size_t(0), s, B.p<float>(o.stats), B.p<float>(o.out), o.ldo, B.p<RunParams>(o.params), o.R, o.H);
     return 1;
 }
 
 int launch_avg3(const Avg3Op& o, const DeviceBases& B, cudaStream_t s) {
-    avg3_kernel<<<grid_for((long long)o.T * o.C, 256), 256, 0, s>>>(B.p<float>(o.a), B.p<float>(o.b), B.p<float>(o.c), o.ld,
+    launch_k(avg3_kernel, dim3(grid_for((long long)o.T * o.C, 256)), dim3(256), size_t(0), s, B.p<float>(o.a), B.p<float>(o.b), B.p<float>(o.c), o.ld,
                                                                     B.p<float>(o.out), o.ldo, B.p<float>(o.raw), o.ldraw, o.T, o.C,
                                                                     o.slope);
     return 1;
 }
 
 int launch_convpost(const ConvPostOp& o, const DeviceBases& B, cudaStream_t s) {
-    convpost_kernel<<<(o.T + 255) / 256, 256, sizeof(float) * o.k * o.C, s>>>(B.p<float>(o.in), B.p<float>(o.w), B.p<float>(o.out), o.T,
+    launch_k(convpost_kernel, dim3((o.T + 255) / 256), dim3(256), size_t(sizeof(float) * o.k * o.C), s, B.p<float>(o.in), B.p<float>(o.w), B.p<float>(o.out), o.T,
                                                                               o.C, o.k);
     return 1;
 }
 
 int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t s) {
-    gather_rows_kernel<<<grid_for((long long)o.R * o.C, 256), 256, 0, s>>>(B.p<float>(o.src), o.lds, B.p<float>(o.out), o.T, o.C,
+    launch_k(gather_rows_kernel, dim3(grid_for((long long)o.R * o.C, 256)), dim3(256), size_t(0), s, B.p<float>(o.src), o.lds, B.p<float>(o.out), o.T, o.C,
                                                                           o.skip, o.R, o.row0);
     return 1;
 }

@@ -27,6 +27,7 @@
 #include "gemm_common.cuh"
 #include "gemm_sched.h"
 #include "launch.h"
+#include "pdl.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -151,6 +152,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int kb0 = z * p.kt_per_split, kb1 = min(nkb_total, kb0 + p.kt_per_split);
     const int nkb = max(0, kb1 - kb0);
 
+    pdl_launch_dependents();
     if (tid == 0) UMMA_DBG(0);
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -168,6 +170,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
+    pdl_wait();  // barrier init, TMEM allocation and descriptor prefetch overlapped the previous kernel
     if (tid == 0) UMMA_DBG(1);
 
     if (warp == 0) {
@@ -411,10 +414,12 @@ bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const float* w_hi, const fl
     cfg.blockDim = dim3(UM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K group = one thread-block cluster along z
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = unsigned(g.splitk);
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     if (cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmWlo, p) != cudaSuccess) return false;
     return true;
 }
