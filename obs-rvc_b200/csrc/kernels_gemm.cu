@@ -10,6 +10,7 @@
 // double-buffered shared memory with register prefetch (one __syncthreads per k-tile).  Global
 // loads are float4 along K (each lane a different row -> transposed, conflict-free STS); the
 // k-major shared layout gives LDS.128 operand fetches.
+#include <algorithm>
 #include <cstdio>
 
 #include "gemm_common.cuh"
@@ -240,6 +241,33 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
     }
 }
 
+// K <= 32 contractions (1x1 / first-layer convs, Conv1d(1,C,k)): one thread per output element, the
+// whole K loop in registers; coalesced along N.  These are outer-product sized - a tiled GEMM only
+// adds latency.
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(GemmParams p) {
+    pdl_enter();
+    const int ncols = p.N;
+    const long long total = (long long)p.M * ncols;
+    const int bz = blockIdx.y;
+    const float* __restrict__ A = p.A + bz * p.sA;
+    const float* __restrict__ W = p.W + bz * p.sW;
+    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
+    float* C = p.C + bz * p.sC;
+    float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
+    const float* R = p.R ? p.R + bz * p.sR : nullptr;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int m = int(e / ncols), n = int(e - (long long)m * ncols);
+        float acc = 0.f, accp = 0.f;
+        for (int k = 0; k < p.K; ++k) {
+            const int seg = k / p.seg_len, within = k - seg * p.seg_len;
+            const float a = __ldg(A + (long long)m * p.lda + (long long)seg * p.seg_stride + within);
+            acc = fmaf(a, __ldg(W + (long long)n * p.ldw + k), acc);
+            if (p.act == ACT_GATE) accp = fmaf(a, __ldg(W + (long long)(n ^ 1) * p.ldw + k), accp);
+        }
+        epilogue_elem(p, bias, C, C2, R, m, n, acc, accp);
+    }
+}
+
 template <int BM, int BN, int TM, int TN>
 void launch_cfg(const GemmParams& p, int batch, bool vec, cudaStream_t s) {
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, batch);
@@ -261,6 +289,12 @@ int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
         return launch_gemm_v2(g, B, stream);
     }
     GemmParams p = make_params(g, B);
+    if (g.K <= 32) {
+        const long long total = (long long)g.M * g.N;
+        const int blocks = int(std::min<long long>((total + 255) / 256, 148 * 16));
+        launch_k(gemm_smallk_kernel, dim3(blocks, g.batch), dim3(256), size_t(0), stream, p);
+        return 1;
+    }
     const bool vec = al16(p.A) && al16(p.W) && g.lda % 4 == 0 && g.seg_len % 4 == 0 && g.seg_stride % 4 == 0 &&
                      g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
     p.vec_store = (g.out_mode == OUT_PLAIN && g.act != ACT_GATE && al16(p.C) && g.ldc % 4 == 0 && g.sC % 4 == 0 &&

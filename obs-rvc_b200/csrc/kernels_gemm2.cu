@@ -41,14 +41,18 @@ __device__ long long g_v2_dbg[16];
 // per k-tile a warp issues BM broadcast LDS.128 + BN/32 conflict-free LDS.128 for 4*64 FMAs, i.e. the
 // tile runs at the FMA rate instead of the shared-memory wavefront rate even at one CTA per SM.
 // The eight per-warp partial tiles are summed through shared memory in fixed warp order.
+constexpr int V2_THREADS = 512;  // 16 warps: 8 k-quads x 2 row halves (latency hiding at one CTA per SM)
+
 template <int BM, int BN, int STAGES>
-__global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
+__global__ void __launch_bounds__(V2_THREADS, 1) gemm_v2_kernel(GemmParams p) {
     constexpr int TN = BN / 32;
-    static_assert(BM * TN == 64, "64 accumulators per thread");
+    constexpr int HM = BM / 2;  // rows per warp
+    static_assert(HM * TN == 32, "32 accumulators per thread");
     constexpr int STAGE_FLOATS = (BM + BN) * LDS2;
     constexpr int CHUNKS = (BM + BN) * (BK2 / 4);          // 16-byte chunks per stage
-    constexpr int CPT = (CHUNKS + 255) / 256;              // chunks per thread
-    constexpr int RS = 256 / BN > 0 ? 256 / BN : 1;        // row stride of the final thread->output map
+    constexpr int CPT = (CHUNKS + V2_THREADS - 1) / V2_THREADS;  // chunks per thread
+    constexpr int RS = V2_THREADS / BN;                    // row stride of the final thread->output map
+    constexpr int OPT = BM * BN / V2_THREADS;              // outputs per thread (4)
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_last;
 
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
     const float* cbase[CPT]; int ckc[CPT]; int cdst[CPT]; bool cisA[CPT], cvalid[CPT];
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
-        const int c = tid + i * 256;
+        const int c = tid + i * V2_THREADS;
         cvalid[i] = c < CHUNKS;
         const int row = c / (BK2 / 4), kc = c % (BK2 / 4);
         ckc[i] = kc * 4;
@@ -106,9 +110,10 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
 
     pdl_wait();  // everything above is index math on kernel parameters only
     V2_DBG(1);
-    float acc[BM][TN];
+    const int kq = warp & 7, rh = warp >> 3;
+    float acc[HM][TN];
 #pragma unroll
-    for (int i = 0; i < BM; ++i)
+    for (int i = 0; i < HM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
@@ -125,16 +130,16 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         if (kt == 1) V2_DBG(4);
         if (kt + STAGES - 1 < nkt) load_stage((kt + STAGES - 1) % STAGES, kt0 + kt + STAGES - 1);
         cp_async_commit();
-        const float* As = smem + (kt % STAGES) * STAGE_FLOATS + warp * 4;
-        const float* Ws = smem + (kt % STAGES) * STAGE_FLOATS + (BM + lane) * LDS2 + warp * 4;
+        const float* As = smem + (kt % STAGES) * STAGE_FLOATS + (rh * HM) * LDS2 + kq * 4;
+        const float* Ws = smem + (kt % STAGES) * STAGE_FLOATS + (BM + lane) * LDS2 + kq * 4;
         float4 b[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Ws + j * 32 * LDS2);
         // rows in groups of RG: the RG broadcast loads are issued together and the FMAs are ordered
         // so that consecutive instructions hit different accumulators (FMA latency 4 is covered)
-        constexpr int RG = BM >= 8 ? 8 : BM;
+        constexpr int RG = HM >= 8 ? 8 : HM;
 #pragma unroll
-        for (int i0 = 0; i0 < BM; i0 += RG) {
+        for (int i0 = 0; i0 < HM; i0 += RG) {
             float4 a[RG];
 #pragma unroll
             for (int r = 0; r < RG; ++r) a[r] = *reinterpret_cast<const float4*>(As + (i0 + r) * LDS2);
@@ -154,17 +159,17 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
     cp_async_wait<0>();
     __syncthreads();  // every warp is done with the stage buffers: reuse them for the partial tiles
     V2_DBG(5);
-    float* red = smem;  // [8 warps][BM][BN]
+    float* red = smem;  // [8 k-quads][BM][BN]
 #pragma unroll
-    for (int i = 0; i < BM; ++i)
+    for (int i = 0; i < HM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) red[(warp * BM + i) * BN + j * 32 + lane] = acc[i][j];
+        for (int j = 0; j < TN; ++j) red[(kq * BM + rh * HM + i) * BN + j * 32 + lane] = acc[i][j];
     __syncthreads();
-    // final map: thread t owns column t % BN and 8 rows (stride RS): coalesced along N
+    // final map: thread t owns column t % BN and OPT rows (stride RS): coalesced along N
     const int col = tid % BN, r0 = tid / BN;
-    float v[8];
+    float v[OPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < OPT; ++i) {
         const int row = r0 + i * RS;
         float s = 0.f;
 #pragma unroll
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
     if (p.splitk > 1) {
         float* part = p.scratch + ((long long)(bz * p.splitk + z) * p.M) * p.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < OPT; ++i) {
             const int m = m0 + r0 + i * RS;
             if (m < p.M && n < p.N) __stcg(part + (long long)m * p.N + n, v[i]);
         }
@@ -199,38 +204,38 @@ __global__ void __launch_bounds__(256) gemm_v2_kernel(GemmParams p) {
         __threadfence();
         const float* base = p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        // partials are summed in z order; 4 splits x 8 rows = 32 independent L2 loads in flight per thread
-        for (int zz0 = 0; zz0 < p.splitk; zz0 += 4) {
-            float t[4][8];
+        for (int i = 0; i < OPT; ++i) v[i] = 0.f;
+        // partials are summed in z order; 8 splits x 4 rows = 32 independent L2 loads in flight per thread
+        for (int zz0 = 0; zz0 < p.splitk; zz0 += 8) {
+            float t[8][OPT];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < OPT; ++i) {
                     const int m = m0 + r0 + i * RS;
                     t[u][i] = (zz0 + u < p.splitk && m < p.M && n < p.N)
                                   ? __ldcg(base + ((long long)(zz0 + u) * p.M + m) * p.N + n) : 0.f;
                 }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += t[u][i];
+                for (int i = 0; i < OPT; ++i) v[i] += t[u][i];
         }
     }
     // epilogue: residual values are fetched up front (R may alias C for in-place accumulation, which
     // would otherwise serialise every load behind the previous store)
     const bool plain = p.out_mode == OUT_PLAIN;
     const bool gate = p.act == ACT_GATE;
-    float rv[8];
+    float rv[OPT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < OPT; ++i) {
         const int m = m0 + r0 + i * RS;
         const int rc = gate ? (n >> 1) : n;
         rv[i] = (R && plain && m < p.M && n < p.N && !(gate && (n & 1))) ? R[(long long)m * p.ldr + rc] : 0.f;
     }
     const float bn_ = (bias && n < p.N) ? __ldg(bias + n) : 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < OPT; ++i) {
         const int m = m0 + r0 + i * RS;
         const float partner = __shfl_xor_sync(0xffffffffu, v[i], 1);
         if (m >= p.M || n >= p.N) continue;
@@ -266,7 +271,7 @@ void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
     const int nkt = (g.K + BK2 - 1) / BK2;
     p.kt_per_split = (nkt + g.splitk - 1) / g.splitk;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch * g.splitk);
-    launch_k(kern, grid, dim3(256), smem, s, p);
+    launch_k(kern, grid, dim3(V2_THREADS), smem, s, p);
 }
 
 }  // namespace
@@ -274,6 +279,7 @@ void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
 int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
     GemmParams p = gemmk::make_params(g, B);
     switch (g.sched_variant) {
+        // (deeper rings were measured slower: profiles/README.md)
         case 1: launch_v2<8, 256, 3>(g, p, stream); break;
         case 2: launch_v2<16, 128, 4>(g, p, stream); break;
         default: launch_v2<32, 64, 4>(g, p, stream); break;

@@ -345,14 +345,23 @@ embed_kernel(const float* __restrict__ phone, const int* __restrict__ pitch, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int pi = pitch[r];
     const float sc = sqrtf(float(H));
-    for (int h = warp; h < H; h += nw) {
-        const float* wr = wp + (long long)h * Cin;
-        float a = 0.f;
-        for (int k = lane; k < Cin; k += 32) a = fmaf(xs[k], __ldg(wr + k), a);
-        a = warp_sum(a);
-        if (lane == 0) {
-            float v = (a + bp[h] + emb_pitch[pi * H + h]) * sc;
-            out[(long long)r * ldo + h] = v > 0.f ? v : 0.1f * v;
+    // 4 output channels per warp pass: their weight rows stream concurrently (latency-bound otherwise)
+    for (int h0 = warp * 4; h0 < H; h0 += nw * 4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 6
+        for (int k = lane; k < Cin; k += 32) {
+            const float x = xs[k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (h0 + u < H) a[u] = fmaf(x, __ldg(wp + (long long)(h0 + u) * Cin + k), a[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float t = warp_sum(a[u]);
+            if (lane == 0 && h0 + u < H) {
+                float v = (t + bp[h0 + u] + emb_pitch[pi * H + h0 + u]) * sc;
+                out[(long long)r * ldo + h0 + u] = v > 0.f ? v : 0.1f * v;
+            }
         }
     }
 }
