@@ -31,6 +31,7 @@
 
 using namespace rvc;
 
+static bool g_sync_each = false;
 namespace rvc { bool g_use_pdl = false; }  // measured: no gain on this path (profiles/README), opt-in with RVC_PDL=1
 
 namespace {
@@ -225,6 +226,11 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
         }
         int rc = issue_one(ctx, op, B, ctx->streams[op.lane], &n);
         if (rc != RVC_OK) return rc;
+        if (g_sync_each) {  // RVC_SYNC_EACH=1: name the op whose kernel faults (debugging aid)
+            cudaError_t se = cudaStreamSynchronize(ctx->streams[op.lane]);
+            if (se == cudaSuccess) se = cudaGetLastError();
+            if (se != cudaSuccess) return ctx->fail(RVC_ERR_CUDA, "op '" + op.name + "' failed: " + cudaGetErrorString(se));
+        }
     }
     CK(cudaGetLastError());
     *launches = n;
@@ -362,6 +368,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     if (ctx->cfg.index_k <= 0 || ctx->cfg.index_k > 16) { g_create_error = "index_k must be in [1,16]"; return RVC_ERR_INVALID_ARG; }
     ctx->data_path = data_path;
     { const char* ev = getenv("RVC_UMMA"); ctx->allow_umma = !(ev && ev[0] == '0'); }
+    { const char* ev = getenv("RVC_SYNC_EACH"); g_sync_each = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -34,13 +34,16 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
         (contiguous || (g.seg_len % 32 == 0 && g.K % g.seg_len == 0)) && g.K >= 96) {
         const int tm = (g.M + 127) / 128;
         const int nkb = (g.K + 31) / 32;
+        // one CTA per SM (smem-limited) and clusters must pack into GPCs: aim for a single wave of
+        // <= ~112 CTAs; prefer 128-wide tiles (less operand traffic per flop) when that still fills it
+        const int tiles128 = tm * ((g.N + 127) / 128) * g.batch;
         int bn = 128;
         if (g.N <= 32) bn = 32;
-        else if (g.N <= 64 || tm * ((g.N + 127) / 128) * g.batch < NUM_SMS) bn = 64;
+        else if (g.N <= 64 || tiles128 < 56) bn = 64;
         s.variant = bn == 128 ? 5 : (bn == 64 ? 6 : 7);
         s.bm = 128; s.bn = bn;
         s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
-        const int want = (NUM_SMS + s.tiles - 1) / s.tiles;     // 1 CTA per SM (smem-limited)
+        const int want = std::max(1, 112 / s.tiles);
         const int maxsplit = std::max(1, nkb / 4);
         // split-K group = one thread-block cluster (partials reduced over DSMEM): power of two <= 8
         s.splitk = 1;

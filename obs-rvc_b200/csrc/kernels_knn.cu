@@ -121,14 +121,22 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
     }
 }
 
-// merges parts*k candidates per query: k rounds of "smallest (d, idx) greater than the previous"
+// merges parts*k candidates per query: k rounds of "smallest (d, idx) greater than the previous".
+// The candidate list is staged once in shared memory when it fits (it does for 2368 parts x k <= 8).
 __global__ void __launch_bounds__(256)
 knn_select_kernel(const float* __restrict__ cand_d, const int* __restrict__ cand_i, int* __restrict__ idx,
-                  float* __restrict__ d2, int M, int k) {
+                  float* __restrict__ d2, int M, int k, int staged) {
     pdl_enter();
+    extern __shared__ __align__(16) float sel_sm[];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* cd = cand_d + (long long)q * M;
     const int* ci = cand_i + (long long)q * M;
+    if (staged) {
+        float* sd_ = sel_sm; int* si_ = reinterpret_cast<int*>(sel_sm + M);
+        for (int m = tid; m < M; m += 256) { sd_[m] = cd[m]; si_[m] = ci[m]; }
+        __syncthreads();
+        cd = sd_; ci = si_;
+    }
     __shared__ float sd[8]; __shared__ int si[8];
     __shared__ float pd_s; __shared__ int pi_s;
     float pd = -FLT_MAX; int pi = -1;
@@ -219,7 +227,13 @@ int launch_knn_scan(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
 }
 
 int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(knn_select_kernel, dim3(o.Q), dim3(256), size_t(0), s, B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx), B.p<float>(o.d2), o.parts * o.k, o.k);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    const int M = o.parts * o.k;
+    const size_t need = size_t(M) * 8;
+    const int staged = need <= 200 * 1024 ? 1 : 0;
+    launch_k(knn_select_kernel, dim3(o.Q), dim3(256), staged ? need : size_t(0), s, B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx),
+             B.p<float>(o.d2), M, o.k, staged);
     return 1;
 }
 

@@ -71,109 +71,112 @@ __global__ void layernorm_kernel(const float* __restrict__ X, long long ldx, flo
 }
 
 // ------------------------------------------------------------------------------------------
-// Multi-head attention, one CTA per (head, 16-query block); K (padded rows) and V in smem
+// Multi-head attention (ContentVec, head dim 64): CTA = (head, 8 query rows), one warp per row.
+// K is staged transposed ([d][T], odd pitch) so the score pass reads consecutive keys per lane,
+// V row-major for the P.V pass, q lives in registers.
 // ------------------------------------------------------------------------------------------
-constexpr int ATT_QB = 16, ATT_WARPS = 8;
+constexpr int ATT_WARPS = 8, ATT_D = 64;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo, int T, int heads, int dim) {
+attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo, int T, int heads) {
     pdl_enter();
-    extern __shared__ float sm[];
-    const int h = blockIdx.x, q0 = blockIdx.y * ATT_QB;
-    const int HD = heads * dim, dk = dim + 1;
-    float* Ks = sm;                       // [T][dim+1]
-    float* Vs = Ks + (size_t)T * dk;      // [T][dim]
-    float* Qs = Vs + (size_t)T * dim;     // [ATT_WARPS][dim]
-    float* Ps = Qs + ATT_WARPS * dim;     // [ATT_WARPS][T]
-    for (int i = threadIdx.x; i < T * dim; i += blockDim.x) {
-        int t = i / dim, d = i - t * dim;
-        Ks[t * dk + d] = qkv[(long long)t * ld + HD + h * dim + d];
-        Vs[t * dim + d] = qkv[(long long)t * ld + 2 * HD + h * dim + d];
+    extern __shared__ __align__(16) float sm[];
+    constexpr int D = ATT_D;
+    const int h = blockIdx.x, q0 = blockIdx.y * ATT_WARPS;
+    const int HD = heads * D, Tp = (T | 1) + 2;          // odd pitch
+    float* Vs = sm;                                       // [T][D]
+    float* Kt = Vs + (size_t)T * D;                       // [D][Tp]
+    float* Ps = Kt + (size_t)D * Tp;                      // [ATT_WARPS][Tp]
+    for (int i = threadIdx.x; i < T * (D / 4); i += blockDim.x) {
+        const int t = i / (D / 4), d4 = i - t * (D / 4);
+        const float4 k = __ldg(reinterpret_cast<const float4*>(qkv + (long long)t * ld + HD + h * D) + d4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(qkv + (long long)t * ld + 2 * HD + h * D) + d4);
+        Kt[(d4 * 4 + 0) * Tp + t] = k.x; Kt[(d4 * 4 + 1) * Tp + t] = k.y;
+        Kt[(d4 * 4 + 2) * Tp + t] = k.z; Kt[(d4 * 4 + 3) * Tp + t] = k.w;
+        reinterpret_cast<float4*>(Vs + (size_t)t * D)[d4] = v;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = q0 + warp;
+    float q[D];
+    if (qi < T) {
+#pragma unroll
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi * ld + h * D) + d4);
+            q[d4 * 4] = t4.x; q[d4 * 4 + 1] = t4.y; q[d4 * 4 + 2] = t4.z; q[d4 * 4 + 3] = t4.w;
+        }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* qs = Qs + warp * dim;
-    float* ps = Ps + warp * T;
-    for (int qi = q0 + warp; qi < min(q0 + ATT_QB, T); qi += ATT_WARPS) {
-        for (int d = lane; d < dim; d += 32) qs[d] = qkv[(long long)qi * ld + h * dim + d];
-        __syncwarp();
-        float mx = -FLT_MAX;
-        for (int j = lane; j < T; j += 32) {
-            float a = 0.f;
-            for (int d = 0; d < dim; ++d) a = fmaf(qs[d], Ks[j * dk + d], a);
-            ps[j] = a;
-            mx = fmaxf(mx, a);
+    if (qi >= T) return;
+    float* ps = Ps + warp * Tp;
+    float mx = -FLT_MAX;
+    for (int j = lane; j < T; j += 32) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; d += 2) {
+            a0 = fmaf(q[d], Kt[d * Tp + j], a0);
+            a1 = fmaf(q[d + 1], Kt[(d + 1) * Tp + j], a1);
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < T; j += 32) { float e = expf(ps[j] - mx); ps[j] = e; sum += e; }
-        sum = warp_sum(sum);
-        __syncwarp();
-        const float inv = 1.0f / sum;
-        for (int d = lane; d < dim; d += 32) {
-            float a = 0.f;
-            for (int j = 0; j < T; ++j) a = fmaf(ps[j], Vs[j * dim + d], a);
-            out[(long long)qi * ldo + h * dim + d] = a * inv;
-        }
-        __syncwarp();
+        const float a = a0 + a1;
+        ps[j] = a;
+        mx = fmaxf(mx, a);
     }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) { const float e = expf(ps[j] - mx); ps[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+        const float pj = ps[j];
+        o0 = fmaf(pj, Vs[j * D + lane], o0);
+        o1 = fmaf(pj, Vs[j * D + lane + 32], o1);
+    }
+    out[(long long)qi * ldo + h * D + lane] = o0 * inv;
+    out[(long long)qi * ldo + h * D + lane + 32] = o1 * inv;
 }
 
-// VITS windowed relative-position attention (enc_p): T <= ~64, one CTA per head
-__global__ void __launch_bounds__(256)
+// VITS windowed relative-position attention (enc_p): one CTA per (head, query row), 128 threads.
+__global__ void __launch_bounds__(128)
 relattn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo,
                const float* __restrict__ rel_k, const float* __restrict__ rel_v, int T, int heads, int dim, int window) {
     pdl_enter();
     extern __shared__ float sm[];
-    const int h = blockIdx.x, HD = heads * dim, dk = dim + 1, nrel = 2 * window + 1;
-    float* Qs = sm;                          // [T][dim+1]
-    float* Ks = Qs + (size_t)T * dk;         // [T][dim+1]
-    float* Vs = Ks + (size_t)T * dk;         // [T][dim]
-    float* Rk = Vs + (size_t)T * dim;        // [nrel][dim+1]
-    float* Rv = Rk + (size_t)nrel * dk;      // [nrel][dim]
-    float* Ps = Rv + (size_t)nrel * dim;     // [T][T]
-    for (int i = threadIdx.x; i < T * dim; i += blockDim.x) {
-        int t = i / dim, d = i - t * dim;
-        Qs[t * dk + d] = qkv[(long long)t * ld + h * dim + d];
-        Ks[t * dk + d] = qkv[(long long)t * ld + HD + h * dim + d];
-        Vs[t * dim + d] = qkv[(long long)t * ld + 2 * HD + h * dim + d];
-    }
-    for (int i = threadIdx.x; i < nrel * dim; i += blockDim.x) {
-        int r = i / dim, d = i - r * dim;
-        Rk[r * dk + d] = rel_k[i];
-        Rv[r * dim + d] = rel_v[i];
-    }
+    const int h = blockIdx.x / T, i = blockIdx.x - h * T;
+    const int HD = heads * dim, nrel = 2 * window + 1;
+    float* qs = sm;            // [dim]
+    float* ps = qs + dim;      // [T]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (int d = tid; d < dim; d += blockDim.x) qs[d] = qkv[(long long)i * ld + h * dim + d];
     __syncthreads();
-    for (int e = threadIdx.x; e < T * T; e += blockDim.x) {
-        int i = e / T, j = e - i * T;
+    for (int j = warp; j < T; j += nw) {   // one key per warp pass, lanes over the head dimension
+        const float* k = qkv + (long long)j * ld + HD + h * dim;
+        const int rel = j - i + window;
+        const float* rk = (rel >= 0 && rel < nrel) ? rel_k + rel * dim : nullptr;
         float a = 0.f;
-        for (int d = 0; d < dim; ++d) a = fmaf(Qs[i * dk + d], Ks[j * dk + d], a);
-        int rel = j - i + window;
-        if (rel >= 0 && rel < nrel)
-            for (int d = 0; d < dim; ++d) a = fmaf(Qs[i * dk + d], Rk[rel * dk + d], a);
-        Ps[e] = a;
+        for (int d = lane; d < dim; d += 32) a = fmaf(qs[d], k[d] + (rk ? rk[d] : 0.f), a);
+        a = warp_sum(a);
+        if (lane == 0) ps[j] = a;
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int i = warp; i < T; i += nw) {
+    if (warp == 0) {
         float mx = -FLT_MAX;
-        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, Ps[i * T + j]);
+        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, ps[j]);
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int j = lane; j < T; j += 32) { float ev = expf(Ps[i * T + j] - mx); Ps[i * T + j] = ev; sum += ev; }
+        for (int j = lane; j < T; j += 32) { const float e = expf(ps[j] - mx); ps[j] = e; sum += e; }
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
-        for (int j = lane; j < T; j += 32) Ps[i * T + j] *= inv;
+        for (int j = lane; j < T; j += 32) ps[j] *= inv;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < T * dim; e += blockDim.x) {
-        int i = e / dim, d = e - i * dim;
+    for (int d = tid; d < dim; d += blockDim.x) {
         float a = 0.f;
         for (int j = 0; j < T; ++j) {
-            float pv = Ps[i * T + j];
-            a = fmaf(pv, Vs[j * dim + d], a);
-            int rel = j - i + window;
-            if (rel >= 0 && rel < nrel) a = fmaf(pv, Rv[rel * dim + d], a);
+            const int rel = j - i + window;
+            float v = qkv[(long long)j * ld + 2 * HD + h * dim + d];
+            if (rel >= 0 && rel < nrel) v += rel_v[rel * dim + d];
+            a = fmaf(ps[j], v, a);
         }
         out[(long long)i * ldo + h * dim + d] = a;
     }
@@ -438,11 +441,8 @@ inline int grid_for(long long n, int block, int cap = 148 * 8) {
     return int(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-size_t attn_smem(int T, int dim) { return sizeof(float) * (size_t(T) * (dim + 1) + size_t(T) * dim + ATT_WARPS * dim + size_t(ATT_WARPS) * T); }
-size_t relattn_smem(int T, int dim, int window) {
-    int nrel = 2 * window + 1;
-    return sizeof(float) * (2 * size_t(T) * (dim + 1) + size_t(T) * dim + size_t(nrel) * (dim + 1) + size_t(nrel) * dim + size_t(T) * T);
-}
+size_t attn_smem(int T) { const int Tp = (T | 1) + 2; return sizeof(float) * (size_t(T) * ATT_D + size_t(ATT_D) * Tp + size_t(ATT_WARPS) * Tp); }
+size_t relattn_smem(int T, int dim) { return sizeof(float) * (size_t(dim) + size_t(T)); }
 
 }  // namespace
 
@@ -468,16 +468,15 @@ int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t s)
 }
 
 int launch_attn(const AttnOp& o, const DeviceBases& B, cudaStream_t s) {
-    dim3 grid(o.heads, (o.T + ATT_QB - 1) / ATT_QB);
-    launch_k(attn_kernel, grid, dim3(ATT_WARPS * 32), attn_smem(o.T, o.dim), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T,
-                                                                    o.heads, o.dim);
+    // head dim is 64 for every ContentVec variant (validated by the plan builder)
+    dim3 grid(o.heads, (o.T + ATT_WARPS - 1) / ATT_WARPS);
+    launch_k(attn_kernel, grid, dim3(ATT_WARPS * 32), attn_smem(o.T), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T, o.heads);
     return 1;
 }
 
 int launch_relattn(const RelAttnOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(relattn_kernel, dim3(o.heads), dim3(256), relattn_smem(o.T, o.dim, o.window), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
-                                                                            B.p<float>(o.rel_k), B.p<float>(o.rel_v), o.T, o.heads,
-                                                                            o.dim, o.window);
+    launch_k(relattn_kernel, dim3(o.heads * o.T), dim3(128), relattn_smem(o.T, o.dim), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
+             B.p<float>(o.rel_k), B.p<float>(o.rel_v), o.T, o.heads, o.dim, o.window);
     return 1;
 }
 

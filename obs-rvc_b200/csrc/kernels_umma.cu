@@ -158,7 +158,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
         if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 2); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -215,20 +215,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (nkb > 0) umma_commit(&bar_acc); else mbar_arrive(&bar_acc);
             UMMA_DBG(5);
         }
-    } else if (warp < 6) {
-        // ===== converter + TMEM-drain warps (128 threads) =====
+    } else if (warp < 10) {
+        // ===== converter warps 2-9 (two per stage); warps 2-5 then drain TMEM =====
         const int ct = tid - 64;
         if (PASSES == 3) {
-            // hi/lo split of the A tile: k-block i belongs to converter warp i % 4, so up to four stages are
-            // converted concurrently (each warp streams a whole 16 KB stage: latency, not bandwidth, bound)
-            const int cw = warp - 2;
-            for (int i = cw; i < nkb; i += 4) {
+            // hi/lo split of the A tile; up to four stages are converted concurrently
+            // Ownership is by STAGE (stage s belongs to warp pair s & 3), never by k-block: a parity wait
+            // may only ever be one phase ahead of its mbarrier, so every waiter must visit every phase.
+            const int cw = (warp - 2) & 3, half = (warp - 2) >> 2;  // stage owner, 8 KB half of the tile
+            for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
+                if ((s & 3) != cw) continue;
                 mbar_wait(&bar_full[s], ph);
-                float4* a = reinterpret_cast<float4*>(stageA(s));
-                float4* lo = reinterpret_cast<float4*>(stageAlo(s));
+                float4* a = reinterpret_cast<float4*>(stageA(s)) + half * (UM_A_BYTES / 32);
+                float4* lo = reinterpret_cast<float4*>(stageAlo(s)) + half * (UM_A_BYTES / 32);
 #pragma unroll 1
-                for (int b = 0; b < UM_A_BYTES / 16 / 32; b += 8) {
+                for (int b = 0; b < UM_A_BYTES / 32 / 32; b += 8) {
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = a[(b + j) * 32 + lane];
@@ -248,6 +250,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) mbar_arrive(&bar_conv[s]);
             }
         }
+        if (warp < 6) {
         if (ct == 0) UMMA_DBG(6);
         mbar_wait(&bar_acc, 0);
         if (ct == 0) UMMA_DBG(7);
@@ -268,6 +271,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(ct_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         if (ct == 0) UMMA_DBG(11);
+        }
     }
     // ---- staged tile -> global: lanes along N (coalesced); split-K partial tiles are reduced across the
     //      cluster through distributed shared memory, each CTA finishing 128/splitk rows ----
