@@ -117,6 +117,22 @@ int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t
 int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32_t k,
                    float* d2, int32_t* idx);
 
+/* ---- streaming glue around the call ("next" row) ---------------------------------
+ * rt_utils::envelop_mixing(input, output, sample_rate, mix_rate) - obs-rvc/src/rt_utils.rs:119-132.
+ * `output` (n_out samples) is modified in place; `input` must hold at least n_out samples.
+ * rms1/rms2 (optional, n_out each) receive the interpolated envelopes the reference's test checks. */
+int rvc_envelop_mixing(rvc_ctx* ctx, const float* input, size_t n_in, float* output, size_t n_out, uint32_t sample_rate,
+                       double mix_rate, float* rms1, float* rms2);
+/* rt_utils::get_sola_offset(input_buffer, sola_buffer, buffer_frame_size, search_frame_size)
+ * - obs-rvc/src/rt_utils.rs:60-90 (normalised cross-correlation, last maximum wins). */
+int rvc_sola_offset(rvc_ctx* ctx, const float* input_buffer, size_t n, const float* sola_buffer, uint32_t buffer_frame_size,
+                    uint32_t search_frame_size, uint32_t* offset);
+/* SOLA tail of process_one_frame - obs-rvc/src/lib.rs:768-794: picks the offset, cross-fades
+ * `infer_out` with `sola_buffer` (sin^2 windows, lib.rs:231-233), updates `sola_buffer` in place and
+ * returns the `sample_frame_size` samples of this block. */
+int rvc_sola_crossfade(rvc_ctx* ctx, const float* infer_out, size_t n, float* sola_buffer, uint32_t buffer_frame_size,
+                       uint32_t search_frame_size, uint32_t sample_frame_size, float* block_out, uint32_t* offset);
+
 /* Results of the last call kept on the device and copied on demand: "f0" (f32[T]),
  * "f0_argmax" (i32[T]), "salience" (f32[T*360]), "pitch" (i32[R]), "pitchf" (f32[R]),
  * "phone" (f32[R*C]), "knn_idx" (i32[Q*k]), "knn_d2" (f32[Q*k]), "mel" (f32[T*128], (T,128)). */

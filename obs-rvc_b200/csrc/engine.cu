@@ -714,6 +714,83 @@ int rvc_plan_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) 
     return RVC_OK;
 }
 
+// ---- streaming glue ("next" row #1): scratch lives in the audio staging region of the state arena ----
+int rvc_envelop_mixing(rvc_ctx* ctx, const float* input, size_t n_in, float* output, size_t n_out, uint32_t sample_rate,
+                       double mix_rate, float* rms1, float* rms2) {
+    int rc = enter(ctx); if (rc) return rc;
+    const int zc = int(sample_rate / 100);
+    if (!input || !output || n_out == 0 || n_in < n_out || zc <= 0 || n_out * 4 + 4096 > size_t(StateLayout::AUDIO_CAP))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "bad envelop_mixing shape");
+    cudaStream_t s = ctx->streams[0];
+    float* base = state_audio(ctx);
+    float* d_in = base; float* d_out = base + n_out; float* d_r1 = d_out + n_out; float* d_r2 = d_r1 + 2048;
+    float* d_dbg1 = d_r2 + 2048; float* d_dbg2 = d_dbg1 + n_out;
+    const int nfr = int((n_out + size_t(4 * zc) / 2 * 2 - size_t(4 * zc)) / size_t(zc)) + 1;  // rt_utils.rs:93-101
+    if (nfr > 2048 || nfr < 2) return ctx->fail(RVC_ERR_BAD_SHAPE, "too many rms frames");
+    CK(cudaMemcpyAsync(d_in, input, n_out * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_out, output, n_out * 4, cudaMemcpyHostToDevice, s));
+    launch_rms(d_in, int(n_out), 4 * zc, zc, d_r1, nfr, s);
+    launch_rms(d_out, int(n_out), 4 * zc, zc, d_r2, nfr, s);
+    launch_envelop_mix(d_out, int(n_out), d_r1, d_r2, nfr, float(1.0 - mix_rate), (rms1 && rms2) ? d_dbg1 : nullptr,
+                       (rms1 && rms2) ? d_dbg2 : nullptr, s);
+    ctx->total_launches += 3;
+    CK(cudaMemcpyAsync(output, d_out, n_out * 4, cudaMemcpyDeviceToHost, s));
+    if (rms1 && rms2) {
+        CK(cudaMemcpyAsync(rms1, d_dbg1, n_out * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rms2, d_dbg2, n_out * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return RVC_OK;
+}
+
+static int sola_common(rvc_ctx* ctx, const float* x, size_t n, const float* sola, uint32_t buf, uint32_t search, float** d_x_out,
+                       float** d_sola_out, int** d_off_out) {
+    if (!x || !sola || buf == 0 || size_t(buf) + search > n || n + buf + search + 64 > size_t(StateLayout::AUDIO_CAP))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "bad SOLA shape");
+    cudaStream_t s = ctx->streams[0];
+    float* base = state_audio(ctx);
+    float* d_x = base; float* d_sola = base + n; float* d_cor = d_sola + buf; int* d_off = reinterpret_cast<int*>(d_cor + search + 1);
+    CK(cudaMemcpyAsync(d_x, x, n * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_sola, sola, size_t(buf) * 4, cudaMemcpyHostToDevice, s));
+    launch_sola(d_x, d_sola, int(buf), int(search), d_cor, d_off, s);
+    ctx->total_launches += 2;
+    *d_x_out = d_x; *d_sola_out = d_sola; *d_off_out = d_off;
+    return RVC_OK;
+}
+
+int rvc_sola_offset(rvc_ctx* ctx, const float* input_buffer, size_t n, const float* sola_buffer, uint32_t buffer_frame_size,
+                    uint32_t search_frame_size, uint32_t* offset) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!offset) return ctx->fail(RVC_ERR_INVALID_ARG, "null offset");
+    float *dx, *ds; int* doff;
+    rc = sola_common(ctx, input_buffer, n, sola_buffer, buffer_frame_size, search_frame_size, &dx, &ds, &doff); if (rc) return rc;
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, doff, 4, cudaMemcpyDeviceToHost, ctx->streams[0]));
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    *offset = uint32_t(h);
+    return RVC_OK;
+}
+
+int rvc_sola_crossfade(rvc_ctx* ctx, const float* infer_out, size_t n, float* sola_buffer, uint32_t buffer_frame_size,
+                       uint32_t search_frame_size, uint32_t sample_frame_size, float* block_out, uint32_t* offset) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!block_out || size_t(search_frame_size) + sample_frame_size + buffer_frame_size > n)
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "infer output shorter than search + block + fade (lib.rs:789)");
+    float *dx, *ds; int* doff;
+    rc = sola_common(ctx, infer_out, n, sola_buffer, buffer_frame_size, search_frame_size, &dx, &ds, &doff); if (rc) return rc;
+    cudaStream_t s = ctx->streams[0];
+    float* d_block = reinterpret_cast<float*>(doff) + 16;
+    launch_sola_crossfade(dx, doff, ds, int(buffer_frame_size), int(sample_frame_size), d_block, s);
+    ctx->total_launches += 2;
+    int h = 0;
+    CK(cudaMemcpyAsync(block_out, d_block, size_t(sample_frame_size) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(sola_buffer, ds, size_t(buffer_frame_size) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&h, doff, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (offset) *offset = uint32_t(h);
+    return RVC_OK;
+}
+
 int rvc_event_record(rvc_ctx* ctx, int slot) {
     int rc = enter(ctx); if (rc) return rc;
     if (slot < 0 || slot >= 8) return ctx->fail(RVC_ERR_INVALID_ARG, "bad timer slot");

@@ -40,6 +40,13 @@ int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t s
 int launch_knn_blend(const KnnBlendOp& o, const DeviceBases& B, cudaStream_t stream);
 int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t stream);
 
+// streaming glue ("next" row #1): obs-rvc/src/rt_utils.rs + lib.rs:779-791 on the device
+void launch_rms(const float* y, int n, int frame_length, int hop, float* out, int n_frames, cudaStream_t s);
+void launch_envelop_mix(float* out, int n_out, const float* r1, const float* r2, int nr, float power, float* dbg1, float* dbg2,
+                        cudaStream_t s);
+void launch_sola(const float* x, const float* sola, int buf, int search, float* cor, int* offset, cudaStream_t s);
+void launch_sola_crossfade(float* out, const int* offset, float* sola_buffer, int buf, int frame, float* block_out, cudaStream_t s);
+
 // one-time per-process kernel attribute setup (dynamic shared memory opt-in)
 void init_kernel_attributes();
 void init_gemm_v2_attributes();

@@ -241,6 +241,42 @@ class RvcInfer:
                                          idx.ctypes.data_as(c_void_p)))
         return d2, idx
 
+    # ------------------------------------------------------------------ streaming glue (next row #1)
+    def envelop_mixing(self, inp, out, sample_rate: int, mix_rate: float, want_rms: bool = False):
+        """rt_utils::envelop_mixing (obs-rvc/src/rt_utils.rs:119-132); returns the mixed output
+        (and the interpolated rms1/rms2 when `want_rms`)."""
+        inp, out = _f32(inp), _f32(out).copy()
+        n = out.shape[0]
+        r1 = np.empty(n, np.float32) if want_rms else None
+        r2 = np.empty(n, np.float32) if want_rms else None
+        self._chk(self._L.rvc_envelop_mixing(self._h, inp.ctypes.data_as(c_void_p), c_size_t(inp.shape[0]),
+                                             out.ctypes.data_as(c_void_p), c_size_t(n), c_uint32(sample_rate),
+                                             ctypes.c_double(mix_rate),
+                                             r1.ctypes.data_as(c_void_p) if want_rms else None,
+                                             r2.ctypes.data_as(c_void_p) if want_rms else None))
+        return (out, r1, r2) if want_rms else out
+
+    def sola_offset(self, input_buffer, sola_buffer, buffer_frame_size: int, search_frame_size: int) -> int:
+        """rt_utils::get_sola_offset (obs-rvc/src/rt_utils.rs:60-90)."""
+        x, sb = _f32(input_buffer), _f32(sola_buffer)
+        off = c_uint32()
+        self._chk(self._L.rvc_sola_offset(self._h, x.ctypes.data_as(c_void_p), c_size_t(x.shape[0]),
+                                          sb.ctypes.data_as(c_void_p), c_uint32(buffer_frame_size),
+                                          c_uint32(search_frame_size), byref(off)))
+        return off.value
+
+    def sola_crossfade(self, infer_out, sola_buffer, buffer_frame_size: int, search_frame_size: int,
+                       sample_frame_size: int):
+        """SOLA tail of process_one_frame (obs-rvc/src/lib.rs:768-794): returns (block, new sola_buffer, offset)."""
+        x, sb = _f32(infer_out), _f32(sola_buffer).copy()
+        block = np.empty(sample_frame_size, np.float32)
+        off = c_uint32()
+        self._chk(self._L.rvc_sola_crossfade(self._h, x.ctypes.data_as(c_void_p), c_size_t(x.shape[0]),
+                                             sb.ctypes.data_as(c_void_p), c_uint32(buffer_frame_size),
+                                             c_uint32(search_frame_size), c_uint32(sample_frame_size),
+                                             block.ctypes.data_as(c_void_p), byref(off)))
+        return block, sb, off.value
+
     def get_last(self, name: str, dtype=np.float32) -> np.ndarray:
         nb = c_size_t()
         self._chk(self._L.rvc_get_last(self._h, name.encode(), None, c_size_t(0), byref(nb)))

@@ -346,3 +346,17 @@ def get_sola_offset(input_buffer: np.ndarray, sola_buffer: np.ndarray, buffer_fr
         if not (val > cor[i]):
             best, val = i, cor[i]
     return best
+
+
+def sola_crossfade(infer_out: np.ndarray, sola_buffer: np.ndarray, buffer_frame_size: int,
+                   search_frame_size: int, sample_frame_size: int):
+    """obs-rvc/src/lib.rs:231-233,768-794: offset search, sin^2 cross-fade with the previous tail,
+    new sola_buffer, and the block of `sample_frame_size` samples that is emitted."""
+    off = get_sola_offset(infer_out, sola_buffer, buffer_frame_size, search_frame_size)
+    out = np.asarray(infer_out, F32)[off:].copy()
+    lin = np.linspace(0.0, 1.0, buffer_frame_size, dtype=F32)
+    fade_in = (np.sin(lin * F32(0.5) * F32(np.pi)).astype(F32) ** 2).astype(F32)
+    fade_out = (F32(1.0) - fade_in).astype(F32)
+    out[:buffer_frame_size] = out[:buffer_frame_size] * fade_in + np.asarray(sola_buffer, F32) * fade_out
+    new_sola = out[sample_frame_size:sample_frame_size + buffer_frame_size].copy()
+    return out[:sample_frame_size].copy(), new_sola, off

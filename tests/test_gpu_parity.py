@@ -281,3 +281,34 @@ def test_rvc_rpc_wire_protocol(env):
             np.testing.assert_array_equal(got, want[w])
     finally:
         p.kill()
+
+
+# ---------------------------------------------------------------- "next" row #1: streaming glue, PINNED goldens
+
+
+def test_sola_offset_golden(env):
+    """obs-rvc/src/tests/sola.rs:10-16: get_sola_offset(infer_wav, sola_buffer, 1920, 480) == 321."""
+    x = np.load(os.path.join(GOLDEN, "sola_infer_wav.npy"))
+    b = np.load(os.path.join(GOLDEN, "sola_buffer.npy"))
+    assert env["eng"].sola_offset(x, b, 1920, 480) == 321
+
+
+def test_envelop_mixing_golden(env):
+    """obs-rvc/src/tests/envelop_mixing.rs:8-36: rms1 / rms2 / mixed output vs the reference's .npy at 1e-6."""
+    g = lambda n: np.load(os.path.join(GOLDEN, n))
+    mixed, r1, r2 = env["eng"].envelop_mixing(g("envelop_input_wav.npy"), g("envelop_infer_wav.npy"), 48000, 0.8, want_rms=True)
+    assert np.abs(r1 - g("envelop_rms1.npy")).max() < 1e-6
+    assert np.abs(r2 - g("envelop_rms2.npy")).max() < 1e-6
+    assert np.abs(mixed - g("envelop_infer_wav2.npy")).max() < 1e-6
+
+
+def test_sola_crossfade_vs_oracle(env):
+    """obs-rvc/src/lib.rs:768-794 on the reference's SOLA fixture: same offset, block and new tail."""
+    from oracle import dsp
+    x = np.load(os.path.join(GOLDEN, "sola_infer_wav.npy"))
+    b = np.load(os.path.join(GOLDEN, "sola_buffer.npy"))
+    frame = 14400  # 0.30 s block at 48 kHz (lib.rs:200-203)
+    blk, tail, off = env["eng"].sola_crossfade(x, b, 1920, 480, frame)
+    wblk, wtail, woff = dsp.sola_crossfade(x, b, 1920, 480, frame)
+    assert off == woff == 321
+    assert np.abs(blk - wblk).max() < 1e-6 and np.abs(tail - wtail).max() < 1e-6
