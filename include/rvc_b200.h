@@ -154,6 +154,12 @@ int rvc_event_elapsed_ms(rvc_ctx* ctx, int slot_a, int slot_b, float* ms);
  * JSON array [{"name","kind","us","flops","wbytes","iobytes","grid"}] (measurement aid: per-op device
  * time + algorithmic work; inputs are whatever the last run left in the work arena). */
 int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t* out_bytes);
+/* End time (us since graph start) of every op of the last plan inside one CUDA-graph replay with all
+ * lanes running concurrently: JSON [{"name","lane","end_us"}] (critical-path analysis aid). */
+int rvc_profile_timeline(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes);
+/* Per-phase device time of every persistent chain kernel of the last plan (most recent run):
+ * JSON [{"chain","lane","grid","phases":[{"ops","us"}]}]. */
+int rvc_profile_chains(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes);
 const char* rvc_version(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,57 @@
+// chain.h - persistent "chain" kernel: a run of small dependent ops executed by ONE cooperative
+// launch, with a grid-wide barrier where a kernel boundary used to be.
+//
+// Why: at batch 1 the RMVPE U-Net (137 exact-fp32 convolutions, reference call site
+// rvc/src/f0/rmvpe.rs:235) and the synthesizer's text encoder / flow (rvc/src/rvc.rs:195) are
+// chains of ~10 us kernels whose cost is launch + prologue + pipeline-fill latency, not work.  Inside
+// one resident grid a dependent op costs a ~1.5 us barrier instead, the next op's weights are
+// prefetched into L2 while the current one computes, and the grid size is a fixed SM budget, so
+// the F0 lane no longer fights the ContentVec lane for SMs (DESIGN.md "Chains").
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gemm_common.cuh"
+
+namespace rvc {
+
+enum ChainKind : int { CH_GEMM = 0, CH_GEMM_DIRECT = 1, CH_AVGPOOL = 2, CH_LAYERNORM = 3, CH_RELATTN = 4 };
+
+// tile shapes of the chain GEMM (256 threads; warp w owns k-quads w, w+8, ... of every k-tile); the small
+// shapes give weight-streaming ops (M <= 32) one tile per CTA without a split-K round trip
+enum ChainTile : int { CT_32x32 = 0, CT_16x64 = 1, CT_8x128 = 2, CT_32x16 = 3, CT_32x8 = 4, CT_8x32 = 5, CT_8x16 = 6, CT_16x16 = 7 };
+
+struct ChainOpDev {
+    int kind, variant;
+    int tiles_m, tiles_n, splitk, batch;
+    int item0, items;          // work items [item0, item0+items) of the op's phase
+    gemmk::GemmParams g;       // CH_GEMM / CH_GEMM_DIRECT
+    // CH_AVGPOOL: x0=in y0=out ld0=ldin i0=T i1=F i2=C
+    // CH_LAYERNORM: x0=X y0=Y x1=gamma x2=beta ld0=ldx ld1=ldy i0=rows i1=cols f0=eps
+    // CH_RELATTN: x0=qkv y0=out x1=rel_k x2=rel_v ld0=ldqkv ld1=ldo i0=T i1=heads i2=dim i3=window
+    const float* x0; float* y0; const float* x1; const float* x2;
+    long long ld0, ld1;
+    int i0, i1, i2, i3;
+    float f0;
+    // weights worth pulling into L2 while the previous phase runs: rows x row_bytes at stride
+    const char* pf_base; long long pf_stride; int pf_rows, pf_row_bytes;
+};
+
+struct ChainPhaseDev { int op0, op1, items, pad; };
+
+struct ChainDev {
+    ChainOpDev* d_ops = nullptr;
+    ChainPhaseDev* d_phases = nullptr;
+    unsigned int* d_bar = nullptr;   // [0] arrivals, [1] exits (self-cleaning)
+    unsigned long long* d_dbg = nullptr;  // optional: globaltimer at every phase start (+ end), CTA 0
+    int n_ops = 0, n_phases = 0, grid = 0;
+};
+
+constexpr int CHAIN_THREADS = 256;
+constexpr int CHAIN_SMEM_BYTES = 90 * 1024;  // stage rings of 75-90 KB (kernels_chain.cu tile table)
+
+int launch_chain(const ChainDev& c, cudaStream_t stream);  // returns kernels launched (1)
+void init_chain_attributes();
+void chain_debug_read(long long* out, int n);  // [256 phases][8] clock64 stamps of the LAST chain launch, CTA 0
+int chain_max_coresident_ctas();  // occupancy-derived upper bound for a cooperative launch
+
+}  // namespace rvc

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/rvc_b200.h"
+#include "chain.h"
 #include "launch.h"
 #include "model.h"
 #include "pdl.cuh"
@@ -97,6 +98,7 @@ struct PlanKey {
 struct PlanEntry {
     Plan plan;
     DevBuf work;
+    std::vector<ChainDev> chains;   // device tables of plan.chains (pointers resolved against this entry's arenas)
     cudaGraphExec_t exec = nullptr;
     cudaGraph_t graph = nullptr;
     int runs = 0;
@@ -104,6 +106,7 @@ struct PlanEntry {
     ~PlanEntry() {
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
+        for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); }
         work.release();
     }
 };
@@ -142,6 +145,7 @@ struct rvc_ctx {
     uint64_t window = 0, total_launches = 0;
     cudaEvent_t timers[8] = {nullptr};
     bool allow_umma = true;
+    int chain_grid_main = 0, chain_grid_side = 0, chain_side_max_m = 8;
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -224,6 +228,11 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
             ++ev;
             continue;
         }
+        if (op.chain >= 0 && size_t(op.chain) < e.chains.size()) {
+            // the whole run executes in one persistent kernel, launched where its first op stood
+            if (&op == &e.plan.ops[size_t(e.plan.chains[size_t(op.chain)].first)]) n += launch_chain(e.chains[size_t(op.chain)], ctx->streams[op.lane]);
+            continue;
+        }
         int rc = issue_one(ctx, op, B, ctx->streams[op.lane], &n);
         if (rc != RVC_OK) return rc;
         if (g_sync_each) {  // RVC_SYNC_EACH=1: name the op whose kernel faults (debugging aid)
@@ -237,6 +246,78 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
     return RVC_OK;
 }
 
+// Resolves the ops of every chain of the plan into the device tables the chain kernel walks.
+int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
+    const DeviceBases B = ctx->bases(e);
+    for (const ChainInfo& ci : e.plan.chains) {
+        std::vector<ChainOpDev> ops(size_t(ci.count));
+        std::vector<ChainPhaseDev> phases(size_t(ci.n_phases), ChainPhaseDev{0, 0, 0, 0});
+        for (int k = 0; k < ci.count; ++k) {
+            const Op& op = e.plan.ops[size_t(ci.first + k)];
+            ChainOpDev d;
+            std::memset(&d, 0, sizeof(d));
+            d.splitk = 1; d.batch = 1;
+            switch (op.kind) {
+                case OP_GEMM: {
+                    const GemmOp& g = op.gemm;
+                    d.g = gemmk::make_params(g, B);
+                    d.g.splitk = g.ch_splitk; d.g.scratch = B.p<float>(g.ch_scratch); d.g.counters = B.p<unsigned int>(g.ch_counters);
+                    d.batch = g.batch;
+                    if (g.ch_variant < 0) {
+                        d.kind = CH_GEMM_DIRECT; d.g.splitk = 1;
+                        d.items = int((int64_t(g.M) * g.N + 1023) / 1024);
+                    } else {
+                        d.kind = CH_GEMM; d.variant = g.ch_variant; d.tiles_m = g.ch_tiles_m; d.tiles_n = g.ch_tiles_n; d.splitk = g.ch_splitk;
+                        const int nkt = (g.K + 31) / 32;
+                        d.g.kt_per_split = (nkt + g.ch_splitk - 1) / g.ch_splitk;
+                        d.items = g.ch_tiles_m * g.ch_tiles_n * g.batch * g.ch_splitk;
+                        if (g.batch == 1 && int64_t(g.N) * g.K * 4 >= 32768) {
+                            d.pf_base = reinterpret_cast<const char*>(d.g.W); d.pf_stride = g.ldw * 4; d.pf_rows = g.N; d.pf_row_bytes = g.K * 4;
+                        }
+                    }
+                    break;
+                }
+                case OP_AVGPOOL:
+                    d.kind = CH_AVGPOOL; d.x0 = B.p<float>(op.pool.in); d.y0 = B.p<float>(op.pool.out); d.ld0 = op.pool.ldin;
+                    d.i0 = op.pool.T; d.i1 = op.pool.F; d.i2 = op.pool.C;
+                    d.items = int((int64_t(op.pool.T / 2) * (op.pool.F / 2) * op.pool.C + 1023) / 1024);
+                    break;
+                case OP_LAYERNORM:
+                    d.kind = CH_LAYERNORM; d.x0 = B.p<float>(op.ln.X); d.y0 = B.p<float>(op.ln.Y); d.x1 = B.p<float>(op.ln.gamma);
+                    d.x2 = B.p<float>(op.ln.beta); d.ld0 = op.ln.ldx; d.ld1 = op.ln.ldy; d.i0 = op.ln.rows; d.i1 = op.ln.cols; d.f0 = op.ln.eps;
+                    d.items = (op.ln.rows + 7) / 8;
+                    break;
+                case OP_RELATTN:
+                    d.kind = CH_RELATTN; d.x0 = B.p<float>(op.relattn.qkv); d.y0 = B.p<float>(op.relattn.out); d.x1 = B.p<float>(op.relattn.rel_k);
+                    d.x2 = B.p<float>(op.relattn.rel_v); d.ld0 = op.relattn.ldqkv; d.ld1 = op.relattn.ldo; d.i0 = op.relattn.T;
+                    d.i1 = op.relattn.heads; d.i2 = op.relattn.dim; d.i3 = op.relattn.window;
+                    d.items = op.relattn.T * op.relattn.heads;
+                    break;
+                default: return ctx->fail(RVC_ERR_INVALID_ARG, "op kind cannot run inside a chain: " + op.name);
+            }
+            ChainPhaseDev& ph = phases[size_t(ci.phase[size_t(k)])];
+            if (ph.op1 == 0) ph.op0 = k;
+            ph.op1 = k + 1;
+            d.item0 = ph.items; ph.items += d.items;
+            ops[size_t(k)] = d;
+        }
+        ChainDev cd;
+        cd.n_ops = ci.count; cd.n_phases = ci.n_phases;
+        cd.grid = std::max(1, std::min(ci.grid, chain_max_coresident_ctas()));
+        CK(cudaMalloc(&cd.d_ops, ops.size() * sizeof(ChainOpDev)));
+        CK(cudaMalloc(&cd.d_phases, phases.size() * sizeof(ChainPhaseDev)));
+        CK(cudaMalloc(&cd.d_bar, 256));
+        CK(cudaMemcpyAsync(cd.d_ops, ops.data(), ops.size() * sizeof(ChainOpDev), cudaMemcpyHostToDevice, ctx->streams[0]));
+        CK(cudaMemcpyAsync(cd.d_phases, phases.data(), phases.size() * sizeof(ChainPhaseDev), cudaMemcpyHostToDevice, ctx->streams[0]));
+        CK(cudaMemsetAsync(cd.d_bar, 0, 256, ctx->streams[0]));
+        CK(cudaMalloc(&cd.d_dbg, size_t(ci.n_phases + 1) * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(cd.d_dbg, 0, size_t(ci.n_phases + 1) * sizeof(unsigned long long), ctx->streams[0]));
+        CK(cudaStreamSynchronize(ctx->streams[0]));  // the host vectors go out of scope
+        e.chains.push_back(cd);
+    }
+    return RVC_OK;
+}
+
 int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     PlanKey key{int(kind), g, (ctx->index.loaded && kind == PLAN_INFER) ? 1 : 0, ctx->index_rows, ctx->cfg.index_k};
     auto it = ctx->plans.find(key);
@@ -245,6 +326,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     opt.index_k = ctx->cfg.index_k; opt.upstream_cents_window = ctx->cfg.upstream_cents_window;
     opt.with_index = key.with_index || kind == PLAN_KNN; opt.index_rows = ctx->index_rows; opt.multi_lane = true;
     opt.allow_umma = ctx->allow_umma;
+    opt.chain_grid_main = ctx->chain_grid_main; opt.chain_grid_side = ctx->chain_grid_side; opt.chain_side_max_m = ctx->chain_side_max_m;
     auto e = std::make_unique<PlanEntry>();
     std::string err;
     if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.d->packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.d->packed : nullptr,
@@ -254,6 +336,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     CK(cudaMalloc(&e->work.d, size_t(e->plan.work_bytes)));
     e->work.bytes = size_t(e->plan.work_bytes);
     CK(cudaMemsetAsync(e->work.d, 0, e->work.bytes, ctx->streams[0]));  // establishes the zero halos once
+    { int rc = build_chain_tables(ctx, *e); if (rc != RVC_OK) return rc; }
     *out = e.get();
     ctx->plans[key] = std::move(e);
     return RVC_OK;
@@ -370,6 +453,13 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_UMMA"); ctx->allow_umma = !(ev && ev[0] == '0'); }
     { const char* ev = getenv("RVC_SYNC_EACH"); g_sync_each = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
+    {   // persistent chains: CTA budgets (0 = off).  RVC_CHAIN=0 disables both.
+        const char* ev = getenv("RVC_CHAIN"); const bool on = !(ev && ev[0] == '0');
+        const char* em = getenv("RVC_CHAIN_MAIN"); const char* es = getenv("RVC_CHAIN_SIDE");
+        ctx->chain_grid_main = on ? (em ? atoi(em) : 148) : 0;
+        ctx->chain_grid_side = on ? (es ? atoi(es) : 32) : 0;
+        const char* emm = getenv("RVC_CHAIN_SIDE_MAXM"); if (emm) ctx->chain_side_max_m = atoi(emm);
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0) {
@@ -385,10 +475,16 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
         return RVC_ERR_CUDA;
     }
     init_kernel_attributes();
-    for (int i = 0; i < MAX_LANES; ++i)
-        if ((e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
+    for (int i = 0; i < MAX_LANES; ++i) {
+        // lane 1 carries the F0 chain, the longest branch of the window: its kernels go first when SMs free up
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char* pe = getenv("RVC_LANE1_PRIO");
+        const bool boost = !(pe && pe[0] == '0');
+        if ((e = cudaStreamCreateWithPriority(&ctx->streams[i], cudaStreamNonBlocking, (i == 1 && boost) ? prio_hi : prio_lo)) != cudaSuccess) {
             g_create_error = cudaGetErrorString(e); return RVC_ERR_CUDA;
         }
+    }
     if ((e = cudaMalloc(&ctx->state.d, size_t(StateLayout::bytes))) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return RVC_ERR_CUDA; }
     ctx->state.bytes = size_t(StateLayout::bytes);
     cudaMemsetAsync(ctx->state.d, 0, ctx->state.bytes, ctx->streams[0]);
@@ -865,6 +961,109 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
         if (js.size() + 1 > cap_bytes) return ctx->fail(RVC_ERR_INVALID_ARG, "profile buffer too small");
         std::memcpy(out, js.data(), js.size()); out[js.size()] = 0;
     }
+    return RVC_OK;
+}
+
+// Timeline of one graph-replayed window: an external timed event is recorded after every op on the
+// op's own lane inside the captured graph, so the end time of each op under real multi-lane
+// concurrency can be read back (critical-path analysis; the event nodes add a little overhead).
+int rvc_profile_timeline(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->last) return ctx->fail(RVC_ERR_INVALID_ARG, "nothing has run yet");
+    PlanEntry& e = *ctx->last;
+    ctx->sync_all();
+    const DeviceBases B = ctx->bases(e);
+    std::vector<cudaEvent_t> evs;
+    std::vector<const Op*> which;
+    cudaEvent_t t0; CK(cudaEventCreate(&t0));
+    cudaStream_t s0 = ctx->streams[0];
+    CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+    CK(cudaEventRecordWithFlags(t0, s0, cudaEventRecordExternal));
+    size_t ev = 0; int n = 0;
+    for (const Op& op : e.plan.ops) {
+        if (op.kind == OP_WAIT) {
+            if (ev >= ctx->events.size()) { cudaEvent_t x; CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming)); ctx->events.push_back(x); }
+            CK(cudaEventRecord(ctx->events[ev], ctx->streams[op.wait.src_lane]));
+            CK(cudaStreamWaitEvent(ctx->streams[op.wait.dst_lane], ctx->events[ev], 0));
+            ++ev; continue;
+        }
+        if (op.chain >= 0 && size_t(op.chain) < e.chains.size()) {
+            if (&op != &e.plan.ops[size_t(e.plan.chains[size_t(op.chain)].first + e.plan.chains[size_t(op.chain)].count - 1)]) continue;
+            n += launch_chain(e.chains[size_t(op.chain)], ctx->streams[op.lane]);  // reported under the chain's LAST op
+        } else {
+            issue_one(ctx, op, B, ctx->streams[op.lane], &n);
+        }
+        cudaEvent_t x; CK(cudaEventCreate(&x));
+        CK(cudaEventRecordWithFlags(x, ctx->streams[op.lane], cudaEventRecordExternal));
+        evs.push_back(x); which.push_back(&op);
+    }
+    cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+    CK(cudaStreamEndCapture(s0, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    for (int i = 0; i < 3; ++i) CK(cudaGraphLaunch(ge, s0));
+    CK(cudaStreamSynchronize(s0));
+    std::string js = "[";
+    for (size_t i = 0; i < evs.size(); ++i) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, t0, evs[i]);
+        char buf[256];
+        std::snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"lane\": %d, \"end_us\": %.3f}", i ? ", " : "", which[i]->name.c_str(),
+                      which[i]->lane, double(ms) * 1e3);
+        js += buf; cudaEventDestroy(evs[i]);
+    }
+    js += "]";
+    cudaEventDestroy(t0); cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+    if (out_bytes) *out_bytes = js.size();
+    if (out && cap_bytes > 0) {
+        if (js.size() + 1 > cap_bytes) return ctx->fail(RVC_ERR_INVALID_ARG, "profile buffer too small");
+        std::memcpy(out, js.data(), js.size()); out[js.size()] = 0;
+    }
+    return RVC_OK;
+}
+
+// Phase-by-phase device time of every persistent chain of the last plan (globaltimer stamps written by
+// CTA 0 at each phase start during the most recent run): JSON [{"chain","lane","grid","phases":[{"ops","us"}]}].
+int rvc_profile_chains(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->last) return ctx->fail(RVC_ERR_INVALID_ARG, "nothing has run yet");
+    PlanEntry& e = *ctx->last;
+    ctx->sync_all();
+    std::string js = "[";
+    for (size_t c = 0; c < e.chains.size(); ++c) {
+        const ChainInfo& ci = e.plan.chains[c];
+        std::vector<unsigned long long> t(size_t(ci.n_phases + 1));
+        CK(cudaMemcpy(t.data(), e.chains[c].d_dbg, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        char buf[256];
+        std::snprintf(buf, sizeof(buf), "%s{\"chain\": %zu, \"lane\": %d, \"grid\": %d, \"phases\": [", c ? ", " : "", c, ci.lane, e.chains[c].grid);
+        js += buf;
+        for (int ph = 0; ph < ci.n_phases; ++ph) {
+            std::string names;
+            for (int k = 0; k < ci.count; ++k)
+                if (ci.phase[size_t(k)] == ph) {
+                    const Op& op = e.plan.ops[size_t(ci.first + k)];
+                    names += (names.empty() ? "" : ",") + op.name;
+                    if (op.kind == OP_GEMM) names += "[v" + std::to_string(op.gemm.ch_variant) + "x" + std::to_string(op.gemm.ch_tiles_m * op.gemm.ch_tiles_n * op.gemm.batch) + "k" + std::to_string(op.gemm.ch_splitk) + "]";
+                }
+            std::snprintf(buf, sizeof(buf), "%s{\"ops\": \"%s\", \"us\": %.3f}", ph ? ", " : "", names.c_str(), double(t[size_t(ph + 1)] - t[size_t(ph)]) * 1e-3);
+            js += buf;
+        }
+        js += "]}";
+    }
+    js += "]";
+    if (out_bytes) *out_bytes = js.size();
+    if (out && cap_bytes > 0) {
+        if (js.size() + 1 > cap_bytes) return ctx->fail(RVC_ERR_INVALID_ARG, "profile buffer too small");
+        std::memcpy(out, js.data(), js.size()); out[js.size()] = 0;
+    }
+    return RVC_OK;
+}
+
+int rvc_debug_chain_stamps(rvc_ctx* ctx, int chain, long long* out2048) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!ctx->last || chain < 0 || size_t(chain) >= ctx->last->chains.size()) return RVC_ERR_INVALID_ARG;
+    ctx->sync_all();
+    launch_chain(ctx->last->chains[size_t(chain)], ctx->streams[0]);   // stand-alone replay on whatever the arena holds
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    chain_debug_read(out2048, 2048);
     return RVC_OK;
 }
 

@@ -8,6 +8,7 @@
 // applies the epilogue (deterministic, one launch).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "ops.h"
 
@@ -22,8 +23,15 @@ struct GemmSched {
 constexpr int GEMM2_BK = 32;
 constexpr int NUM_SMS = 148;
 
+inline int sched_env(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return (e && *e) ? std::atoi(e) : dflt;
+}
+
 inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     GemmSched s;
+    static const int kWant = sched_env("RVC_UMMA_WANT", 112), kBn128 = sched_env("RVC_UMMA_BN128_MIN", 56),
+                     kKbMin = sched_env("RVC_UMMA_KB_MIN", 4);
     const bool aligned = g.A.off % 16 == 0 && g.W.off % 16 == 0 && g.lda % 4 == 0 && g.seg_len % 4 == 0 &&
                          g.seg_stride % 4 == 0 && g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
     if (!aligned || g.K < 64) return s;  // tiny / oddly aligned contractions stay on the v1 kernel
@@ -39,12 +47,12 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
         const int tiles128 = tm * ((g.N + 127) / 128) * g.batch;
         int bn = 128;
         if (g.N <= 32) bn = 32;
-        else if (g.N <= 64 || tiles128 < 56) bn = 64;
+        else if (g.N <= 64 || tiles128 < kBn128) bn = 64;
         s.variant = bn == 128 ? 5 : (bn == 64 ? 6 : 7);
         s.bm = 128; s.bn = bn;
         s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
-        const int want = std::max(1, 112 / s.tiles);
-        const int maxsplit = std::max(1, nkb / 4);
+        const int want = std::max(1, kWant / s.tiles);
+        const int maxsplit = std::max(1, nkb / kKbMin);
         // split-K group = one thread-block cluster (partials reduced over DSMEM): power of two <= 8
         s.splitk = 1;
         while (s.splitk * 2 <= std::min(std::min(want, maxsplit), 8)) s.splitk *= 2;

@@ -1,0 +1,672 @@
+// kernels_chain.cu - the persistent chain kernel (chain.h): op table interpreter + grid barrier.
+//
+// One cooperative launch of G CTAs x 256 threads walks a table of phases.  A phase is a set of
+// mutually independent ops (plan.cpp decides that at buffer granularity); its work items (GEMM
+// tiles x split-K slices, pooling / normalisation row groups) are dealt round-robin to the CTAs;
+// a grid barrier (one L2 atomic + acquire spin per CTA) separates phases.  Activations written in
+// one phase are read in the next through L2 only (cp.async.cg / ld.global.cg): the L1s are not
+// coherent across SMs and there is no kernel boundary to invalidate them.
+//
+// GEMM tile (exact fp32, same contraction as ops.h GemmOp): BM x BN = 1024 outputs, BK = 32,
+// cp.async ring; warp w owns k-quad w of every k-tile and accumulates the whole tile for it
+// (32 accumulators per thread: lanes along N, rows in registers), the 8 per-warp partial tiles
+// are summed through shared memory in fixed order; split-K slices go to a scratch area and the
+// last CTA to arrive on a tile (atomic ticket) adds them in z order - deterministic sums.
+#include <cstdio>
+
+#include "chain.h"
+#include "launch.h"
+
+namespace rvc {
+
+namespace {
+
+using namespace gemmk;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// activation out of line: the transcendental bodies (erff, tanhf, expf) would otherwise be replicated in every
+// tile variant and blow the kernel past the instruction cache
+__device__ __noinline__ float chain_act(int act, float v) { return apply_act(act, v); }
+__device__ __forceinline__ float chain_act_fast(int act, float v) {
+    if (act == ACT_NONE) return v;
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    return chain_act(act, v);
+}
+
+// final accumulator -> output element; identical arithmetic to gemmk::epilogue_elem, residual read through L2
+__device__ __noinline__ void chain_epilogue(const GemmParams& p, const float* __restrict__ bias, float* C, float* C2, const float* R,
+                                               int m, int n, float acc, float acc_partner, float r_pre = 0.f) {
+    const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
+    if (p.act == ACT_GATE) {
+        if (n & 1) return;
+        const float v0 = fmaf(p.alpha, acc, bias ? __ldg(bias + n) : 0.f);
+        const float v1 = fmaf(p.alpha, acc_partner, bias ? __ldg(bias + n + 1) : 0.f);
+        float g = tanhf(v0) * sigmoid_f(v1);
+        const int col = n >> 1;
+        if (R) g += __ldcg(R + (long long)m * p.ldr + col);
+        if (masked) g = 0.f;
+        C[(long long)m * p.ldc + col] = g;
+        if (C2) C2[(long long)m * p.ldc2 + col] = masked ? 0.f : apply_act(p.act2, g);
+        return;
+    }
+    float v = apply_act(p.act, fmaf(p.alpha, acc, bias ? __ldg(bias + n) : 0.f));
+    if (p.out_mode == OUT_PLAIN) {
+        v += r_pre;   // residual fetched ahead of the contraction (0 when R is read here)
+        if (R) v += __ldcg(R + (long long)m * p.ldr + n);
+        if (masked) v = 0.f;
+        C[(long long)m * p.ldc + n] = v;
+        if (C2) C2[(long long)m * p.ldc2 + n] = masked ? 0.f : apply_act(p.act2, v);
+    } else if (p.out_mode == OUT_PIXSHUF2) {
+        const int qt = m / p.om_a, qf = m - qt * p.om_a;
+        if (qf >= p.om_a - 2) return;
+        const int ph = n / p.om_b, co = n - ph * p.om_b, rt = ph >> 1, rf = ph & 1;
+        C[((long long)(2 * qt + rt) * p.om_c + (2 * qf + rf)) * p.ldc + co] = masked ? 0.f : v;
+    } else {  // OUT_CONVT1D
+        const int r = n / p.om_b, co = n - r * p.om_b;
+        const int o = m * p.om_a + r - p.om_c;
+        if (o < 0 || o >= p.om_d) return;
+        C[(long long)o * p.ldc + co] = v;
+        if (C2) C2[(long long)o * p.ldc2 + co] = apply_act(p.act2, v);
+    }
+}
+
+__device__ long long g_chain_stamp[256 * 8];   // [phase][event] clock64 of CTA 0 thread 0, first item of the phase
+#define CH_STAMP(e) do { if (blockIdx.x == 0 && threadIdx.x == 0 && stamp_row >= 0) g_chain_stamp[stamp_row * 8 + (e)] = clock64(); } while (0)
+
+// Per-shape constants of one tile variant.  Lanes = LC columns x LK k-quads (LC * LK = 32), every thread
+// keeps all BM rows of its CT columns in registers (BM * CT <= 32 accumulators): the A fragment of a k-quad is
+// one 16-byte broadcast per row, the W fragment one conflict-free LDS.128 per column (rows padded by 4 words:
+// row r starts at bank 4r).  A k-tile holds BK = 32 * LK * QPW floats = 8 * LK * QPW k-quads, warp w / lane
+// group lk owning quads (w * LK + lk) + j * 8 * LK.  Narrow tiles (BN = 8, 16) therefore keep the full
+// register reuse of the 32-wide tile: weight-streaming ops (M <= 32) get one tile per CTA without split-K.
+template <int BM, int BN, int LK, int QPW, int STAGES>
+struct TileCfg {
+    static constexpr int LK_ = LK, QPW_ = QPW;
+    static constexpr int BK = 32 * LK * QPW;
+    static constexpr int LDS = BK + 4;
+    static constexpr int LC = 32 / LK;             // lanes along N
+    static constexpr int CT = BN / LC;             // columns per thread (stride LC)
+    static constexpr int NP = 8 * LK;              // partial tiles to sum at the end
+    static constexpr int STAGE_FLOATS = (BM + BN) * LDS;
+    static constexpr int CHUNKS_A = BM * (BK / 4), CHUNKS_W = BN * (BK / 4);
+    static constexpr int CPT_A = (CHUNKS_A + CHAIN_THREADS - 1) / CHAIN_THREADS;
+    static constexpr int CPT_W = (CHUNKS_W + CHAIN_THREADS - 1) / CHAIN_THREADS;
+    static constexpr int OUTS = BM * BN;
+    static constexpr int OPT = (OUTS + CHAIN_THREADS - 1) / CHAIN_THREADS;
+    static_assert(CT >= 1 && CT * LC == BN && BM * CT <= 32, "tile shape");
+    static_assert(STAGES * STAGE_FLOATS * 4 <= CHAIN_SMEM_BYTES, "stage ring exceeds the chain's shared memory");
+    static_assert(NP * OUTS * 4 <= CHAIN_SMEM_BYTES, "reduction buffer exceeds the chain's shared memory");
+};
+
+// W half of the stage loads of k-tiles [kt_first, kt_end): weights do not depend on earlier phases, so the
+// caller may issue these BEFORE the grid barrier (no commit here: they join the first A group)
+template <class T, int BM>
+__device__ __forceinline__ void gemm_issue_w(const GemmParams& p, int n0, int bz, int kt_first, int kt_end, int slot0, float* smem) {
+    const float* __restrict__ W = p.W + bz * p.sW;
+#pragma unroll 1
+    for (int i = 0; i < T::CPT_W; ++i) {
+        const int c = threadIdx.x + i * CHAIN_THREADS;
+        if (c >= T::CHUNKS_W) break;
+        const int row = c / (T::BK / 4), kc = (c % (T::BK / 4)) * 4;
+        const int n = n0 + row;
+        const float* base = n < p.N ? W + (long long)n * p.ldw : nullptr;
+#pragma unroll 1
+        for (int kt = kt_first, slot = slot0; kt < kt_end; ++kt, ++slot) {
+            const int kk = kt * T::BK + kc;
+            const bool ok = base && kk < p.K;
+            cp_async16(smem + slot * T::STAGE_FLOATS + (BM + row) * T::LDS + kc, ok ? base + kk : p.W, ok ? 16 : 0);
+        }
+    }
+}
+
+// L2 prefetch of this tile's own weight rows beyond the stages already requested
+template <class T>
+__device__ __forceinline__ void gemm_prefetch_w(const GemmParams& p, int n0, int bz, int k_from, int k_to) {
+    if (k_to <= k_from) return;
+    const char* W = reinterpret_cast<const char*>(p.W + bz * p.sW);
+    const int lpr = ((k_to - k_from) * 4 + 127) >> 7;
+    const int rows = min(T::CT * T::LC, p.N - n0);
+    for (int l = threadIdx.x; l < rows * lpr; l += CHAIN_THREADS) {
+        const int r = l / lpr, c = l - r * lpr;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(W + ((long long)(n0 + r) * p.ldw + k_from) * 4 + c * 128));
+    }
+}
+
+template <class T, int BM, int BN, int STAGES>
+__device__ __forceinline__ void gemm_tile(const GemmParams& p, int m0, int n0, int z, int bz, int tile_id, float* smem, int* s_last,
+                                          bool w_preloaded, int stamp_row) {
+    CH_STAMP(1);
+    constexpr int LC = T::LC, LK = T::LK_, CT = T::CT, LDS = T::LDS, BK = T::BK, OUTS = T::OUTS, OPT = T::OPT;
+    constexpr int CPT_A = T::CPT_A, CPT_W = T::CPT_W;
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    const int lc = lane % LC, lk = lane / LC;
+    const int K = p.K, seg_len = p.seg_len >= p.K ? (1 << 30) : p.seg_len;
+    const long long seg_wrap = p.seg_stride - p.seg_len;   // pointer bump when a chunk walks into the next segment
+    const int nkt_total = (K + BK - 1) / BK;
+    const int kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split);
+    const int nkt = max(0, kt1 - kt0);
+
+    // Per-thread chunk cursors (16-byte pieces of the stage): source pointer + position inside the A segment,
+    // advanced by BK after every issue - no divisions, no descriptor reads inside the k loop.
+    const float* aptr[CPT_A]; int awithin[CPT_A]; int adst[CPT_A];
+    const float* wptr[CPT_W]; int wdst[CPT_W];
+    int a_k, w_k;   // k index of chunk column 0 of the next k-tile to issue (per operand)
+    {
+        const float* __restrict__ A = p.A + bz * p.sA;
+        const float* __restrict__ W = p.W + bz * p.sW;
+        const int kbase = kt0 * BK;
+#pragma unroll
+        for (int i = 0; i < CPT_A; ++i) {
+            const int c = tid + i * CHAIN_THREADS;
+            const int row = c / (BK / 4), kc = (c % (BK / 4)) * 4;
+            const int m = m0 + row, kk = kbase + kc;
+            adst[i] = (c < T::CHUNKS_A) ? row * LDS + kc : -1;
+            const int seg = kk / seg_len;
+            awithin[i] = kk - seg * seg_len;
+            aptr[i] = (m < p.M) ? A + (long long)m * p.lda + (long long)seg * p.seg_stride + awithin[i] : nullptr;
+        }
+        const int wskip = w_preloaded ? min(nkt, STAGES - 1) : 0;   // W stages already requested before the barrier
+#pragma unroll
+        for (int i = 0; i < CPT_W; ++i) {
+            const int c = tid + i * CHAIN_THREADS;
+            const int row = c / (BK / 4), kc = (c % (BK / 4)) * 4;
+            const int n = n0 + row;
+            wdst[i] = (c < T::CHUNKS_W) ? (BM + row) * LDS + kc : -1;
+            wptr[i] = (n < p.N) ? W + (long long)n * p.ldw + kbase + wskip * BK + kc : nullptr;
+        }
+        a_k = kbase; w_k = kbase + wskip * BK;
+    }
+    auto issue_a = [&](int slot) {
+        float* st = smem + slot * T::STAGE_FLOATS;
+#pragma unroll
+        for (int i = 0; i < CPT_A; ++i) {
+            if (adst[i] >= 0) {
+                const int kc = adst[i] % LDS;
+                const bool ok = aptr[i] && (a_k + kc) < K;
+                cp_async16(st + adst[i], ok ? aptr[i] : p.W, ok ? 16 : 0);
+                if (aptr[i]) {
+                    aptr[i] += BK; awithin[i] += BK;
+                    while (awithin[i] >= seg_len) { awithin[i] -= seg_len; aptr[i] += seg_wrap; }
+                }
+            }
+        }
+        a_k += BK;
+    };
+    auto issue_w = [&](int slot) {
+        float* st = smem + slot * T::STAGE_FLOATS;
+#pragma unroll
+        for (int i = 0; i < CPT_W; ++i) {
+            if (wdst[i] >= 0) {
+                const int kc = (wdst[i] - BM * LDS) % LDS;
+                const bool ok = wptr[i] && (w_k + kc) < K;
+                cp_async16(st + wdst[i], ok ? wptr[i] : p.W, ok ? 16 : 0);
+                if (wptr[i]) wptr[i] += BK;
+            }
+        }
+        w_k += BK;
+    };
+
+    float acc[BM][CT];
+#pragma unroll
+    for (int i = 0; i < BM; ++i)
+#pragma unroll
+        for (int j = 0; j < CT; ++j) acc[i][j] = 0.f;
+    // residual operand of the epilogue: requested now so its L2 round trip overlaps the contraction
+    const float* Rb = p.R ? p.R + bz * p.sR : nullptr;
+    const bool r_plain = Rb && p.out_mode == OUT_PLAIN && p.act != ACT_GATE && (p.splitk == 1);
+    float rpre[OPT];
+#pragma unroll
+    for (int i = 0; i < OPT; ++i) {
+        const int idx = tid + i * CHAIN_THREADS;
+        const int m = m0 + idx / BN, n = n0 + idx % BN;
+        rpre[i] = (r_plain && idx < OUTS && m < p.M && n < p.N) ? __ldcg(Rb + (long long)m * p.ldr + n) : 0.f;
+    }
+
+#pragma unroll 1
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nkt) { if (!w_preloaded) issue_w(s); issue_a(s); }
+        cp_async_commit();
+    }
+    CH_STAMP(2);
+#pragma unroll 1
+    for (int kt = 0; kt < nkt; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kt == 0) CH_STAMP(3);
+        if (kt == 1) CH_STAMP(4);
+        if (kt + STAGES - 1 < nkt) {
+            const int slot = (kt + STAGES - 1) % STAGES;
+            issue_w(slot); issue_a(slot);
+        }
+        cp_async_commit();
+        const float* st = smem + (kt % STAGES) * T::STAGE_FLOATS;
+#pragma unroll
+        for (int qq = 0; qq < T::QPW_; ++qq) {
+            const int kq = wq * LK + lk + qq * 8 * LK;
+            const float* As = st + kq * 4;
+            const float* Ws = st + (BM + lc) * LDS + kq * 4;
+            float4 b[CT];
+#pragma unroll
+            for (int j = 0; j < CT; ++j) b[j] = *reinterpret_cast<const float4*>(Ws + j * LC * LDS);
+            constexpr int RG = BM >= 8 ? 8 : BM;
+#pragma unroll
+            for (int i0 = 0; i0 < BM; i0 += RG) {
+                float4 a[RG];
+#pragma unroll
+                for (int r = 0; r < RG; ++r) a[r] = *reinterpret_cast<const float4*>(As + (i0 + r) * LDS);
+#pragma unroll
+                for (int j = 0; j < CT; ++j) {
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].x, b[j].x, acc[i0 + r][j]);
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].y, b[j].y, acc[i0 + r][j]);
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].z, b[j].z, acc[i0 + r][j]);
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) acc[i0 + r][j] = fmaf(a[r].w, b[j].w, acc[i0 + r][j]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // stage buffers are free: reuse them for the per-(warp, lane group) partial tiles
+    CH_STAMP(5);
+    float* red = smem;  // [8 * LK][BM][BN]
+    {
+        const int pw = wq * LK + lk;
+#pragma unroll
+        for (int i = 0; i < BM; ++i)
+#pragma unroll
+            for (int j = 0; j < CT; ++j) red[(pw * BM + i) * BN + j * LC + lc] = acc[i][j];
+    }
+    __syncthreads();
+    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
+    float* C = p.C + bz * p.sC;
+    float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
+    const float* R = r_plain ? nullptr : Rb;
+    float v[OPT];
+#pragma unroll
+    for (int i = 0; i < OPT; ++i) {
+        const int idx = tid + i * CHAIN_THREADS;
+        float s = 0.f;
+        if (idx < OUTS) {
+#pragma unroll
+            for (int w = 0; w < T::NP; ++w) s += red[w * OUTS + idx];
+        }
+        v[i] = s;
+    }
+    if (p.splitk > 1) {
+        float* part = p.scratch + ((long long)(bz * p.splitk + z) * p.M) * p.N;
+#pragma unroll
+        for (int i = 0; i < OPT; ++i) {
+            const int idx = tid + i * CHAIN_THREADS;
+            const int m = m0 + idx / BN, n = n0 + idx % BN;
+            if (idx < OUTS && m < p.M && n < p.N) __stcg(part + (long long)m * p.N + n, v[i]);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned ticket = atomicAdd(p.counters + tile_id, 1u);
+            *s_last = (ticket == unsigned(p.splitk - 1)) ? 1 : 0;
+            if (*s_last) p.counters[tile_id] = 0;  // self-cleaning for the next replay
+        }
+        __syncthreads();
+        const int last = *s_last;
+        if (!last) return;   // (uniform per CTA) the caller syncs before the next item touches smem
+        __threadfence();
+        const float* base = p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N;
+#pragma unroll
+        for (int i = 0; i < OPT; ++i) v[i] = 0.f;
+#pragma unroll 1
+        for (int zz = 0; zz < p.splitk; ++zz) {
+#pragma unroll
+            for (int i = 0; i < OPT; ++i) {
+                const int idx = tid + i * CHAIN_THREADS;
+                const int m = m0 + idx / BN, n = n0 + idx % BN;
+                if (idx < OUTS && m < p.M && n < p.N) v[i] += __ldcg(base + ((long long)zz * p.M + m) * p.N + n);
+            }
+        }
+    }
+    if (p.out_mode == OUT_PLAIN && p.act != ACT_GATE) {
+        // common case inline, parameters in registers (same arithmetic as chain_epilogue)
+        const int act = p.act, act2 = p.act2, mask_period = p.mask_period, mask_valid = p.mask_valid;
+        const float alpha = p.alpha;
+        const long long ldc = p.ldc, ldc2 = p.ldc2, ldr = p.ldr;
+#pragma unroll
+        for (int i = 0; i < OPT; ++i) {
+            const int idx = tid + i * CHAIN_THREADS;
+            const int m = m0 + idx / BN, n = n0 + idx % BN;
+            if (idx >= OUTS || m >= p.M || n >= p.N) continue;
+            float o = chain_act_fast(act, fmaf(alpha, v[i], bias ? __ldg(bias + n) : 0.f)) + rpre[i];
+            if (R) o += __ldcg(R + (long long)m * ldr + n);
+            const bool masked = mask_period > 0 && (m % mask_period) >= mask_valid;
+            if (masked) o = 0.f;
+            C[(long long)m * ldc + n] = o;
+            if (C2) C2[(long long)m * ldc2 + n] = masked ? 0.f : chain_act_fast(act2, o);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < OPT; ++i) {
+            const int idx = tid + i * CHAIN_THREADS;
+            const int m = m0 + idx / BN, n = n0 + idx % BN;
+            const float partner = __shfl_xor_sync(0xffffffffu, v[i], 1);  // BN is even: the gate partner column is a lane neighbour
+            if (idx >= OUTS || m >= p.M || n >= p.N) continue;
+            chain_epilogue(p, bias, C, C2, R, m, n, v[i], partner, rpre[i]);
+        }
+    }
+    CH_STAMP(6);
+}
+
+// dispatch over the tile variants (chain.h ChainTile); `what` 0 = run the tile, 1 = issue the first W stages and
+// prefetch the rest of the tile's weight rows into L2 (both before the grid barrier)
+__device__ __forceinline__ void gemm_dispatch(const ChainOpDev& o, int local, float* smem, int* s_last, bool w_preloaded, int what,
+                                              int stamp_row = -1) {
+    const GemmParams& p = o.g;
+    const int z = local % o.splitk;
+    const int tile = local / o.splitk;
+    const int tn = tile % o.tiles_n;
+    const int tm = (tile / o.tiles_n) % o.tiles_m;
+    const int bz = tile / (o.tiles_n * o.tiles_m);
+#define RVC_TILE_CASE(ID, BM, BN, LK, QPW, ST)                                                                               \
+    case ID: {                                                                                                               \
+        using T = TileCfg<BM, BN, LK, QPW, ST>;                                                                              \
+        if (what == 0) gemm_tile<T, BM, BN, ST>(p, tm * BM, tn * BN, z, bz, tile, smem, s_last, w_preloaded, stamp_row);     \
+        else {                                                                                                               \
+            const int nkt_total = (p.K + T::BK - 1) / T::BK, kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split); \
+            const int kte = min(kt1, kt0 + ST - 1);                                                                          \
+            gemm_issue_w<T, BM>(p, tn * BN, bz, kt0, kte, 0, smem);                                                          \
+            gemm_prefetch_w<T>(p, tn * BN, bz, kte * T::BK, min(p.K, kt1 * T::BK));                                          \
+        }                                                                                                                    \
+        break;                                                                                                               \
+    }
+    switch (o.variant) {
+        // (BM, BN, LK, QPW, stages): every ring keeps 75-90 KB of loads in flight per CTA - at ~0.5-0.8 us of L2
+        // latency that is what one SM needs to pull ~100 GB/s
+        RVC_TILE_CASE(CT_32x32, 32, 32, 1, 2, 5)
+        RVC_TILE_CASE(CT_16x64, 16, 64, 1, 2, 4)
+        RVC_TILE_CASE(CT_8x128, 8, 128, 1, 1, 4)
+        RVC_TILE_CASE(CT_32x16, 32, 16, 2, 1, 6)
+        RVC_TILE_CASE(CT_32x8, 32, 8, 4, 1, 4)
+        RVC_TILE_CASE(CT_8x32, 8, 32, 1, 4, 4)
+        RVC_TILE_CASE(CT_8x16, 8, 16, 2, 2, 6)
+        RVC_TILE_CASE(CT_16x16, 16, 16, 2, 2, 5)
+        default: break;
+    }
+#undef RVC_TILE_CASE
+}
+
+// tiny / unaligned contractions (K < 64 or rows that are not 16-byte aligned): one output per thread-slot
+__device__ __forceinline__ void gemm_direct_item(const GemmParams& p, int local) {
+    const long long total = (long long)p.M * p.N;
+    const bool contiguous = p.seg_len >= p.K;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const long long o = (long long)local * 1024 + i * CHAIN_THREADS + threadIdx.x;
+        const bool ok = o < total;
+        const int m = ok ? int(o / p.N) : 0, n = ok ? int(o - (long long)m * p.N) : 0;
+        const float* a = p.A + (long long)m * p.lda;
+        const float* w = p.W + (long long)n * p.ldw;
+        float acc = 0.f;
+        if (ok) {
+            if (contiguous) {
+                for (int k = 0; k < p.K; ++k) acc = fmaf(__ldcg(a + k), __ldg(w + k), acc);
+            } else {
+                for (int k = 0; k < p.K; ++k) {
+                    const int seg = k / p.seg_len, within = k - seg * p.seg_len;
+                    acc = fmaf(__ldcg(a + (long long)seg * p.seg_stride + within), __ldg(w + k), acc);
+                }
+            }
+        }
+        const float partner = __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (ok) chain_epilogue(p, p.bias, p.C, p.C2, p.R, m, n, acc, partner);
+    }
+}
+
+__device__ __forceinline__ void avgpool_item(const ChainOpDev& o, int local) {
+    const int T = o.i0, F = o.i1, C = o.i2, To = T / 2, Fo = F / 2;
+    const long long n = (long long)To * Fo * C, ldin = o.ld0;
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+        const long long e = (long long)local * 1024 + i * CHAIN_THREADS + threadIdx.x;
+        if (e >= n) continue;
+        const int c = int(e % C);
+        const long long r = e / C;
+        const int f = int(r % Fo), t = int(r / Fo);
+        const float* q = o.x0 + ((long long)(2 * t + 1) * (F + 2) + 2 * f + 1) * ldin + c;
+        const float v = (__ldcg(q) + __ldcg(q + ldin) + __ldcg(q + (long long)(F + 2) * ldin) + __ldcg(q + (long long)(F + 3) * ldin)) * 0.25f;
+        o.y0[((long long)(t + 1) * (Fo + 2) + f + 1) * C + c] = v;
+    }
+}
+
+// one warp per row, 8 rows per item (cols <= 1024)
+__device__ __forceinline__ void layernorm_item(const ChainOpDev& o, int local) {
+    const int row = local * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int rows = o.i0, cols = o.i1;
+    if (row >= rows) return;
+    const float* x = o.x0 + (long long)row * o.ld0;
+    float v[32];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = lane + i * 32;
+        v[i] = c < cols ? __ldcg(x + c) : 0.f;
+        s += v[i];
+    }
+    const float mean = warp_sum(s) / float(cols);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = lane + i * 32;
+        const float d = c < cols ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / float(cols) + o.f0);
+    float* y = o.y0 + (long long)row * o.ld1;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int c = lane + i * 32;
+        if (c < cols) y[c] = (v[i] - mean) * rstd * __ldg(o.x1 + c) + __ldg(o.x2 + c);
+    }
+}
+
+// VITS windowed relative-position attention: one item = one (head, query row); same arithmetic order as
+// relattn_kernel (kernels_misc.cu) so the chain and the stand-alone kernel agree bit for bit
+__device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, float* sm) {
+    const int T = o.i0, heads = o.i1, dim = o.i2, window = o.i3;
+    const int h = local / T, i = local - h * T;
+    const int HD = heads * dim, nrel = 2 * window + 1;
+    const long long ld = o.ld0;
+    const float* qkv = o.x0;
+    float* qs = sm;          // [dim]
+    float* ps = qs + dim;    // [T]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = CHAIN_THREADS >> 5;
+    for (int d = tid; d < dim; d += CHAIN_THREADS) qs[d] = __ldcg(qkv + (long long)i * ld + h * dim + d);
+    __syncthreads();
+    for (int j = warp; j < T; j += nw) {
+        const float* k = qkv + (long long)j * ld + HD + h * dim;
+        const int rel = j - i + window;
+        const float* rk = (rel >= 0 && rel < nrel) ? o.x1 + rel * dim : nullptr;
+        float a = 0.f;
+        for (int d = lane; d < dim; d += 32) a = fmaf(qs[d], __ldcg(k + d) + (rk ? __ldg(rk + d) : 0.f), a);
+        a = warp_sum(a);
+        if (lane == 0) ps[j] = a;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -3.402823466e+38f;
+        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, ps[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) { const float e = expf(ps[j] - mx); ps[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < T; j += 32) ps[j] *= inv;
+    }
+    __syncthreads();
+    for (int d = tid; d < dim; d += CHAIN_THREADS) {
+        float a = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const int rel = j - i + window;
+            float v = __ldcg(qkv + (long long)j * ld + 2 * HD + h * dim + d);
+            if (rel >= 0 && rel < nrel) v += __ldg(o.x2 + rel * dim + d);
+            a = fmaf(ps[j], v, a);
+        }
+        o.y0[(long long)i * o.ld1 + h * dim + d] = a;
+    }
+}
+
+constexpr int CHAIN_MAX_OPS = 256;   // table entries kept in shared memory (plan.cpp splits longer runs)
+
+__global__ void __launch_bounds__(CHAIN_THREADS, 1)
+chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict__ phases, int n_ops, int n_phases, unsigned int* bar,
+             unsigned long long* dbg) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ ChainOpDev s_op;
+    __shared__ ChainPhaseDev s_phase[CHAIN_MAX_OPS];
+    __shared__ int s_item_end[CHAIN_MAX_OPS];   // item0 + items of every op (within its phase)
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const unsigned int G = gridDim.x;
+    for (int i = tid; i < n_phases; i += CHAIN_THREADS) s_phase[i] = phases[i];
+    for (int i = tid; i < n_ops; i += CHAIN_THREADS) s_item_end[i] = ops[i].item0 + ops[i].items;
+    __syncthreads();
+    int cur = -1;            // op whose descriptor sits in s_op
+    bool pre = false;        // s_op + the W stages of this CTA's first item of the phase are already in flight
+    auto fetch_op = [&](const ChainPhaseDev& P, int item) {   // all threads; ends with a barrier
+        int o = P.op0;
+        while (o + 1 < P.op1 && item >= s_item_end[o]) ++o;
+        if (o != cur) {
+            const int* src = reinterpret_cast<const int*>(ops + o);
+            int* dst = reinterpret_cast<int*>(&s_op);
+            for (int i = tid; i < int(sizeof(ChainOpDev) / 4); i += CHAIN_THREADS) dst[i] = src[i];
+            cur = o;
+        }
+        __syncthreads();
+    };
+    constexpr int OP_WORDS = int(sizeof(ChainOpDev) / 4);
+    static_assert(OP_WORDS <= CHAIN_THREADS, "descriptor is copied one word per thread");
+    for (int ph = 0; ph < n_phases; ++ph) {
+        const ChainPhaseDev P = s_phase[ph];
+        if (dbg && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[ph] = t; }
+        // descriptor of this CTA's first item of the NEXT phase: requested now (one word per thread, in
+        // registers) so that it has long arrived when the phase ends
+        int nxt_o = -1, nxt_word = 0;
+        if (ph + 1 < n_phases) {
+            const ChainPhaseDev Q = s_phase[ph + 1];
+            if (int(blockIdx.x) < Q.items) {
+                int o = Q.op0;
+                while (o + 1 < Q.op1 && int(blockIdx.x) >= s_item_end[o]) ++o;
+                nxt_o = o;
+                if (tid < OP_WORDS) nxt_word = __ldg(reinterpret_cast<const int*>(ops + o) + tid);
+            }
+        }
+        bool first = true;
+        for (int item = blockIdx.x; item < P.items; item += G) {
+            const bool preloaded = first && pre;
+            if (!preloaded) {
+                __syncthreads();  // previous item is done with smem / s_op
+                fetch_op(P, item);
+            }
+            const int stamp_row = (first && ph < 256) ? ph : -1;
+            CH_STAMP(0);
+            first = false;
+            const int local = item - s_op.item0;
+            switch (s_op.kind) {
+                case CH_GEMM: gemm_dispatch(s_op, local, smem, &s_last, preloaded, 0, stamp_row); break;
+                case CH_GEMM_DIRECT: gemm_direct_item(s_op.g, local); break;
+                case CH_AVGPOOL: avgpool_item(s_op, local); break;
+                case CH_LAYERNORM: layernorm_item(s_op, local); break;
+                case CH_RELATTN: relattn_item(s_op, local, smem); break;
+                default: break;
+            }
+        }
+        pre = false;
+        if (ph + 1 < n_phases) {
+            // arrive first, then use the wait: descriptor + first weight stages of this CTA's next item
+            __syncthreads();
+            if (tid == 0) {
+                // arrivals are counted on bar[0]; the last one publishes the phase on bar[32] (its own 128-byte
+                // line), so the waiters' polling never queues behind the atomics
+                __threadfence();
+                const unsigned int ticket = atomicAdd(bar, 1u);
+                if (ticket == (unsigned int)(ph + 1) * G - 1) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 32), "r"((unsigned int)(ph + 1)) : "memory"); }
+                if (blockIdx.x == 0 && ph < 256) g_chain_stamp[ph * 8 + 7] = clock64();
+            }
+            if (nxt_o >= 0) {
+                if (tid < OP_WORDS) reinterpret_cast<int*>(&s_op)[tid] = nxt_word;
+                cur = nxt_o;
+                __syncthreads();
+                if (s_op.kind == CH_GEMM) gemm_dispatch(s_op, int(blockIdx.x) - s_op.item0, smem, &s_last, false, 1);
+                pre = true;
+            }
+            if (tid == 0) {
+                const unsigned int target = (unsigned int)(ph + 1);
+                const long long t0 = clock64();
+                while (true) {
+                    unsigned int v;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 32) : "memory");
+                    if (v >= target) break;
+                    if (nxt_o < 0) __nanosleep(200);   // CTAs with nothing to do next phase poll gently
+                    if (clock64() - t0 > (6ll << 30)) __trap();  // a CTA that never arrives must fail loudly, not hang the GPU
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (dbg && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[n_phases] = t; }
+    // exit ticket: the last CTA out re-arms the barrier words for the next launch / graph replay
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(bar + 1, 1u) == G - 1) { bar[0] = 0; bar[1] = 0; bar[32] = 0; __threadfence(); }
+    }
+}
+
+int g_chain_max_ctas = 0;
+
+}  // namespace
+
+void init_chain_attributes() {
+    cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES);
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_kernel, CHAIN_THREADS, CHAIN_SMEM_BYTES);
+    g_chain_max_ctas = per_sm * sms;
+}
+
+int chain_max_coresident_ctas() { return g_chain_max_ctas; }
+
+void chain_debug_read(long long* out, int n) { cudaMemcpyFromSymbol(out, g_chain_stamp, sizeof(long long) * size_t(n)); }
+
+int launch_chain(const ChainDev& c, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = CHAIN_SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident or none: the grid barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const ChainOpDev* ops = c.d_ops; const ChainPhaseDev* phases = c.d_phases; int no = c.n_ops, n = c.n_phases; unsigned int* bar = c.d_bar;
+    unsigned long long* dbg = c.d_dbg;
+    cudaLaunchKernelEx(&cfg, chain_kernel, ops, phases, no, n, bar, dbg);
+    return 1;
+}
+
+}  // namespace rvc

@@ -5,6 +5,7 @@
 
 #include <cfloat>
 
+#include "chain.h"
 #include "launch.h"
 #include "pdl.cuh"
 #include "noise.h"
@@ -454,6 +455,7 @@ void init_kernel_attributes() {
     cudaFuncSetAttribute(relattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     init_gemm_v2_attributes();
     init_umma_attributes();
+    init_chain_attributes();
 }
 
 void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n, cudaStream_t stream) {

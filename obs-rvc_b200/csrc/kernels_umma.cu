@@ -117,6 +117,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 __device__ long long g_umma_dbg[16];
+// 1 = store the truncated A_hi back (explicit); 0 = leave the fp32 tile as delivered by TMA and rely on the tensor
+// core ignoring the 13 low mantissa bits of a tf32 operand (saves a third of the converter's shared-memory writes)
+__device__ int g_dev_write_hi = 0;   // RVC_UMMA_WRITE_HI=1 restores the explicit store
 #define UMMA_DBG(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_umma_dbg[i] = clock64(); } while (0)
 
 template <int BN, int PASSES>
@@ -241,7 +244,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
                         h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
                         h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
-                        a[(b + j) * 32 + lane] = h;
+                        if (g_dev_write_hi) a[(b + j) * 32 + lane] = h;
                         lo[(b + j) * 32 + lane] = make_float4(v[j].x - h.x, v[j].y - h.y, v[j].z - h.z, v[j].w - h.w);
                     }
                 }
@@ -439,6 +442,7 @@ void init_umma_attributes() {
     cudaFuncSetAttribute(umma_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 1>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 1>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 1>::SMEM_BYTES);
+    { const char* w = getenv("RVC_UMMA_WRITE_HI"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_dev_write_hi, &v, sizeof(int)); }
     const char* e = getenv("RVC_UMMA_PASSES");
     if (e && e[0] == '1') g_umma_passes = 1;
 }

@@ -64,11 +64,16 @@ struct PlanOptions {
     bool with_index = false; int32_t index_rows = 0;
     bool multi_lane = true;  // independent branches on separate stream lanes
     bool allow_umma = true;  // dense GEMMs on the tcgen05 3xTF32 kernel (needs hi/lo weight copies)
+    // persistent chain kernels (chain.h): CTA budget of a chain on lane 0 (nothing else running) and
+    // on a side lane (shares the GPU with the tcgen05 GEMMs of lane 0); 0 disables chains
+    int32_t chain_grid_main = 0, chain_grid_side = 0;
+    int32_t chain_side_max_m = 0;  // side-lane GEMMs join a chain only up to this many rows (0 = no limit)
 };
 
 struct Plan {
     std::vector<Op> ops;
     std::vector<NamedBuf> bufs;
+    std::vector<ChainInfo> chains;
     int64_t work_bytes = 0;
     int32_t n_lanes = 1;
     // well-known buffers

@@ -59,6 +59,9 @@ struct GemmOp {
     // kernel schedule chosen at plan time (gemm_sched.h): 0 = v1 tile kernel, >0 = v2 cp.async
     // split-K variant; scratch[splitk][batch][M][N] partial tiles + one arrival counter per tile
     int32_t sched_variant = 0, splitk = 1; Ref scratch, counters;
+    // schedule of the same op when it runs inside a persistent chain (chain.h): tile shape
+    // (-1 = scalar "direct" path for tiny / unaligned contractions), tile grid and split-K
+    int32_t ch_variant = -1, ch_tiles_m = 0, ch_tiles_n = 0, ch_splitk = 1; Ref ch_scratch, ch_counters;
 };
 
 struct LayerNormOp {  // y = (x-mean)/sqrt(var+eps)*gamma+beta over `cols`, biased variance
@@ -160,6 +163,7 @@ enum OpKind : int32_t {
 struct Op {
     int32_t kind = OP_FILL;
     int32_t lane = 0;
+    int32_t chain = -1;  // index into Plan::chains when the op executes inside a persistent chain kernel
     std::string name;  // plan-unique; debug lookups + parity tests
     // exactly one of these is meaningful, selected by `kind`
     GemmOp gemm; LayerNormOp ln; AttnOp attn; RelAttnOp relattn; Conv0StatsOp c0s; Conv0ApplyOp c0a;
@@ -182,6 +186,10 @@ struct RunParams {
 static const int NOISE_KIND_Z = 1;
 static const int NOISE_KIND_SINE = 2;
 static const int KNN_PARTS = 148 * 16;  // one part per warp; 2 CTAs of 8 warps per SM
+
+// A run of consecutive same-lane ops executed by one persistent cooperative kernel (chain.h).
+// phase[i] is the barrier phase of op first+i: ops of one phase touch disjoint buffers.
+struct ChainInfo { int32_t first = 0, count = 0, lane = 0, grid = 0, n_phases = 0; std::vector<int32_t> phase; };
 
 // A named buffer of the plan (debug / result lookups).
 struct NamedBuf { std::string name; Ref ref; int64_t elems = 0; int32_t is_int = 0; };

@@ -27,9 +27,12 @@ struct PB {
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
 
+    std::vector<int64_t> alloc_starts;  // byte offsets of every work-arena allocation (ascending)
+
     Ref alloc(const std::string& name, int64_t elems, bool is_int = false) {
         work = (work + 255) & ~int64_t(255);
         Ref r{SP_WORK, work};
+        alloc_starts.push_back(work);
         work += elems * 4;
         if (!name.empty()) plan.bufs.push_back(NamedBuf{name, r, elems, is_int ? 1 : 0});
         return r;
@@ -492,6 +495,121 @@ void schedule_gemms(PB& b) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent chains (chain.h): runs of small same-lane ops that one cooperative kernel executes
+// with grid barriers instead of kernel boundaries.
+// ------------------------------------------------------------------------------------------
+bool gemm_aligned(const GemmOp& g) {
+    return g.A.off % 16 == 0 && g.W.off % 16 == 0 && g.lda % 4 == 0 && g.seg_len % 4 == 0 && g.seg_stride % 4 == 0 &&
+           g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
+}
+
+bool chain_eligible(const Op& op, int side_max_m) {
+    switch (op.kind) {
+        case OP_GEMM: {
+            const GemmOp& g = op.gemm;
+            if (g.sched_variant >= 5) return false;              // tcgen05 kernel
+            // side lanes share the GPU with lane 0: only their weight-streaming ops (tiny M, one tile per CTA of a
+            // small grid) are worth a resident chain; the wide ones want all SMs for a few microseconds each
+            if (op.lane != 0 && side_max_m > 0 && g.M > side_max_m) return false;
+            if (gemm_aligned(g) && g.K >= 64) return true;       // tile path
+            return g.K < 64 && g.batch == 1;                     // scalar path: tiny contractions only
+        }
+        case OP_AVGPOOL: return op.lane == 0 || side_max_m <= 0;
+        case OP_LAYERNORM: return op.ln.cols <= 1024;
+        case OP_RELATTN: return op.relattn.dim + op.relattn.T <= 4096;
+        default: return false;
+    }
+}
+
+// buffer identity at allocation granularity (work arena) / whole space (everything else)
+int64_t buf_id(const PB& b, const Ref& r) {
+    if (r.null()) return INT64_MIN;
+    if (r.space != SP_WORK) return -int64_t(r.space) - 1;
+    auto it = std::upper_bound(b.alloc_starts.begin(), b.alloc_starts.end(), r.off);
+    return int64_t(it - b.alloc_starts.begin()) - 1;
+}
+
+void op_buffers(const PB& b, const Op& op, std::vector<int64_t>& rd, std::vector<int64_t>& wr) {
+    rd.clear(); wr.clear();
+    auto R = [&](const Ref& r) { if (!r.null()) rd.push_back(buf_id(b, r)); };
+    auto Wt = [&](const Ref& r) { if (!r.null()) wr.push_back(buf_id(b, r)); };
+    switch (op.kind) {
+        case OP_GEMM: R(op.gemm.A); R(op.gemm.R); Wt(op.gemm.C); Wt(op.gemm.C2); break;
+        case OP_AVGPOOL: R(op.pool.in); Wt(op.pool.out); break;
+        case OP_LAYERNORM: R(op.ln.X); Wt(op.ln.Y); break;
+        case OP_RELATTN: R(op.relattn.qkv); Wt(op.relattn.out); break;
+        default: break;
+    }
+}
+
+// Tile shape + split-K of a GEMM inside a chain of G CTAs: minimise a small cost model (cycles) over the
+// eight tile variants of chain.h - waves x (K x max(FMA rate, L2->SM load rate) + per-k-tile and per-tile
+// overheads), with an optional split-K round trip when even the smallest useful tile leaves CTAs idle.
+void chain_schedule_gemm(PB& b, GemmOp& g, int G) {
+    if (!(gemm_aligned(g) && g.K >= 64)) { g.ch_variant = -1; g.ch_splitk = 1; return; }
+    // id (chain.h ChainTile), BM, BN, LK (k-quads across lanes), BK
+    static const struct { int id, bm, bn, lk, bk; } V[8] = {{0, 32, 32, 1, 64},  {1, 16, 64, 1, 64},  {2, 8, 128, 1, 32}, {3, 32, 16, 2, 64},
+                                                            {4, 32, 8, 4, 128},  {5, 8, 32, 1, 128},  {6, 8, 16, 2, 128}, {7, 16, 16, 2, 128}};
+    double best = 1e30;
+    for (const auto& v : V) {
+        const int tm = (g.M + v.bm - 1) / v.bm, tn = (g.N + v.bn - 1) / v.bn, tiles = tm * tn * g.batch;
+        const int nkt = (g.K + v.bk - 1) / v.bk;
+        const int ct = v.bn / (32 / v.lk);
+        // cycles per unit of K for one CTA: FMA issue (~60% of 128 lanes), shared-memory wavefronts (one 16-byte
+        // broadcast per row + 4 per W column, 8 * LK quads in flight), L2 -> SM bytes at ~64 B/clk; + per-k-tile sync
+        const double per_k = std::max(std::max(v.bm * v.bn / 77.0, 1.5 * (v.bm + 4.0 * ct) / (4.0 * v.lk)), (v.bm + v.bn) * 4 / 64.0) + 150.0 / v.bk;
+        for (int sk = 1; sk <= 8; sk *= 2) {
+            if (sk > 1 && (tiles * sk > G || nkt / sk < 2)) break;
+            const int waves = (tiles * sk + G - 1) / G;
+            const double cost = waves * (double(nkt / sk + (nkt % sk ? 1 : 0)) * v.bk * per_k + 2500.0) + (sk > 1 ? 4000.0 : 0.0);
+            if (cost < best - 1e-9) {
+                best = cost; g.ch_variant = v.id; g.ch_tiles_m = tm; g.ch_tiles_n = tn; g.ch_splitk = sk;
+            }
+        }
+    }
+    if (g.ch_splitk > 1) {
+        g.ch_scratch = b.alloc("", int64_t(g.ch_splitk) * g.batch * g.M * g.N);
+        g.ch_counters = b.alloc("", g.ch_tiles_m * g.ch_tiles_n * g.batch, true);
+    }
+}
+
+void form_chains(PB& b, const PlanOptions& opt) {
+    std::vector<Op>& ops = b.plan.ops;
+    const int n = int(ops.size());
+    std::vector<int64_t> rd, wr;
+    int i = 0;
+    while (i < n) {
+        if (!chain_eligible(ops[i], opt.chain_side_max_m)) { ++i; continue; }
+        int j = i;
+        while (j < n && j - i < 256 && ops[j].lane == ops[i].lane && chain_eligible(ops[j], opt.chain_side_max_m)) ++j;  // 256 = table size of the kernel
+        const int G = ops[i].lane == 0 ? opt.chain_grid_main : opt.chain_grid_side;
+        if (j - i >= 4 && G > 0) {
+            ChainInfo c;
+            c.first = i; c.count = j - i; c.lane = ops[i].lane; c.grid = G;
+            std::vector<int64_t> cur_rd, cur_wr;
+            int phase = 0;
+            for (int k = i; k < j; ++k) {
+                op_buffers(b, ops[k], rd, wr);
+                bool conflict = false;
+                for (int64_t x : rd) conflict |= std::find(cur_wr.begin(), cur_wr.end(), x) != cur_wr.end();
+                for (int64_t x : wr)
+                    conflict |= std::find(cur_wr.begin(), cur_wr.end(), x) != cur_wr.end() ||
+                                std::find(cur_rd.begin(), cur_rd.end(), x) != cur_rd.end();
+                if (conflict) { ++phase; cur_rd.clear(); cur_wr.clear(); }
+                cur_rd.insert(cur_rd.end(), rd.begin(), rd.end());
+                cur_wr.insert(cur_wr.end(), wr.begin(), wr.end());
+                c.phase.push_back(phase);
+                ops[k].chain = int(b.plan.chains.size());
+                if (ops[k].kind == OP_GEMM) chain_schedule_gemm(b, ops[k].gemm, G);
+            }
+            c.n_phases = phase + 1;
+            b.plan.chains.push_back(c);
+        }
+        i = j;
+    }
+}
+
 }  // namespace
 
 bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const Packed* cv, const CvInfo* cvi,
@@ -522,6 +640,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         s.ks.cand_d = cd; s.ks.cand_i = ci; s.ks.idx = idx; s.ks.d2 = d2; s.ks.Q = Q; s.ks.k = k; s.ks.parts = parts;
         plan.knn_q = Q;
         schedule_gemms(b);
+    form_chains(b, opt);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -531,6 +650,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm, N, plan.params, true, 0);
         plan.f0_T = o.T;
         schedule_gemms(b);
+    form_chains(b, opt);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -546,6 +666,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
             if (int64_t(2 * T + 1) * cvi->out_dim > StateLayout::AUDIO_CAP) b.fail("feature too large");
         }
         schedule_gemms(b);
+    form_chains(b, opt);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -557,6 +678,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
         plan.f0_T = o.T;
         schedule_gemms(b);
+    form_chains(b, opt);
         plan.work_bytes = b.work + 256;
         return b.ok;
     }
@@ -626,6 +748,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     build_synth(b, syn, *syi, phone, pitch, pitchf, plan.params, plan.audio, R, ml);
     plan.audio_len = audio_len;
     schedule_gemms(b);
+    form_chains(b, opt);
     plan.work_bytes = b.work + 256;
     return b.ok;
 }

@@ -315,6 +315,22 @@ class RvcInfer:
         self._chk(self._L.rvc_profile_ops(self._h, c_int32(iters), buf, c_size_t(cap), byref(nb)))
         return json.loads(buf.value.decode())
 
+    def profile_timeline(self) -> list:
+        import json
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        nb = c_size_t()
+        self._chk(self._L.rvc_profile_timeline(self._h, buf, c_size_t(cap), byref(nb)))
+        return json.loads(buf.value.decode())
+
+    def profile_chains(self) -> list:
+        import json
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        nb = c_size_t()
+        self._chk(self._L.rvc_profile_chains(self._h, buf, c_size_t(cap), byref(nb)))
+        return json.loads(buf.value.decode())
+
     def reset_state(self):
         self._chk(self._L.rvc_reset_state(self._h))
 
