@@ -45,13 +45,14 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
         // one CTA per SM (smem-limited) and clusters must pack into GPCs: aim for a single wave of
         // <= ~112 CTAs; prefer 128-wide tiles (less operand traffic per flop) when that still fills it
         const int tiles128 = tm * ((g.N + 127) / 128) * g.batch;
+        const int bn128_min = g.cta_budget > 0 ? std::max(1, kBn128 * g.cta_budget / kWant) : kBn128;
         int bn = 128;
         if (g.N <= 32) bn = 32;
-        else if (g.N <= 64 || tiles128 < kBn128) bn = 64;
+        else if (g.N <= 64 || tiles128 < bn128_min) bn = 64;
         s.variant = bn == 128 ? 5 : (bn == 64 ? 6 : 7);
         s.bm = 128; s.bn = bn;
         s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
-        const int want = std::max(1, kWant / s.tiles);
+        const int want = std::max(1, (g.cta_budget > 0 ? g.cta_budget : kWant) / s.tiles);
         const int maxsplit = std::max(1, nkb / kKbMin);
         // split-K group = one thread-block cluster (partials reduced over DSMEM): power of two <= 8
         s.splitk = 1;

@@ -139,6 +139,7 @@ __device__ __forceinline__ void gemm_issue_w(const GemmParams& p, int n0, int bz
 // L2 prefetch of this tile's own weight rows beyond the stages already requested
 template <class T>
 __device__ __forceinline__ void gemm_prefetch_w(const GemmParams& p, int n0, int bz, int k_from, int k_to) {
+    if (p.bias && threadIdx.x == CHAIN_THREADS - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bias + bz * p.sBias + n0));
     if (k_to <= k_from) return;
     const char* W = reinterpret_cast<const char*>(p.W + bz * p.sW);
     const int lpr = ((k_to - k_from) * 4 + 127) >> 7;
@@ -231,12 +232,14 @@ __device__ __forceinline__ void gemm_tile(const GemmParams& p, int m0, int n0, i
     // residual operand of the epilogue: requested now so its L2 round trip overlaps the contraction
     const float* Rb = p.R ? p.R + bz * p.sR : nullptr;
     const bool r_plain = Rb && p.out_mode == OUT_PLAIN && p.act != ACT_GATE && (p.splitk == 1);
-    float rpre[OPT];
+    float rpre[OPT], bpre[OPT];   // bias too: parameter vectors are cold in L2 every window (HBM round trip)
+    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
 #pragma unroll
     for (int i = 0; i < OPT; ++i) {
         const int idx = tid + i * CHAIN_THREADS;
         const int m = m0 + idx / BN, n = n0 + idx % BN;
         rpre[i] = (r_plain && idx < OUTS && m < p.M && n < p.N) ? __ldcg(Rb + (long long)m * p.ldr + n) : 0.f;
+        bpre[i] = (bias && idx < OUTS && n < p.N) ? __ldg(bias + n) : 0.f;
     }
 
 #pragma unroll 1
@@ -297,7 +300,6 @@ __device__ __forceinline__ void gemm_tile(const GemmParams& p, int m0, int n0, i
             for (int j = 0; j < CT; ++j) red[(pw * BM + i) * BN + j * LC + lc] = acc[i][j];
     }
     __syncthreads();
-    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
     float* C = p.C + bz * p.sC;
     float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
     const float* R = r_plain ? nullptr : Rb;
@@ -354,7 +356,7 @@ __device__ __forceinline__ void gemm_tile(const GemmParams& p, int m0, int n0, i
             const int idx = tid + i * CHAIN_THREADS;
             const int m = m0 + idx / BN, n = n0 + idx % BN;
             if (idx >= OUTS || m >= p.M || n >= p.N) continue;
-            float o = chain_act_fast(act, fmaf(alpha, v[i], bias ? __ldg(bias + n) : 0.f)) + rpre[i];
+            float o = chain_act_fast(act, fmaf(alpha, v[i], bpre[i])) + rpre[i];
             if (R) o += __ldcg(R + (long long)m * ldr + n);
             const bool masked = mask_period > 0 && (m % mask_period) >= mask_valid;
             if (masked) o = 0.f;
@@ -463,6 +465,36 @@ __device__ __forceinline__ void layernorm_item(const ChainOpDev& o, int local) {
     const float* x = o.x0 + (long long)row * o.ld0;
     float v[32];
     float s = 0.f;
+    const int nv = (cols + 31) >> 5;   // columns per lane actually present (<= 32)
+    if (nv <= 8) {
+        // narrow rows (the synthesizer's 192 channels): everything in flight at once, gamma / beta included -
+        // parameter vectors are cold every window
+        float gg[8], bb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane + i * 32;
+            v[i] = c < cols ? __ldcg(x + c) : 0.f;
+            gg[i] = c < cols ? __ldg(o.x1 + c) : 0.f;
+            bb[i] = c < cols ? __ldg(o.x2 + c) : 0.f;
+            s += v[i];
+        }
+        const float mean = warp_sum(s) / float(cols);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane + i * 32;
+            const float d = c < cols ? v[i] - mean : 0.f;
+            q += d * d;
+        }
+        const float rstd = rsqrtf(warp_sum(q) / float(cols) + o.f0);
+        float* y = o.y0 + (long long)row * o.ld1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane + i * 32;
+            if (c < cols) y[c] = (v[i] - mean) * rstd * gg[i] + bb[i];
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         const int c = lane + i * 32;
@@ -486,25 +518,36 @@ __device__ __forceinline__ void layernorm_item(const ChainOpDev& o, int local) {
     }
 }
 
-// VITS windowed relative-position attention: one item = one (head, query row); same arithmetic order as
-// relattn_kernel (kernels_misc.cu) so the chain and the stand-alone kernel agree bit for bit
+// VITS windowed relative-position attention: one item = one (head, query row).  K, V and the two relative
+// tables of the head are staged in shared memory with every load in flight at once (a dependent chain of L2 /
+// cold-HBM round trips otherwise); the reductions keep the order of relattn_kernel (kernels_misc.cu), so the
+// chain and the stand-alone kernel agree bit for bit.
 __device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, float* sm) {
     const int T = o.i0, heads = o.i1, dim = o.i2, window = o.i3;
     const int h = local / T, i = local - h * T;
     const int HD = heads * dim, nrel = 2 * window + 1;
     const long long ld = o.ld0;
     const float* qkv = o.x0;
-    float* qs = sm;          // [dim]
-    float* ps = qs + dim;    // [T]
+    float* qs = sm;                  // [dim]
+    float* ps = qs + dim;            // [T]
+    float* ks = ps + ((T + 3) & ~3); // [T][dim]
+    float* vs = ks + T * dim;        // [T][dim]
+    float* rks = vs + T * dim;       // [nrel][dim]
+    float* rvs = rks + nrel * dim;   // [nrel][dim]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = CHAIN_THREADS >> 5;
     for (int d = tid; d < dim; d += CHAIN_THREADS) qs[d] = __ldcg(qkv + (long long)i * ld + h * dim + d);
+    for (int e = tid; e < T * dim; e += CHAIN_THREADS) {
+        const int j = e / dim, d = e - j * dim;
+        ks[e] = __ldcg(qkv + (long long)j * ld + HD + h * dim + d);
+        vs[e] = __ldcg(qkv + (long long)j * ld + 2 * HD + h * dim + d);
+    }
+    for (int e = tid; e < nrel * dim; e += CHAIN_THREADS) { rks[e] = __ldg(o.x1 + e); rvs[e] = __ldg(o.x2 + e); }
     __syncthreads();
     for (int j = warp; j < T; j += nw) {
-        const float* k = qkv + (long long)j * ld + HD + h * dim;
         const int rel = j - i + window;
-        const float* rk = (rel >= 0 && rel < nrel) ? o.x1 + rel * dim : nullptr;
+        const bool inw = rel >= 0 && rel < nrel;
         float a = 0.f;
-        for (int d = lane; d < dim; d += 32) a = fmaf(qs[d], __ldcg(k + d) + (rk ? __ldg(rk + d) : 0.f), a);
+        for (int d = lane; d < dim; d += 32) a = fmaf(qs[d], ks[j * dim + d] + (inw ? rks[rel * dim + d] : 0.f), a);
         a = warp_sum(a);
         if (lane == 0) ps[j] = a;
     }
@@ -524,8 +567,8 @@ __device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, flo
         float a = 0.f;
         for (int j = 0; j < T; ++j) {
             const int rel = j - i + window;
-            float v = __ldcg(qkv + (long long)j * ld + 2 * HD + h * dim + d);
-            if (rel >= 0 && rel < nrel) v += __ldg(o.x2 + rel * dim + d);
+            float v = vs[j * dim + d];
+            if (rel >= 0 && rel < nrel) v += rvs[rel * dim + d];
             a = fmaf(ps[j], v, a);
         }
         o.y0[(long long)i * o.ld1 + h * dim + d] = a;
@@ -614,6 +657,14 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 cur = nxt_o;
                 __syncthreads();
                 if (s_op.kind == CH_GEMM) gemm_dispatch(s_op, int(blockIdx.x) - s_op.item0, smem, &s_last, false, 1);
+                else if (s_op.kind == CH_LAYERNORM || s_op.kind == CH_RELATTN) {
+                    // parameter vectors of the next op towards L2 (they are cold every window)
+                    const int bytes = (s_op.kind == CH_LAYERNORM ? s_op.i1 : (2 * s_op.i3 + 1) * s_op.i2) * 4;
+                    for (int l = tid * 128; l < bytes; l += CHAIN_THREADS * 128) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(s_op.x1) + l));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(s_op.x2) + l));
+                    }
+                }
                 pre = true;
             }
             if (tid == 0) {

@@ -58,6 +58,7 @@ struct GemmOp {
     int32_t out_mode = OUT_PLAIN; int32_t om_a = 0, om_b = 0, om_c = 0, om_d = 0;
     // kernel schedule chosen at plan time (gemm_sched.h): 0 = v1 tile kernel, >0 = v2 cp.async
     // split-K variant; scratch[splitk][batch][M][N] partial tiles + one arrival counter per tile
+    int32_t cta_budget = 0;  // >0: CTA target of this op (it shares the GPU with sibling lanes); 0 = scheduler default
     int32_t sched_variant = 0, splitk = 1; Ref scratch, counters;
     // schedule of the same op when it runs inside a persistent chain (chain.h): tile shape
     // (-1 = scalar "direct" path for tiny / unaligned contractions), tile grid and split-K

@@ -405,6 +405,10 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
         b.lane = 0;
     }
     static const int RATES[4] = {10, 10, 2, 2}, UK[4] = {16, 16, 4, 4}, RK[3] = {3, 7, 11}, RD[3] = {1, 3, 5};
+    // the three ResBlocks of a stage run on three lanes at once: each conv is scheduled for a third of the GPU
+    // so the lanes really overlap instead of queueing behind each other's full-width grids
+    static const int rb_budget_env = sched_env("RVC_RB_WANT", 0);
+    const int rb_budget = multi_lane ? rb_budget_env : 0;
     // conv_pre (+ cond(g) folded into the bias); lrelu'd copy feeds ups[0] (1 halo row)
     Ref pre_raw = b.alloc("sy.conv_pre", int64_t(R) * 512);
     Ref upin_pad = b.alloc("", int64_t(R + 2) * 512);
@@ -449,13 +453,14 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
             for (int dd = 0; dd < 3; ++dd) {
                 const int dil = RD[dd], pad1 = (rk * dil - dil) / 2, pad2 = (rk - 1) / 2;
                 std::string wn = d + "rb" + S(j) + "." + S(dd) + ".";
-                b.gemm(rn + S(dd) + ".c1", in_act_pad.plus(int64_t(HH - pad1) * cout), cout, cout, int64_t(dil) * cout,
+                GemmOp& g1 = b.gemm(rn + S(dd) + ".c1", in_act_pad.plus(int64_t(HH - pad1) * cout), cout, cout, int64_t(dil) * cout,
                        W(wn + "c1.w"), rk * cout, W(wn + "c1.b"), ta_pad.plus(int64_t(HH) * cout), cout, Tout, cout,
                        rk * cout, ACT_LRELU01);
+                g1.cta_budget = rb_budget;
                 GemmOp& g = b.gemm(rn + S(dd) + ".c2", ta_pad.plus(int64_t(HH - pad2) * cout), cout, rk * cout, 0,
                                    W(wn + "c2.w"), rk * cout, W(wn + "c2.b"), y, cout, Tout, cout, rk * cout,
                                    ACT_NONE);
-                g.R = res; g.ldr = cout;
+                g.R = res; g.ldr = cout; g.cta_budget = rb_budget;
                 if (dd < 2) { g.C2 = ya_pad.plus(int64_t(HH) * cout); g.ldc2 = cout; g.act2 = ACT_LRELU01; }
                 in_act_pad = ya_pad; res = y;
             }
@@ -517,7 +522,8 @@ bool chain_eligible(const Op& op, int side_max_m) {
         }
         case OP_AVGPOOL: return op.lane == 0 || side_max_m <= 0;
         case OP_LAYERNORM: return op.ln.cols <= 1024;
-        case OP_RELATTN: return op.relattn.dim + op.relattn.T <= 4096;
+        case OP_RELATTN:  // q, p, K, V and both relative tables staged in the chain's shared memory (90 KB)
+            return (op.relattn.dim + op.relattn.T + 4 + (2 * op.relattn.T + 2 * (2 * op.relattn.window + 1)) * op.relattn.dim) * 4 <= 88 * 1024;
         default: return false;
     }
 }
