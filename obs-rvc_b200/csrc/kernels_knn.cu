@@ -18,12 +18,16 @@ namespace rvc {
 
 namespace {
 
-template <int CV, int QN, int G, int KK>
-__global__ void __launch_bounds__(256)
+// RR index rows per warp iteration are held in registers, so every query fragment fetched from shared memory
+// is used RR times (the scan is otherwise bound by shared-memory reads of the queries, not by HBM); only the Q
+// real queries of a padded group are evaluated.  The 8 per-warp top-k lists of a CTA are merged in shared
+// memory before they leave the SM: one candidate list per CTA (`parts` = gridDim.x).
+template <int CV, int QN, int G, int KK, int RR>
+__global__ void __launch_bounds__(256, 1)
 knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __restrict__ queries, long long ldq, int Q,
                 float* __restrict__ cand_d, int* __restrict__ cand_i, int parts, int k) {
     pdl_enter();
-    extern __shared__ __align__(16) float qs[];  // [G*QN][C], zero padded
+    extern __shared__ __align__(16) float qs[];  // [G*QN][C], zero padded; reused for the CTA merge at the end
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C4 = C >> 2;
     for (int e = tid; e < G * QN * C; e += 256) {
@@ -31,8 +35,6 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
         qs[e] = q < Q ? queries[(long long)q * ldq + c] : 0.f;
     }
     __syncthreads();
-    const int part = blockIdx.x * 8 + warp;
-    if (part >= parts) return;
 
     float ld[G][KK]; int li[G][KK];
 #pragma unroll
@@ -41,81 +43,131 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
         for (int j = 0; j < KK; ++j) { ld[g][j] = FLT_MAX; li[g][j] = -1; }
 
     const float4* qs4 = reinterpret_cast<const float4*>(qs);
-    float4 y[CV], yn[CV];
-    auto load_row = [&](float4* dst, int n) {
-        const float4* row = reinterpret_cast<const float4*>(index + (long long)n * C);
+    float4 y[RR][CV], yn[RR][CV];
+    auto load_rows = [&](float4 (*dst)[CV], long long base) {
 #pragma unroll
-        for (int i = 0; i < CV; ++i) {
-            int c4 = lane + i * 32;
-            dst[i] = c4 < C4 ? __ldcs(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // streamed once: evict-first
+        for (int r = 0; r < RR; ++r) {
+            const float4* row = reinterpret_cast<const float4*>(index + (base + r) * C);
+            const bool ok = base + r < N;
+#pragma unroll
+            for (int i = 0; i < CV; ++i) {
+                int c4 = lane + i * 32;
+                dst[r][i] = (ok && c4 < C4) ? __ldcs(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);  // streamed once: evict-first
+            }
         }
     };
-    if (part < N) load_row(y, part);
-    for (int n = part; n < N; n += parts) {
-        const bool more = n + parts < N;
-        if (more) load_row(yn, n + parts);  // next row in flight while this one is reduced
+    const long long stride = (long long)parts * 8 * RR;
+    long long base = ((long long)blockIdx.x * 8 + warp) * RR;
+    if (base < N) load_rows(y, base);
+    for (; base < N; base += stride) {
+        const bool more = base + stride < N;
+        if (more) load_rows(yn, base + stride);  // next rows in flight while these are reduced
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            float v[QN];
+            float v[RR][QN];
 #pragma unroll
             for (int qq = 0; qq < QN; ++qq) {
-                const float4* xq = qs4 + (size_t)(g * QN + qq) * C4;
-                float a = 0.f;
+                float a[RR];
 #pragma unroll
-                for (int i = 0; i < CV; ++i) {
-                    int c4 = lane + i * 32;
-                    if (c4 < C4) {
-                        float4 x = xq[c4];
-                        float d0 = x.x - y[i].x, d1 = x.y - y[i].y, d2 = x.z - y[i].z, d3 = x.w - y[i].w;
-                        a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
+                for (int r = 0; r < RR; ++r) a[r] = 0.f;
+                if (g * QN + qq < Q) {   // warp-uniform: padded queries cost nothing
+                    const float4* xq = qs4 + (size_t)(g * QN + qq) * C4;
+#pragma unroll
+                    for (int i = 0; i < CV; ++i) {
+                        int c4 = lane + i * 32;
+                        if (c4 < C4) {
+                            const float4 x = xq[c4];
+#pragma unroll
+                            for (int r = 0; r < RR; ++r) {
+                                float d0 = x.x - y[r][i].x, d1 = x.y - y[r][i].y, d2 = x.z - y[r][i].z, d3 = x.w - y[r][i].w;
+                                a[r] = fmaf(d0, d0, a[r]); a[r] = fmaf(d1, d1, a[r]); a[r] = fmaf(d2, d2, a[r]); a[r] = fmaf(d3, d3, a[r]);
+                            }
+                        }
                     }
                 }
-                v[qq] = a;
+#pragma unroll
+                for (int r = 0; r < RR; ++r) v[r][qq] = a[r];
             }
-            // full-width steps while fewer than 32 values per lane group
 #pragma unroll
-            for (int s = 16; s >= QN; s >>= 1)
+            for (int r = 0; r < RR; ++r) {
+                // full-width steps while fewer than 32 values per lane group
 #pragma unroll
-                for (int i = 0; i < QN; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
-            // halving butterfly: after it, lane l holds the total of query (l & (QN-1))
+                for (int s = 16; s >= QN; s >>= 1)
 #pragma unroll
-            for (int s = QN / 2; s >= 1; s >>= 1) {
-                const bool up = (lane & s) != 0;
+                    for (int i = 0; i < QN; ++i) v[r][i] += __shfl_xor_sync(0xffffffffu, v[r][i], s);
+                // halving butterfly: after it, lane l holds the total of query (l & (QN-1))
 #pragma unroll
-                for (int i = 0; i < s; ++i) {
-                    float send = up ? v[i] : v[i + s];
-                    float keep = up ? v[i + s] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                for (int s = QN / 2; s >= 1; s >>= 1) {
+                    const bool up = (lane & s) != 0;
+#pragma unroll
+                    for (int i = 0; i < s; ++i) {
+                        float send = up ? v[r][i] : v[r][i + s];
+                        float keep = up ? v[r][i + s] : v[r][i];
+                        v[r][i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                    }
                 }
-            }
-            float cd = v[0];
-            if (cd < ld[g][KK - 1]) {
-                int ci = n;
+                float cd = v[r][0];
+                if (base + r < N && cd < ld[g][KK - 1]) {
+                    int ci = int(base + r);
 #pragma unroll
-                for (int j = 0; j < KK; ++j) {
-                    if (cd < ld[g][j]) {
-                        float td = ld[g][j]; int ti = li[g][j];
-                        ld[g][j] = cd; li[g][j] = ci; cd = td; ci = ti;
+                    for (int j = 0; j < KK; ++j) {
+                        if (cd < ld[g][j]) {
+                            float td = ld[g][j]; int ti = li[g][j];
+                            ld[g][j] = cd; li[g][j] = ci; cd = td; ci = ti;
+                        }
                     }
                 }
             }
         }
         if (more) {
 #pragma unroll
-            for (int i = 0; i < CV; ++i) y[i] = yn[i];
+            for (int r = 0; r < RR; ++r)
+#pragma unroll
+                for (int i = 0; i < CV; ++i) y[r][i] = yn[r][i];
         }
     }
+    // ---- CTA merge: 8 warp lists -> one list per query, (distance, row) ascending ----
+    __syncthreads();   // every warp is done with the queries
+    float* md = qs;                                               // [8][G*QN][KK]
+    int* mi = reinterpret_cast<int*>(qs + 8 * G * QN * KK);       // [8][G*QN][KK]
     if (lane < QN) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const int q = g * QN + lane;
-            if (q < Q) {
+        for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int j = 0; j < KK; ++j)
-                    if (j < k) {
-                        cand_d[((long long)q * parts + part) * k + j] = ld[g][j];
-                        cand_i[((long long)q * parts + part) * k + j] = li[g][j];
-                    }
+            for (int j = 0; j < KK; ++j) {
+                md[(warp * G * QN + g * QN + lane) * KK + j] = ld[g][j];
+                mi[(warp * G * QN + g * QN + lane) * KK + j] = li[g][j];
+            }
+    }
+    __syncthreads();
+    constexpr int NC = 8 * KK;            // candidates per query in the CTA
+    constexpr int CPL = (NC + 31) / 32;   // per lane
+    for (int q = warp; q < Q; q += 8) {
+        float cd_[CPL]; int ci_[CPL];
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) {
+            const int c = lane + u * 32, w = c / KK, j = c - w * KK;
+            const bool ok = c < NC;
+            const int id = ok ? mi[(w * G * QN + q) * KK + j] : -1;
+            cd_[u] = (ok && id >= 0) ? md[(w * G * QN + q) * KK + j] : FLT_MAX;
+            ci_[u] = (ok && id >= 0) ? id : INT_MAX;
+        }
+        for (int r = 0; r < k; ++r) {
+            float bd = FLT_MAX; int bi = INT_MAX;
+#pragma unroll
+            for (int u = 0; u < CPL; ++u)
+                if (cd_[u] < bd || (cd_[u] == bd && ci_[u] < bi)) { bd = cd_[u]; bi = ci_[u]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float od = __shfl_xor_sync(0xffffffffu, bd, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+#pragma unroll
+            for (int u = 0; u < CPL; ++u)
+                if (ci_[u] == bi && bi != INT_MAX) { cd_[u] = FLT_MAX; ci_[u] = INT_MAX; }   // row ids are unique: taken
+            if (lane == 0) {
+                cand_d[((long long)q * parts + blockIdx.x) * k + r] = bd;
+                cand_i[((long long)q * parts + blockIdx.x) * k + r] = bi == INT_MAX ? -1 : bi;
             }
         }
     }
@@ -186,13 +238,14 @@ knn_blend_kernel(const float* __restrict__ index, const int* __restrict__ idx, c
     }
 }
 
-template <int CV, int QN, int G, int KK>
+template <int CV, int QN, int G, int KK, int RR>
 void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaStream_t s) {
-    auto kern = knn_scan_kernel<CV, QN, G, KK>;
-    size_t smem = sizeof(float) * size_t(G) * QN * o.C;
+    auto kern = knn_scan_kernel<CV, QN, G, KK, RR>;
+    const size_t q_bytes = sizeof(float) * size_t(G) * QN * o.C, m_bytes = size_t(8) * G * QN * KK * 8;
+    const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-    launch_k(kern, dim3((o.parts + 7) / 8), dim3(256), smem, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
+    launch_k(kern, dim3(o.parts), dim3(256), smem, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
                                               B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k,
                                               B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
 }
@@ -203,10 +256,10 @@ int scan_dispatch_q(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
     int launches = 0;
     for (int q0 = 0; q0 < o.Q; q0 += maxq) {
         int nq = o.Q - q0 < maxq ? o.Q - q0 : maxq;
-        if (nq <= 8) scan_launch<CV, 8, 1, KK>(o, B, q0, nq, s);
-        else if (nq <= 16) scan_launch<CV, 16, 1, KK>(o, B, q0, nq, s);
-        else if (nq <= 32) scan_launch<CV, 32, 1, KK>(o, B, q0, nq, s);
-        else scan_launch<CV, 32, 4, 8>(o, B, q0, nq, s);
+        if (nq <= 8) scan_launch<CV, 8, 1, KK, (CV <= 2 ? 4 : 2)>(o, B, q0, nq, s);
+        else if (nq <= 16) scan_launch<CV, 16, 1, KK, 2>(o, B, q0, nq, s);
+        else if (nq <= 32) scan_launch<CV, 32, 1, KK, (CV <= 2 ? 2 : 1)>(o, B, q0, nq, s);
+        else scan_launch<CV, 32, 4, 8, (CV <= 2 ? 2 : 1)>(o, B, q0, nq, s);
         ++launches;
     }
     return launches;

@@ -137,7 +137,7 @@ struct ConvPostOp {  // tanh(conv1d(Cin->1, k)) on halo-padded channels-last inp
     Ref in; Ref w; Ref out; int32_t T = 0, C = 0, k = 0;
 };
 
-struct KnnScanOp {  // per-part top-k of D[q,n] = sum_c (x[q,c]-index[n,c])^2; part p owns rows p, p+parts, ...
+struct KnnScanOp {  // per-part top-k of D[q,n] = sum_c (x[q,c]-index[n,c])^2; the parts partition the rows (how is up to the executor)
     Ref index; Ref queries; int64_t ldq = 0; Ref cand_d, cand_i;  // [Q][parts][k]
     int32_t N = 0, C = 0, Q = 0, k = 0, parts = 0;
 };
@@ -186,7 +186,7 @@ struct RunParams {
 
 static const int NOISE_KIND_Z = 1;
 static const int NOISE_KIND_SINE = 2;
-static const int KNN_PARTS = 148 * 16;  // one part per warp; 2 CTAs of 8 warps per SM
+static const int KNN_PARTS = 148;  // one candidate list per CTA (8 warp lists merged on chip), one CTA per SM
 
 // A run of consecutive same-lane ops executed by one persistent cooperative kernel (chain.h).
 // phase[i] is the barrier phase of op first+i: ops of one phase touch disjoint buffers.
