@@ -15,7 +15,7 @@
 namespace rvc {
 
 struct GemmSched {
-    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM64/BN128 (v2);
+    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM32/BN32 (v2);
                       // 5/6/7: tcgen05 3xTF32 kernel (kernels_umma.cu) with BN = 128/64/32
     int bm = 0, bn = 0, splitk = 1, tiles = 0;
 };
@@ -63,6 +63,8 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     else if (g.M <= 16) { s.variant = 2; s.bm = 16; s.bn = 128; }
     else if (g.M <= 256) { s.variant = 3; s.bm = 32; s.bn = 64; }
     else { s.variant = 3; s.bm = 32; s.bn = 64; }
+    // tall, narrow outputs (RMVPE's top levels: thousands of pixels x 16 / 32 channels): half the tile width, half the k loop
+    if (g.N <= 32 && g.M >= 256) { s.variant = 4; s.bm = 32; s.bn = 32; }
     // narrow outputs: do not waste a 256/128-wide tile on a 32..64-column problem
     if (s.variant == 1 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
     if (s.variant == 2 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }

@@ -47,7 +47,7 @@ template <int BM, int BN, int STAGES>
 __global__ void __launch_bounds__(V2_THREADS, 1) gemm_v2_kernel(GemmParams p) {
     constexpr int TN = BN / 32;
     constexpr int HM = BM / 2;  // rows per warp
-    static_assert(HM * TN == 32, "32 accumulators per thread");
+    static_assert(HM * TN <= 32 && HM >= 1 && TN >= 1, "at most 32 accumulators per thread");
     constexpr int STAGE_FLOATS = (BM + BN) * LDS2;
     constexpr int CHUNKS = (BM + BN) * (BK2 / 4);          // 16-byte chunks per stage
     constexpr int CPT = (CHUNKS + V2_THREADS - 1) / V2_THREADS;  // chunks per thread
@@ -282,6 +282,7 @@ int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
         // (deeper rings were measured slower: profiles/README.md)
         case 1: launch_v2<8, 256, 3>(g, p, stream); break;
         case 2: launch_v2<16, 128, 4>(g, p, stream); break;
+        case 4: launch_v2<32, 32, 4>(g, p, stream); break;
         default: launch_v2<32, 64, 4>(g, p, stream); break;
     }
     return 1;
@@ -294,6 +295,7 @@ void init_gemm_v2_attributes() {
     cudaFuncSetAttribute(gemm_v2_kernel<8, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 3 * (8 + 256) * LDS2));
     cudaFuncSetAttribute(gemm_v2_kernel<16, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 4 * (16 + 128) * LDS2));
     cudaFuncSetAttribute(gemm_v2_kernel<32, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(gemm_v2_kernel<32, 32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
 }
 
 }  // namespace rvc

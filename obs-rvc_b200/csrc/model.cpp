@@ -322,7 +322,7 @@ bool pack_rmvpe(const RvcwFile& f, Packed& out, F0Info& info, std::string& err) 
     }
     pack_conv3x3(L, out, "cnn", "cnn.weight", "", "cnn.bias", 3, 16);
     {   // BiGRU(384 -> 256): input GEMM weights re-indexed onto the padded cnn rows [(F+2)*3]
-        const int F = 128, H = 256, KI = (F + 2) * 3;
+        const int F = 128, H = 256, KI = (F + 2) * 4;  // cnn map pixels are padded to 4 channels (plan.cpp)
         int64_t ow = out.add("gru.wih", int64_t(2) * 3 * H * KI), ob = out.add("gru.bih", 2 * 3 * H);
         int64_t oh = out.add("gru.whh_t", int64_t(2) * H * 3 * H), obh = out.add("gru.bhh", 2 * 3 * H);
         const char* sfx[2] = {"", "_reverse"};
@@ -334,7 +334,7 @@ bool pack_rmvpe(const RvcwFile& f, Packed& out, F0Info& info, std::string& err) 
             if (!wi || !wh || !bi || !bh) break;
             for (int g = 0; g < 3 * H; ++g) {
                 for (int c = 0; c < 3; ++c) for (int fq = 0; fq < F; ++fq)
-                    out.p(ow)[(int64_t(d) * 3 * H + g) * KI + (fq + 1) * 3 + c] = wi[int64_t(g) * 3 * F + c * F + fq];
+                    out.p(ow)[(int64_t(d) * 3 * H + g) * KI + (fq + 1) * 4 + c] = wi[int64_t(g) * 3 * F + c * F + fq];
                 out.p(ob)[d * 3 * H + g] = bi[g];
                 out.p(obh)[d * 3 * H + g] = bh[g];
                 for (int k = 0; k < H; ++k) out.p(oh)[(int64_t(d) * H + k) * 3 * H + g] = wh[int64_t(g) * H + k];

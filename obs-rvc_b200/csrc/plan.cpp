@@ -23,6 +23,7 @@ struct PB {
     bool ok = true;
     int64_t work = 0;
     int lane = 0;
+    int sc_lane = -1;   // >= 0: the 1x1 shortcut convs of RMVPE's residual blocks run on this lane, beside c1
     bool allow_umma = true;
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
@@ -188,15 +189,21 @@ void conv3x3(PB& b, const Packed* P, const std::string& name, const std::string&
 void conv_block_res(PB& b, const Packed* P, const std::string& name, const std::string& wp, const Map2d& in,
                     int cout, Ref dst_interior, int64_t ld_dst) {
     Map2d t1{b.pad2d(name + "t1", in.T, in.F, cout), in.T, in.F, cout};
-    conv3x3(b, P, name + "c1", wp + "c1", in, cout, t1.base.plus(interior(t1)), cout, ACT_RELU, Ref{}, 0);
     Ref R; int64_t ldr;
     const int M = in.T * (in.F + 2);
     if (in.C != cout) {
         Ref sc = b.alloc(name + "sc", int64_t(M) * cout);
+        const int home = b.lane;
+        const bool side = b.sc_lane >= 0 && b.sc_lane != home;
+        if (side) { b.wait(home, b.sc_lane); b.lane = b.sc_lane; }   // shortcut and c1 both only read `in`
         b.gemm(name + "sc", in.base.plus(interior(in)), in.C, in.C, 0, b.w(P, SP_F0, wp + "sc.w"), in.C,
                b.w(P, SP_F0, wp + "sc.b"), sc, cout, M, cout, in.C, ACT_NONE);
+        if (side) b.lane = home;
+        conv3x3(b, P, name + "c1", wp + "c1", in, cout, t1.base.plus(interior(t1)), cout, ACT_RELU, Ref{}, 0);
+        if (side) b.wait(b.sc_lane, home);
         R = sc; ldr = cout;
     } else {
+        conv3x3(b, P, name + "c1", wp + "c1", in, cout, t1.base.plus(interior(t1)), cout, ACT_RELU, Ref{}, 0);
         R = in.base.plus(interior(in)); ldr = in.C;
     }
     conv3x3(b, P, name + "c2", wp + "c2", t1, cout, dst_interior, ld_dst, ACT_RELU, R, ldr);
@@ -284,10 +291,12 @@ F0Out build_rmvpe(PB& b, const Packed* P, const F0Info& info, Ref pcm_window, in
         cin = cout;
     }
     b.alias("rm.dec4", cur.base, (int64_t(T + 2) * (F + 2)) * 16);
-    Map2d cn{b.pad2d("rm.cnn", T, F, 3), T, F, 3};
-    conv3x3(b, P, "rm.cnn", "cnn", cur, 3, cn.base.plus(interior(cn)), 3, ACT_NONE, Ref{}, 0);
+    // 3 output channels stored with a pixel stride of 4 (4th stays zero): rows of (F+2)*4 floats are 16-byte
+    // aligned, so the GRU input projection runs on the vectorised split-K kernel instead of the scalar one
+    Map2d cn{b.pad2d("rm.cnn", T, F, 4), T, F, 4};
+    conv3x3(b, P, "rm.cnn", "cnn", cur, 3, cn.base.plus(interior(cn)), 4, ACT_NONE, Ref{}, 0);
     // BiGRU input projections for both directions: rows of the padded cnn map are the GEMM rows
-    const int KI = (F + 2) * 3;
+    const int KI = (F + 2) * 4;
     Ref gi = b.alloc("rm.gi", int64_t(T) * 1536);
     b.gemm("rm.gi", cn.base.plus(KI), KI, KI, 0, W("gru.wih"), KI, W("gru.bih"), gi, 1536, T, 1536, KI, ACT_NONE);
     Ref h = b.alloc("rm.gru", int64_t(T) * 512);
@@ -695,14 +704,17 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     const int R = g.return_length, skip = g.skip_head;
     if (R <= 0) { err = "return_length must be positive"; return false; }
     const bool ml = opt.multi_lane;
-    // lane 1: F0 chain, concurrently with ContentVec on lane 0
-    if (ml) { b.wait(0, 1); b.lane = 1; }
-    F0Out fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
-    b.lane = 0;
-    plan.f0_T = fo.T;
+    // lane 1 (+ lane 3 for the shortcut convs): F0 chain, concurrently with ContentVec on lane 0.  The fork is
+    // recorded first, ContentVec is emitted before the F0 ops: graph nodes are created in op order and the lane
+    // that is emitted first was observed to start first (the other way round ContentVec began ~0.5 ms late).
+    if (ml) b.wait(0, 1);
     int T = 0;
     Ref x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
     if (!b.ok) return false;
+    if (ml) { b.lane = 1; b.sc_lane = 3; }
+    F0Out fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
+    b.lane = 0; b.sc_lane = -1;
+    plan.f0_T = fo.T;
     const int C = cvi->out_dim;
     plan.hubert_T = T; plan.hubert_C = C;
     const int ext = 2 * T + 1;
