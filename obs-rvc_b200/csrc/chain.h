@@ -52,6 +52,7 @@ constexpr int CHAIN_SMEM_BYTES = 90 * 1024;  // stage rings of 75-90 KB (kernels
 int launch_chain(const ChainDev& c, cudaStream_t stream);  // returns kernels launched (1)
 void init_chain_attributes();
 void chain_debug_read(long long* out, int n);  // [256 phases][8] clock64 stamps of the LAST chain launch, CTA 0
+void chain_debug_read2(long long* out, int n); // [256 phases][2]: barrier spin start / end of CTA 0
 int chain_max_coresident_ctas();  // occupancy-derived upper bound for a cooperative launch
 
 }  // namespace rvc

@@ -85,8 +85,10 @@ void cache_store(const std::string& key, const std::shared_ptr<ModelData>& d) {
 
 struct PlanKey {
     int kind; Geometry g; int with_index; int index_rows; int k;
+    int chains = 1;   // persistent chains on (single live stream on the device) or off (several streams share it)
     bool operator<(const PlanKey& o) const {
         if (kind != o.kind) return kind < o.kind;
+        if (chains != o.chains) return chains < o.chains;
         if (g < o.g) return true;
         if (o.g < g) return false;
         if (with_index != o.with_index) return with_index < o.with_index;
@@ -146,6 +148,7 @@ struct rvc_ctx {
     cudaEvent_t timers[8] = {nullptr};
     bool allow_umma = true;
     int chain_grid_main = 0, chain_grid_side = 0, chain_side_max_m = 8;
+    bool chain_force = false;   // RVC_CHAIN=2: keep chains even when several contexts share the device
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -246,6 +249,14 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
     return RVC_OK;
 }
 
+// Live contexts per device.  A chain is a cooperative launch that holds its CTAs for hundreds of microseconds:
+// the right trade for one latency-critical stream, the wrong one when several streams share the GPU (their
+// chains would queue behind each other: measured 450 vs 547 windows/s with 8 streams) - so plans are built
+// with chains only while the context is alone on its device.
+std::mutex g_live_mu;
+std::map<int, int> g_live_ctx;
+int live_contexts(int device) { std::lock_guard<std::mutex> lk(g_live_mu); return g_live_ctx[device]; }
+
 // Resolves the ops of every chain of the plan into the device tables the chain kernel walks.
 int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
     const DeviceBases B = ctx->bases(e);
@@ -320,13 +331,15 @@ int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
 
 int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     PlanKey key{int(kind), g, (ctx->index.loaded && kind == PLAN_INFER) ? 1 : 0, ctx->index_rows, ctx->cfg.index_k};
+    key.chains = (ctx->chain_force || live_contexts(ctx->cfg.device) <= 1) ? 1 : 0;
     auto it = ctx->plans.find(key);
     if (it != ctx->plans.end()) { *out = it->second.get(); return RVC_OK; }
     PlanOptions opt;
     opt.index_k = ctx->cfg.index_k; opt.upstream_cents_window = ctx->cfg.upstream_cents_window;
     opt.with_index = key.with_index || kind == PLAN_KNN; opt.index_rows = ctx->index_rows; opt.multi_lane = true;
     opt.allow_umma = ctx->allow_umma;
-    opt.chain_grid_main = ctx->chain_grid_main; opt.chain_grid_side = ctx->chain_grid_side; opt.chain_side_max_m = ctx->chain_side_max_m;
+    opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
+    opt.chain_side_max_m = ctx->chain_side_max_m;
     auto e = std::make_unique<PlanEntry>();
     std::string err;
     if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.d->packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.d->packed : nullptr,
@@ -455,6 +468,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
     {   // persistent chains: CTA budgets (0 = off).  RVC_CHAIN=0 disables both.
         const char* ev = getenv("RVC_CHAIN"); const bool on = !(ev && ev[0] == '0');
+        ctx->chain_force = ev && ev[0] == '2';
         const char* em = getenv("RVC_CHAIN_MAIN"); const char* es = getenv("RVC_CHAIN_SIDE");
         ctx->chain_grid_main = on ? (em ? atoi(em) : 148) : 0;
         ctx->chain_grid_side = on ? (es ? atoi(es) : 32) : 0;
@@ -489,6 +503,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     ctx->state.bytes = size_t(StateLayout::bytes);
     cudaMemsetAsync(ctx->state.d, 0, ctx->state.bytes, ctx->streams[0]);
     cudaStreamSynchronize(ctx->streams[0]);
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx[ctx->cfg.device]++; }
     *out = ctx.release();
     return RVC_OK;
 }
@@ -502,6 +517,7 @@ void rvc_destroy(rvc_ctx* ctx) {
     for (auto ev : ctx->events) cudaEventDestroy(ev);
     for (auto ev : ctx->timers) if (ev) cudaEventDestroy(ev);
     for (auto s : ctx->streams) if (s) cudaStreamDestroy(s);
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live_ctx[ctx->cfg.device]--; }
     delete ctx;
 }
 
@@ -950,8 +966,9 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
             flops = 3.0 * double(op.kd.N) * op.kd.C * op.kd.Q; wbytes = 4.0 * double(op.kd.N) * op.kd.C;
         }
         char buf[512];
-        std::snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"kind\": \"%s\", \"lane\": %d, \"us\": %.3f, \"flops\": %.0f, \"wbytes\": %.0f, \"iobytes\": %.0f, \"M\": %lld, \"variant\": %d, \"splitk\": %d}",
-                      first ? "" : ", ", op.name.c_str(), KN[op.kind], op.lane, double(ms) * 1e3 / iters, flops, wbytes, iobytes, grid, variant, splitk);
+        std::snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"kind\": \"%s\", \"lane\": %d, \"us\": %.3f, \"flops\": %.0f, \"wbytes\": %.0f, \"iobytes\": %.0f, \"M\": %lld, \"variant\": %d, \"splitk\": %d, \"chain\": %d}",
+                      first ? "" : ", ", op.name.c_str(), KN[op.kind], op.lane, double(ms) * 1e3 / iters, flops, wbytes, iobytes, grid, variant, splitk,
+                      (op.chain >= 0 && size_t(op.chain) < e.chains.size()) ? op.chain : -1);
         js += buf; first = false;
     }
     js += "]";
@@ -1064,6 +1081,7 @@ int rvc_debug_chain_stamps(rvc_ctx* ctx, int chain, long long* out2048) {
     launch_chain(ctx->last->chains[size_t(chain)], ctx->streams[0]);   // stand-alone replay on whatever the arena holds
     CK(cudaStreamSynchronize(ctx->streams[0]));
     chain_debug_read(out2048, 2048);
+    chain_debug_read2(out2048 + 2048, 512);
     return RVC_OK;
 }
 

@@ -87,6 +87,7 @@ __device__ __noinline__ void chain_epilogue(const GemmParams& p, const float* __
     }
 }
 
+__device__ long long g_chain_stamp2[256 * 2];  // [phase]: spin start, spin end (CTA 0)
 __device__ long long g_chain_stamp[256 * 8];   // [phase][event] clock64 of CTA 0 thread 0, first item of the phase
 #define CH_STAMP(e) do { if (blockIdx.x == 0 && threadIdx.x == 0 && stamp_row >= 0) g_chain_stamp[stamp_row * 8 + (e)] = clock64(); } while (0)
 
@@ -376,8 +377,9 @@ __device__ __forceinline__ void gemm_tile(const GemmParams& p, int m0, int n0, i
     CH_STAMP(6);
 }
 
-// dispatch over the tile variants (chain.h ChainTile); `what` 0 = run the tile, 1 = issue the first W stages and
-// prefetch the rest of the tile's weight rows into L2 (both before the grid barrier)
+// dispatch over the tile variants (chain.h ChainTile); `what` 0 = run the tile, 1 = prefetch the tile's weight rows
+// and bias into L2 (issued between the barrier arrival and the wait: weights do not depend on the previous phase.
+// Requesting the first cp.async stages there as well was measured slower: the extra instructions delay the poll.)
 __device__ __forceinline__ void gemm_dispatch(const ChainOpDev& o, int local, float* smem, int* s_last, bool w_preloaded, int what,
                                               int stamp_row = -1) {
     const GemmParams& p = o.g;
@@ -392,9 +394,7 @@ __device__ __forceinline__ void gemm_dispatch(const ChainOpDev& o, int local, fl
         if (what == 0) gemm_tile<T, BM, BN, ST>(p, tm * BM, tn * BN, z, bz, tile, smem, s_last, w_preloaded, stamp_row);     \
         else {                                                                                                               \
             const int nkt_total = (p.K + T::BK - 1) / T::BK, kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split); \
-            const int kte = min(kt1, kt0 + ST - 1);                                                                          \
-            gemm_issue_w<T, BM>(p, tn * BN, bz, kt0, kte, 0, smem);                                                          \
-            gemm_prefetch_w<T>(p, tn * BN, bz, kte * T::BK, min(p.K, kt1 * T::BK));                                          \
+            gemm_prefetch_w<T>(p, tn * BN, bz, kt0 * T::BK, min(p.K, kt1 * T::BK));                                          \
         }                                                                                                                    \
         break;                                                                                                               \
     }
@@ -632,7 +632,7 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
             first = false;
             const int local = item - s_op.item0;
             switch (s_op.kind) {
-                case CH_GEMM: gemm_dispatch(s_op, local, smem, &s_last, preloaded, 0, stamp_row); break;
+                case CH_GEMM: gemm_dispatch(s_op, local, smem, &s_last, false, 0, stamp_row); break;
                 case CH_GEMM_DIRECT: gemm_direct_item(s_op.g, local); break;
                 case CH_AVGPOOL: avgpool_item(s_op, local); break;
                 case CH_LAYERNORM: layernorm_item(s_op, local); break;
@@ -670,13 +670,16 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
             if (tid == 0) {
                 const unsigned int target = (unsigned int)(ph + 1);
                 const long long t0 = clock64();
+                if (blockIdx.x == 0 && ph < 256) g_chain_stamp2[ph * 2] = t0;
                 while (true) {
                     unsigned int v;
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 32) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 32) : "memory");   // plain L2 poll ...
                     if (v >= target) break;
                     if (nxt_o < 0) __nanosleep(200);   // CTAs with nothing to do next phase poll gently
                     if (clock64() - t0 > (6ll << 30)) __trap();  // a CTA that never arrives must fail loudly, not hang the GPU
                 }
+                __threadfence();   // ... one acquire-side fence once the phase is published
+                if (blockIdx.x == 0 && ph < 256) g_chain_stamp2[ph * 2 + 1] = clock64();
             }
             __syncthreads();
         }
@@ -706,6 +709,7 @@ void init_chain_attributes() {
 int chain_max_coresident_ctas() { return g_chain_max_ctas; }
 
 void chain_debug_read(long long* out, int n) { cudaMemcpyFromSymbol(out, g_chain_stamp, sizeof(long long) * size_t(n)); }
+void chain_debug_read2(long long* out, int n) { cudaMemcpyFromSymbol(out, g_chain_stamp2, sizeof(long long) * size_t(n)); }
 
 int launch_chain(const ChainDev& c, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};

@@ -278,7 +278,9 @@ def test_rvc_rpc_wire_protocol(env):
             p.stdin.flush()
             (nb,) = struct.unpack("<I", p.stdout.read(4))
             got = np.frombuffer(p.stdout.read(nb), dtype="<f4")
-            np.testing.assert_array_equal(got, want[w])
+            # the child process is alone on the GPU and runs the persistent-chain plan; this process holds other
+            # contexts and runs the same ops as separate kernels (engine.cu live_contexts): fp32 sums in another order
+            np.testing.assert_allclose(got, want[w], rtol=0, atol=2e-5)
     finally:
         p.kill()
 

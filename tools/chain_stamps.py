@@ -16,13 +16,13 @@ for i in range(3):
 chains = eng.profile_chains()
 L = rvc_b200.lib()
 for c in chains:
-    out = (ctypes.c_longlong * 2048)()
+    out = (ctypes.c_longlong * 2560)()
     rc = L.rvc_debug_chain_stamps(eng.handle, ctypes.c_int(c["chain"]), out)
-    t = np.array(list(out), dtype=np.int64).reshape(256, 8)
+    t = np.array(list(out)[:2048], dtype=np.int64).reshape(256, 8); t2 = np.array(list(out)[2048:], dtype=np.int64).reshape(256, 2)
     print(f"chain {c['chain']} grid {c['grid']} rc={rc}")
     for ph, P in enumerate(c["phases"][:256]):
         if ph % int(os.environ.get("EVERY", 4)) and "pool" not in P["ops"]:
             continue
         r = t[ph]
         nxt = t[ph + 1][0] if ph + 1 < len(c["phases"]) else r[7]
-        print(f"  ph{ph:3d} {P['ops'][:44]:44s} tile@{r[1]-r[0]:5d} issued@{r[2]-r[0]:6d} kt0@{r[3]-r[0]:6d} kt1@{r[4]-r[0]:6d} kdone@{r[5]-r[0]:6d} epi@{r[6]-r[0]:6d} arrive@{r[7]-r[0]:6d} next@{nxt-r[0]:6d}")
+        print(f"  ph{ph:3d} {P['ops'][:44]:44s} tile@{r[1]-r[0]:5d} issued@{r[2]-r[0]:6d} kt0@{r[3]-r[0]:6d} kt1@{r[4]-r[0]:6d} kdone@{r[5]-r[0]:6d} epi@{r[6]-r[0]:6d} arrive@{r[7]-r[0]:6d} spin@{t2[ph][0]-r[0]:6d} released@{t2[ph][1]-r[0]:6d} next@{nxt-r[0]:6d}")

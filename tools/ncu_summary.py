@@ -18,13 +18,16 @@ KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 
 
-def launches(tag):
+def launches(tag, last_n=0):
     path = os.path.join(GO, "launches.csv")
     if not os.path.exists(path):
         return
     lines = [l for l in open(path) if not l.startswith("==")]
     tot = collections.defaultdict(float); cnt = collections.Counter()
-    for row in csv.DictReader(lines):
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if last_n > 0:
+        rows = rows[-last_n:]   # exactly the last window (tools/ncu_window.py prints its launch count)
+    for row in rows:
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
         name = row["Kernel Name"].split("(")[0]
@@ -34,7 +37,7 @@ def launches(tag):
     s = sum(tot.values())
     with open(os.path.join(OUT, f"{tag}_launches_summary.md"), "w") as f:
         f.write(f"# ncu launch list, one graph-replayed window ({sum(cnt.values())} kernels, {s:.0f} us serialised, cold cache)\n\n")
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 815 -c 412 python bench.py --steps 3 --warmup 3`\n\n")
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python tools/ncu_window.py` (last window of the run)\n\n")
         f.write("| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(tot.items(), key=lambda x: -x[1]):
             f.write(f"| `{k}` | {cnt[k]} | {v:.1f} | {100 * v / s:.1f}% | {v / cnt[k]:.1f} |\n")
@@ -63,6 +66,6 @@ def full(tag, rep):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
-    launches(tag)
-    for rep in ("prof_umma", "prof_knn", "prof_gemm2"):
+    launches(tag, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    for rep in ("prof_umma", "prof_knn", "prof_gemm2", "prof_chain", "prof_knn2"):
         full(tag, rep)
