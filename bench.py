@@ -326,7 +326,9 @@ def main():
 
         order = sorted(fam.items(), key=lambda kv: -kv[1]["us"])
         roof = roof_of(*order[0])
-        roof["traffic"] = None
+        # dram__bytes_read+write of one launch of this kernel under `ncu --set full` (profiles/r01_d_prof_umma.md: grid
+        # (4,2,8) = a HiFiGAN stage-0 ResBlock conv, M=210 N=256; its W_hi + W_lo planes are 3.7-5.8 MB, + A): ~algorithmic
+        roof["traffic"] = 6.26e6 if order[0][0].startswith("umma") else None
         roof["note"] = ("achieved = sum of algorithmic bytes (weights + activations) or flops (2MNK) of this kernel's launches in one "
                         "window / sum of their device times; each op timed as a 10-launch CUDA graph between events on the "
                         "engine stream (rvc_profile_ops); ncu captures: profiles/")

@@ -33,7 +33,7 @@
 using namespace rvc;
 
 static bool g_sync_each = false;
-namespace rvc { bool g_use_pdl = false; }  // measured: no gain on this path (profiles/README), opt-in with RVC_PDL=1
+namespace rvc { bool g_use_pdl = false; thread_local int g_launch_priority = 0; }  // measured: no gain on this path (profiles/README), opt-in with RVC_PDL=1
 
 namespace {
 
@@ -148,6 +148,7 @@ struct rvc_ctx {
     cudaEvent_t timers[8] = {nullptr};
     bool allow_umma = true;
     int chain_grid_main = 0, chain_grid_side = 0, chain_side_max_m = 8;
+    int f0_priority = 0;        // launch priority of the F0 lanes' kernels (highest stream priority of the device; RVC_F0_PRIO=0 disables)
     bool chain_force = false;   // RVC_CHAIN=2: keep chains even when several contexts share the device
 
     int fail(int code, const std::string& m) { err = m; return code; }
@@ -231,6 +232,7 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
             ++ev;
             continue;
         }
+        rvc::g_launch_priority = (ctx->f0_priority != 0 && (op.lane == 1 || op.lane == 3) && op.name.compare(0, 3, "sy.") != 0) ? ctx->f0_priority : 0;
         if (op.chain >= 0 && size_t(op.chain) < e.chains.size()) {
             // the whole run executes in one persistent kernel, launched where its first op stood
             if (&op == &e.plan.ops[size_t(e.plan.chains[size_t(op.chain)].first)]) n += launch_chain(e.chains[size_t(op.chain)], ctx->streams[op.lane]);
@@ -244,6 +246,7 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
             if (se != cudaSuccess) return ctx->fail(RVC_ERR_CUDA, "op '" + op.name + "' failed: " + cudaGetErrorString(se));
         }
     }
+    rvc::g_launch_priority = 0;
     CK(cudaGetLastError());
     *launches = n;
     return RVC_OK;
@@ -493,6 +496,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
         // lane 1 carries the F0 chain, the longest branch of the window: its kernels go first when SMs free up
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        { const char* fp = getenv("RVC_F0_PRIO"); ctx->f0_priority = (fp && fp[0] == '0') ? 0 : prio_hi; }
         const char* pe = getenv("RVC_LANE1_PRIO");
         const bool boost = !(pe && pe[0] == '0');
         if ((e = cudaStreamCreateWithPriority(&ctx->streams[i], cudaStreamNonBlocking, (i == 1 && boost) ? prio_hi : prio_lo)) != cudaSuccess) {

@@ -16,6 +16,7 @@
 
 #include "chain.h"
 #include "launch.h"
+#include "pdl.cuh"
 
 namespace rvc {
 
@@ -714,10 +715,12 @@ void chain_debug_read2(long long* out, int n) { cudaMemcpyFromSymbol(out, g_chai
 int launch_chain(const ChainDev& c, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = CHAIN_SMEM_BYTES; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident or none: the grid barrier cannot deadlock
     attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = g_launch_priority;
+    cfg.attrs = attr; cfg.numAttrs = g_launch_priority != 0 ? 2 : 1;
     const ChainOpDev* ops = c.d_ops; const ChainPhaseDev* phases = c.d_phases; int no = c.n_ops, n = c.n_phases; unsigned int* bar = c.d_bar;
     unsigned long long* dbg = c.d_dbg;
     cudaLaunchKernelEx(&cfg, chain_kernel, ops, phases, no, n, bar, dbg);

@@ -21,15 +21,21 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 
 extern bool g_use_pdl;  // RVC_PDL=0 disables (engine.cu)
+// Launch priority of the kernels issued next by this thread (0 = default).  engine.cu raises it for the ops of the
+// F0 lanes: the F0 chain is the longest branch of the window and must not queue behind ContentVec's wide grids.
+// Set as a launch attribute so that it survives stream capture (kernel-node attribute of the CUDA graph).
+extern thread_local int g_launch_priority;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = g_launch_priority;
+    cfg.attrs = attr; cfg.numAttrs = g_launch_priority != 0 ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 

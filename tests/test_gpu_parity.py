@@ -151,6 +151,34 @@ def test_graph_replay_equals_eager(env):
     np.testing.assert_array_equal(outs[0], outs[1])
 
 
+def test_persistent_chains_match_separate_kernels(env, monkeypatch):
+    """The persistent chain kernel (chain.h: enc_p, flow, RMVPE bottleneck in one cooperative launch each) and the
+    same ops as separate kernels give the same window: F0 argmax / coarse pitch identical, audio equal up to the
+    order of fp32 partial sums.  RVC_CHAIN=2 forces chains although the fixture's context shares the device."""
+    rb = env["rvc_b200"]
+    g = env["pipeline"].BASELINE_GEOM
+    x = env["pipeline"].synthetic_pcm(g["n16k"] + g["sf16k"], seed=11)
+    res = {}
+    for mode in ("2", "0"):
+        monkeypatch.setenv("RVC_CHAIN", mode)
+        e = rb.RvcInfer(env["paths"]["data"], noise_seed=5)
+        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+        outs = [e.infer(x[w * g["sf16k"]: w * g["sf16k"] + g["n16k"]], g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+                for w in range(2)]
+        chains = e.profile_chains()
+        res[mode] = dict(audio=outs, argmax=e.get_last("f0_argmax", np.int32).copy(), pitch=e.get_last("pitch", np.int32).copy(),
+                         n_chains=len(chains), phases=sum(len(c["phases"]) for c in chains), launches=e.plan_info().get("launches", 0))
+        e.close()
+    monkeypatch.delenv("RVC_CHAIN")
+    assert res["2"]["n_chains"] >= 3 and res["2"]["phases"] >= 100, res["2"]
+    assert res["0"]["n_chains"] == 0
+    np.testing.assert_array_equal(res["2"]["argmax"], res["0"]["argmax"])
+    np.testing.assert_array_equal(res["2"]["pitch"], res["0"]["pitch"])
+    for a, b in zip(res["2"]["audio"], res["0"]["audio"]):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+        assert _rms(a) > 0.01
+
+
 def test_noise_modes_and_pitch_shift_quirk(env):
     """noise_mode 0 = deterministic zeros; pitch shift is integer octaves (rvc.rs:121)."""
     rb = env["rvc_b200"]
