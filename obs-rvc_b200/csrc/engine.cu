@@ -50,6 +50,7 @@ struct ModelData {
     Packed packed;  // offsets kept; host copy dropped after upload
     DevBuf dev;
     int64_t hilo_stride = 0;  // bytes from the fp32 arena to its tf32 hi copy (and again to lo); 0 = none
+    int64_t hilo16_off = 0, hilo16_plane = 0;  // fp16 split planes (launch.h DeviceBases)
     CvInfo cvi; F0Info f0i; SynInfo syi;
     int rows = 0, cols = 0;   // retrieval index only
     ~ModelData() { dev.release(); }
@@ -164,6 +165,8 @@ struct rvc_ctx {
         B.b[SP_SYN] = syn.d ? syn.d->dev.d : nullptr; B.b[SP_IDX] = index.d ? index.d->dev.d : nullptr;
         B.b[SP_WORK] = e.work.d; B.b[SP_STATE] = state.d;
         B.hilo_stride[SP_CV] = cv.d ? cv.d->hilo_stride : 0; B.hilo_stride[SP_SYN] = syn.d ? syn.d->hilo_stride : 0;
+        B.hilo16_off[SP_CV] = cv.d ? cv.d->hilo16_off : 0; B.hilo16_off[SP_SYN] = syn.d ? syn.d->hilo16_off : 0;
+        B.hilo16_plane[SP_CV] = cv.d ? cv.d->hilo16_plane : 0; B.hilo16_plane[SP_SYN] = syn.d ? syn.d->hilo16_plane : 0;
         return B;
     }
 };
@@ -175,7 +178,8 @@ namespace {
 int upload(rvc_ctx* ctx, ModelData& m, bool with_hilo) {
     size_t bytes = (m.packed.host.size() * sizeof(float) + 1023) & ~size_t(1023);
     m.dev.release();
-    CK(cudaMalloc(&m.dev.d, bytes * (with_hilo ? 3 : 1) + 256));
+    // layout: fp32 arena | tf32 hi | tf32 lo | fp16 hi plane, fp16 scaled-lo plane (one more arena's worth)
+    CK(cudaMalloc(&m.dev.d, bytes * (with_hilo ? 4 : 1) + 256));
     m.dev.bytes = bytes;
     CK(cudaMemcpy(m.dev.d, m.packed.host.data(), m.packed.host.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (with_hilo) {
@@ -183,6 +187,10 @@ int upload(rvc_ctx* ctx, ModelData& m, bool with_hilo) {
         launch_split_hilo(reinterpret_cast<const float*>(m.dev.d), reinterpret_cast<float*>(m.dev.d + bytes),
                           reinterpret_cast<float*>(m.dev.d + 2 * bytes), m.packed.host.size(), ctx->streams[0]);
         m.hilo_stride = int64_t(bytes);
+        // 2-term fp16 split planes for the tcgen05 kind::f16 path
+        launch_split_hilo16(reinterpret_cast<const float*>(m.dev.d), reinterpret_cast<unsigned short*>(m.dev.d + 3 * bytes),
+                            reinterpret_cast<unsigned short*>(m.dev.d + 3 * bytes + bytes / 2), m.packed.host.size(), ctx->streams[0]);
+        m.hilo16_off = int64_t(3 * bytes); m.hilo16_plane = int64_t(bytes / 2);
     }
     CK(cudaDeviceSynchronize());
     std::vector<float>().swap(m.packed.host);
@@ -1099,7 +1107,7 @@ int rvc_debug_umma_timing(rvc_ctx* ctx, const char* op_name, long long* out16) {
         if (op.name == want) { int n = 0; issue_one(ctx, op, B, ctx->streams[0], &n); issue_one(ctx, op, B, ctx->streams[0], &n); break; }
     }
     CK(cudaStreamSynchronize(ctx->streams[0]));
-    if (std::string(op_name).find("@v2") != std::string::npos) rvc::v2_debug_read(out16); else rvc::umma_debug_read(out16);
+    if (std::string(op_name).find("@v2") != std::string::npos) rvc::v2_debug_read(out16); else { rvc::umma_debug_read(out16); rvc::umma_debug_read2(out16 + 16); }
     return RVC_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cooperative_groups.h>
 
 #include <cfloat>
+#include <cuda_fp16.h>
 
 #include "chain.h"
 #include "launch.h"
@@ -437,6 +438,15 @@ __global__ void split_hilo_kernel(const float* __restrict__ src, float* __restri
     }
 }
 
+__global__ void split_hilo16_kernel(const float* __restrict__ src, unsigned short* __restrict__ hi, unsigned short* __restrict__ lo, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        const __half h = __float2half_rn(v);
+        hi[i] = __half_as_ushort(h);
+        lo[i] = __half_as_ushort(__float2half_rn((v - __half2float(h)) * 2048.0f));
+    }
+}
+
 inline int grid_for(long long n, int block, int cap = 148 * 8) {
     long long g = (n + block - 1) / block;
     return int(g < 1 ? 1 : (g > cap ? cap : g));
@@ -456,6 +466,10 @@ void init_kernel_attributes() {
     init_gemm_v2_attributes();
     init_umma_attributes();
     init_chain_attributes();
+}
+
+void launch_split_hilo16(const float* src, unsigned short* dst_hi, unsigned short* dst_lo, size_t n, cudaStream_t stream) {
+    split_hilo16_kernel<<<148 * 8, 256, 0, stream>>>(src, dst_hi, dst_lo, n);
 }
 
 void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n, cudaStream_t stream) {

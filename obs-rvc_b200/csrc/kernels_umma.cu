@@ -20,6 +20,7 @@
 //              tile reduces in fixed order), bias / activation / residual / masks / scatter modes.
 #include <cooperative_groups.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -75,6 +76,11 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* smem_d
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// L2 prefetch of one box of a 3-D tensor map (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* smem_dst, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -117,19 +123,50 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 __device__ long long g_umma_dbg[16];
+__device__ long long g_umma_dbg2[5 * 16];   // [event][k-block < 16] of CTA (0,0,0): producer empty-ok / tma-issued, MMA full-ok / conv-ok / issued
+#define UMMA_DBG2(e, i) do { if ((i) < 16 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_umma_dbg2[(e) * 16 + (i)] = clock64(); } while (0)
 // 1 = store the truncated A_hi back (explicit); 0 = leave the fp32 tile as delivered by TMA and rely on the tensor
 // core ignoring the 13 low mantissa bits of a tf32 operand (saves a third of the converter's shared-memory writes)
+__device__ int g_dev_dbg_skip = 0;     // timing experiments only (RVC_UMMA_DBG_SKIP=1: no A loads, 2: no W loads, 3: no conversion): results are garbage
+__device__ int g_dev_w_prefetch = 0;   // RVC_UMMA_WPREFETCH=1: up-front L2 prefetch of the CTA's weight slice (measured: no gain)
 __device__ int g_dev_write_hi = 0;   // RVC_UMMA_WRITE_HI=1 restores the explicit store
 #define UMMA_DBG(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_umma_dbg[i] = clock64(); } while (0)
 
+// PASSES: 3 = 3xTF32 (A split in smem into tf32 hi / lo fp32 words), 1 = single tf32 pass (debug),
+//         16 = 2-term FP16 split (kernel header): same 11+11 mantissa bits per operand as 3xTF32, half the
+//              operand bytes in shared memory and in the weight stream.
 template <int BN, int PASSES>
 struct UmmaCfg {
-    static constexpr int W_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = (UM_A_BYTES + W_BYTES) * (PASSES == 3 ? 2 : 1);
+    static constexpr bool F16 = PASSES == 16;
+    static constexpr int W_BYTES = F16 ? BN * 64 : BN * 128;                 // one weight plane of a k-block
+    static constexpr int A16_BYTES = UM_BM * 64;                             // one fp16 plane of the A k-block
+    static constexpr int STAGE_BYTES = F16 ? (UM_A_BYTES + 2 * A16_BYTES + 2 * W_BYTES)
+                                           : (UM_A_BYTES + W_BYTES) * (PASSES == 3 ? 2 : 1);
     static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > 6 ? 6 : (196 * 1024 / STAGE_BYTES);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int ACC_COLS = F16 ? 2 * BN : BN;              // F16: main + correction accumulator
+    static constexpr int TMEM_COLS = ACC_COLS < 32 ? 32 : ACC_COLS;
 };
+
+// K-major SWIZZLE_64B descriptor (rows of 32 halves = 64 B, 8-row atoms of 512 B)
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
+    d |= uint64_t(1) << 16;
+    d |= uint64_t(512 >> 4) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(4) << 61;                       // layout type SWIZZLE_64B
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+constexpr float F16_LO_SCALE = 2048.0f;   // lo' = (x - float(half(x))) * 2^11 keeps the residual in fp16's normal range
 
 template <int BN, int PASSES>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -146,8 +183,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     auto stageA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
     auto stageAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES; };
-    auto stageW = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES * (PASSES == 3 ? 2 : 1); };
+    auto stageW = [&](int s) { return smem + s * Cfg::STAGE_BYTES + (Cfg::F16 ? UM_A_BYTES + 2 * Cfg::A16_BYTES : UM_A_BYTES * (PASSES == 3 ? 2 : 1)); };
     auto stageWlo = [&](int s) { return stageW(s) + Cfg::W_BYTES; };
+    auto stageAhi16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES; };                    // F16 mode only
+    auto stageAlo16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES + Cfg::A16_BYTES; };
 
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
     const int z = blockIdx.z % p.splitk, bz = blockIdx.z / p.splitk;
@@ -160,8 +199,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
-        if (PASSES == 3) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 2); mbar_init(&bar_empty[s], 1); }
+        if (PASSES != 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 8); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -177,19 +216,40 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (tid == 0) UMMA_DBG(1);
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES, ph = (i / STAGES) & 1;
+        // ===== TMA producer: lanes 0 / 1 / 2 each issue one of the three loads of a k-block (a bulk-tensor issue costs
+        // ~190 cycles of its thread: one thread issuing all three was 570 cycles per k-block - measured) =====
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES, ph = (i / STAGES) & 1;
+            if (lane == 0) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
-                mbar_expect_tx(&bar_full[s], UM_A_BYTES + Cfg::W_BYTES * (PASSES == 3 ? 2 : 1));
-                const int kk = (kb0 + i) * UM_BK;
-                const int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
-                tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);
-                tma_load_3d(&tmW, stageW(s), &bar_full[s], kk, n0, bz);
-                if (PASSES == 3) tma_load_3d(&tmWlo, stageWlo(s), &bar_full[s], kk, n0, bz);
+                UMMA_DBG2(0, i);
+                mbar_expect_tx(&bar_full[s], (g_dev_dbg_skip == 1 ? 0 : UM_A_BYTES) + (g_dev_dbg_skip == 2 ? 0 : Cfg::W_BYTES * (PASSES != 1 ? 2 : 1)));
             }
-            UMMA_DBG(2);
+            __syncwarp();
+            const int kk = (kb0 + i) * UM_BK;
+            if (lane == 0) {
+                const int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
+                if (g_dev_dbg_skip != 1) tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);
+                UMMA_DBG2(1, i);
+            } else if (g_dev_dbg_skip == 2) {
+            } else if (lane == 1) {
+                tma_load_3d(&tmW, stageW(s), &bar_full[s], kk, n0, bz);
+            } else if (lane == 2 && PASSES != 1) {
+                tma_load_3d(&tmWlo, stageWlo(s), &bar_full[s], kk, n0, bz);
+            }
+        }
+        if (lane == 0) UMMA_DBG(2);
+    } else if (warp == UM_WARPS - 1) {
+        // ===== weight prefetch (a store warp that is idle during the k loop): the weight slice of this CTA is cold in L2
+        // every window (850 MB of weights stream through a 126 MB L2) and does not depend on the previous kernel, so it
+        // is requested now, one k-block per lane: the stage round trip (TMA -> convert -> MMA -> release) that bounds
+        // the k loop then pays an L2 hit instead of an HBM miss =====
+        if (g_dev_w_prefetch) {
+            for (int i = STAGES + lane; i < nkb; i += 32) {
+                const int kk = (kb0 + i) * UM_BK;
+                tma_prefetch_3d(&tmW, kk, n0, bz);
+                if (PASSES != 1) tma_prefetch_3d(&tmWlo, kk, n0, bz);
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -199,9 +259,28 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
                 mbar_wait(&bar_full[s], ph);
                 if (i == 0) UMMA_DBG(3);
-                if (PASSES == 3) mbar_wait(&bar_conv[s], ph);
+                UMMA_DBG2(2, i);
+                if (PASSES != 1) mbar_wait(&bar_conv[s], ph);
                 if (i == 0) UMMA_DBG(4);
+                UMMA_DBG2(3, i);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if constexpr (Cfg::F16) {
+                    // D0 += Ahi.Whi ; D1 += Alo'.Whi + Ahi.Wlo'   (K = 16 halves = 32 B per instruction)
+                    const uint32_t idesc16 = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t(UM_BM >> 4) << 24);
+                    const uint32_t a_hi = smem_u32(stageAhi16(s)), a_lo = smem_u32(stageAlo16(s));
+                    const uint32_t w_hi = smem_u32(stageW(s)), w_lo = smem_u32(stageWlo(s));
+#pragma unroll
+                    for (int ks = 0; ks < UM_BK / 16; ++ks) {
+                        const uint32_t off = ks * 32;
+                        const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+                        umma_f16(tmem_base, umma_desc64(a_hi + off), umma_desc64(w_hi + off), idesc16, first);
+                        umma_f16(tmem_base + BN, umma_desc64(a_lo + off), umma_desc64(w_hi + off), idesc16, first);
+                        umma_f16(tmem_base + BN, umma_desc64(a_hi + off), umma_desc64(w_lo + off), idesc16, 1u);
+                    }
+                    umma_commit(&bar_empty[s]);
+                    UMMA_DBG2(4, i);
+                    continue;
+                }
                 const uint32_t a_hi = smem_u32(stageA(s)), a_lo = smem_u32(stageAlo(s));
                 const uint32_t w_hi = smem_u32(stageW(s)), w_lo = smem_u32(stageWlo(s));
 #pragma unroll
@@ -221,24 +300,60 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp < 10) {
         // ===== converter warps 2-9 (two per stage); warps 2-5 then drain TMEM =====
         const int ct = tid - 64;
-        if (PASSES == 3) {
+        if constexpr (Cfg::F16) {
+            // fp32 tile (TMA, SWIZZLE_128B) -> two fp16 planes (SWIZZLE_64B): hi = half(x), lo' = half((x - hi) * 2^11).
+            // One task = one 16-byte chunk of the planes (8 consecutive k of one row) = two float4 of the tile.
+            // All 8 converter warps work on the SAME (oldest) stage: the k loop is bound by the round trip of a stage
+            // (TMA -> convert -> MMA -> release), not by converter throughput, so the conversion must be short.
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&bar_full[s], ph);
+                const uint8_t* a32 = stageA(s);
+                uint8_t* h16 = stageAhi16(s);
+                uint8_t* l16 = stageAlo16(s);
+#pragma unroll
+                for (int t0 = 0; t0 < 2; ++t0) {
+                    if (g_dev_dbg_skip == 3) break;
+                    const int t = t0 * 256 + ct;                   // 512 tasks per stage, 256 threads
+                    const int r = t >> 2, q = t & 3;
+                    const float4 v0 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * q) ^ (r & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
+                    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // packed conversions (one F2FP per pair): the scalar F2F path is quarter-rate and was the k loop's limiter
+                        const __half2 h2 = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn((x[2 * e] - hf.x) * F16_LO_SCALE, (x[2 * e + 1] - hf.y) * F16_LO_SCALE);
+                        hw[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                        lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    const int dst = r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+                    *reinterpret_cast<uint4*>(h16 + dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(l16 + dst) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_conv[s]);
+            }
+        } else if (PASSES == 3) {
             // hi/lo split of the A tile; up to four stages are converted concurrently
             // Ownership is by STAGE (stage s belongs to warp pair s & 3), never by k-block: a parity wait
             // may only ever be one phase ahead of its mbarrier, so every waiter must visit every phase.
-            const int cw = (warp - 2) & 3, half = (warp - 2) >> 2;  // stage owner, 8 KB half of the tile
+            const int cwarp = warp - 2;   // 0..7: every warp converts an eighth (2 KB) of EVERY stage (see the F16 branch)
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
-                if ((s & 3) != cw) continue;
                 mbar_wait(&bar_full[s], ph);
-                float4* a = reinterpret_cast<float4*>(stageA(s)) + half * (UM_A_BYTES / 32);
-                float4* lo = reinterpret_cast<float4*>(stageAlo(s)) + half * (UM_A_BYTES / 32);
-#pragma unroll 1
-                for (int b = 0; b < UM_A_BYTES / 32 / 32; b += 8) {
-                    float4 v[8];
+                float4* a = reinterpret_cast<float4*>(stageA(s)) + cwarp * (UM_A_BYTES / 128);
+                float4* lo = reinterpret_cast<float4*>(stageAlo(s)) + cwarp * (UM_A_BYTES / 128);
+                {
+                    constexpr int b = 0;
+                    float4 v[4];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = a[(b + j) * 32 + lane];
+                    for (int j = 0; j < 4; ++j) v[j] = a[(b + j) * 32 + lane];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 4; ++j) {
                         float4 h;
                         h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
                         h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
@@ -265,8 +380,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* ct_row = reinterpret_cast<float*>(smem) + row * CT_LD;
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];
-            if (nkb > 0) tmem_ld16(trow + c0, v);
-            else {
+            if (nkb > 0) {
+                tmem_ld16(trow + c0, v);
+                if constexpr (Cfg::F16) {
+                    float c[16];
+                    tmem_ld16(trow + BN + c0, c);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaf(c[j], 1.0f / F16_LO_SCALE, v[j]);
+                }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
@@ -378,19 +500,22 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool encode(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+            bool f16 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<float*>(base), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // fp32 tiles: rows of 32 floats = 128 B (SWIZZLE_128B); fp16 weight planes: rows of 32 halves = 64 B (SWIZZLE_64B)
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, cuuint32_t(rank), const_cast<void*>(base), dims,
+                    strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 template <int BN, int PASSES>
-bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const float* w_hi, const float* w_lo, cudaStream_t s) {
+bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const void* w_hi, const void* w_lo, cudaStream_t s) {
     using Cfg = UmmaCfg<BN, PASSES>;
+    constexpr int WB = Cfg::F16 ? 2 : 4;   // bytes per weight element of the planes
     CUtensorMap tmA, tmW, tmWlo;
     const int nseg = (g.seg_len >= g.K) ? 1 : g.K / g.seg_len;
     const int seg_len = nseg == 1 ? g.K : g.seg_len;
@@ -403,10 +528,10 @@ bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const float* w_hi, const fl
     }
     {
         cuuint64_t dims[3] = {cuuint64_t(g.K), cuuint64_t(g.N), cuuint64_t(g.batch)};
-        cuuint64_t str[2] = {cuuint64_t(g.ldw) * 4, g.batch > 1 ? cuuint64_t(g.sW) * 4 : big};
+        cuuint64_t str[2] = {cuuint64_t(g.ldw) * WB, g.batch > 1 ? cuuint64_t(g.sW) * WB : big};
         cuuint32_t box[3] = {UM_BK, cuuint32_t(BN), 1};
-        if (!encode(&tmW, w_hi, 3, dims, str, box)) return false;
-        if (!encode(&tmWlo, w_lo, 3, dims, str, box)) return false;
+        if (!encode(&tmW, w_hi, 3, dims, str, box, Cfg::F16)) return false;
+        if (!encode(&tmWlo, w_lo, 3, dims, str, box, Cfg::F16)) return false;
     }
     const int nkb = (g.K + UM_BK - 1) / UM_BK;
     p.kt_per_split = (nkb + g.splitk - 1) / g.splitk;
@@ -432,6 +557,7 @@ bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const float* w_hi, const fl
 }
 
 int g_umma_passes = 3;
+bool g_umma_f16 = true;   // 2-term FP16 split (RVC_UMMA_F16=0: 3xTF32)
 
 }  // namespace
 
@@ -442,12 +568,19 @@ void init_umma_attributes() {
     cudaFuncSetAttribute(umma_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 1>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 1>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 1>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 16>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 16>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 16>::SMEM_BYTES);
+    { const char* f = getenv("RVC_UMMA_F16"); g_umma_f16 = !(f && f[0] == '0'); }
+    { const char* w = getenv("RVC_UMMA_DBG_SKIP"); int v = w ? atoi(w) : 0; cudaMemcpyToSymbol(g_dev_dbg_skip, &v, sizeof(int)); }
+    { const char* w = getenv("RVC_UMMA_WPREFETCH"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_dev_w_prefetch, &v, sizeof(int)); }
     { const char* w = getenv("RVC_UMMA_WRITE_HI"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_dev_write_hi, &v, sizeof(int)); }
     const char* e = getenv("RVC_UMMA_PASSES");
     if (e && e[0] == '1') g_umma_passes = 1;
 }
 
 void umma_debug_read(long long* out) { cudaMemcpyFromSymbol(out, g_umma_dbg, sizeof(long long) * 16); }
+void umma_debug_read2(long long* out) { cudaMemcpyFromSymbol(out, g_umma_dbg2, sizeof(long long) * 80); }
 
 // returns 0 when the tensor maps could not be encoded (caller falls back to the CUDA-core kernel)
 int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
@@ -458,6 +591,16 @@ int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream)
     const float* w_lo = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + 2 * hl);
     const int bn = g.sched_variant == 5 ? 128 : (g.sched_variant == 6 ? 64 : 32);
     bool ok;
+    const int64_t h16 = B.hilo16_off[g.W.space];
+    const int64_t woff = reinterpret_cast<const uint8_t*>(p.W) - B.b[g.W.space];   // byte offset of W inside its fp32 arena
+    // fp16 planes: TMA needs 16-byte aligned bases and row pitches -> element offsets / strides that are multiples of 8
+    if (g_umma_f16 && g_umma_passes == 3 && h16 > 0 && woff % 32 == 0 && g.ldw % 8 == 0 && g.sW % 8 == 0) {
+        const uint8_t* hi16 = B.b[g.W.space] + h16 + woff / 2;
+        const uint8_t* lo16 = hi16 + B.hilo16_plane[g.W.space];
+        ok = bn == 128 ? launch_umma_cfg<128, 16>(g, p, hi16, lo16, stream)
+           : bn == 64 ? launch_umma_cfg<64, 16>(g, p, hi16, lo16, stream) : launch_umma_cfg<32, 16>(g, p, hi16, lo16, stream);
+        return ok ? 1 : 0;
+    }
     if (g_umma_passes == 3) {
         ok = bn == 128 ? launch_umma_cfg<128, 3>(g, p, w_hi, w_lo, stream)
            : bn == 64 ? launch_umma_cfg<64, 3>(g, p, w_hi, w_lo, stream) : launch_umma_cfg<32, 3>(g, p, w_hi, w_lo, stream);

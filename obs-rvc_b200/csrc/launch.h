@@ -12,6 +12,9 @@ struct DeviceBases {
     uint8_t* b[SP_COUNT] = {nullptr};
     // byte distance from the fp32 weights of a space to their tf32 "hi" copy (and again to "lo"); 0 = none
     int64_t hilo_stride[SP_COUNT] = {0};
+    // fp16 split planes of a weight space: byte offset of the hi plane from the fp32 arena, byte size of one plane
+    // (element i of the arena sits at hi16_off + 2 i, its scaled residual one plane further); 0 = none
+    int64_t hilo16_off[SP_COUNT] = {0}, hilo16_plane[SP_COUNT] = {0};
     template <typename T> T* p(const Ref& r) const {
         return r.null() ? nullptr : reinterpret_cast<T*>(b[r.space] + r.off);
     }
@@ -52,10 +55,13 @@ void init_kernel_attributes();
 void init_gemm_v2_attributes();
 void init_umma_attributes();
 void umma_debug_read(long long* out);
+void umma_debug_read2(long long* out);  // [5 events][16 k-blocks] of the last tcgen05 GEMM CTA (0,0,0)
 void v2_debug_read(long long* out);  // phase timestamps of the last tcgen05 GEMM CTA (0,0,0)
 // tcgen05 path; returns 0 if the TMA descriptors cannot be built (caller falls back)
 int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);
 // dst_hi[i] = src[i] with the 13 low mantissa bits cleared, dst_lo[i] = src[i] - dst_hi[i]
 void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n, cudaStream_t stream);
+// dst_hi[i] = half(src[i]), dst_lo[i] = half((src[i] - float(dst_hi[i])) * 2048)  (raw 16-bit storage)
+void launch_split_hilo16(const float* src, unsigned short* dst_hi, unsigned short* dst_lo, size_t n, cudaStream_t stream);
 
 }  // namespace rvc
