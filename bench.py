@@ -298,7 +298,7 @@ def main():
             if o["kind"] != "gemm":
                 return o["kind"]
             v = o.get("variant", 0)
-            return "umma_gemm_kernel(tcgen05 3xTF32)" if v >= 5 else ("gemm_v2_kernel(fp32 split-K)" if v >= 1 else "gemm_f32_kernel")
+            return "umma_gemm_kernel(tcgen05 2xFP16 split)" if v >= 5 else ("gemm_v2_kernel(fp32 split-K)" if v >= 1 else "gemm_f32_kernel")
 
         fam = {}
         for o in prof:
@@ -326,9 +326,10 @@ def main():
 
         order = sorted(fam.items(), key=lambda kv: -kv[1]["us"])
         roof = roof_of(*order[0])
-        # dram__bytes_read+write of one launch of this kernel under `ncu --set full` (profiles/r01_d_prof_umma.md: grid
-        # (4,2,8) = a HiFiGAN stage-0 ResBlock conv, M=210 N=256; its W_hi + W_lo planes are 3.7-5.8 MB, + A): ~algorithmic
-        roof["traffic"] = 6.26e6 if order[0][0].startswith("umma") else None
+        # dram__bytes_read+write of one launch of this kernel under `ncu --set full` (profiles/r01_e_prof_umma.md: grid
+        # (4,2,8) = a HiFiGAN stage-0 ResBlock conv, M=210 N=256 K=1792: fp16 hi + scaled-lo weight planes = 4 N K = 1.8 MB
+        # ... 2.9 MB for K=2816, + the fp32 A rows) - at the algorithmic figure, half of the 3xTF32 planes (6.26 MB, r01_d)
+        roof["traffic"] = 3.38e6 if order[0][0].startswith("umma") else None
         roof["note"] = ("achieved = sum of algorithmic bytes (weights + activations) or flops (2MNK) of this kernel's launches in one "
                         "window / sum of their device times; each op timed as a 10-launch CUDA graph between events on the "
                         "engine stream (rvc_profile_ops); ncu captures: profiles/")

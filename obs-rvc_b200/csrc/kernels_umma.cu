@@ -215,10 +215,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     pdl_wait();  // barrier init, TMEM allocation and descriptor prefetch overlapped the previous kernel
     if (tid == 0) UMMA_DBG(1);
 
-    if (warp == 0) {
-        // ===== TMA producer: lanes 0 / 1 / 2 each issue one of the three loads of a k-block (a bulk-tensor issue costs
-        // ~190 cycles of its thread: one thread issuing all three was 570 cycles per k-block - measured) =====
-        for (int i = 0; i < nkb; ++i) {
+    if (warp == 0 || warp == UM_WARPS - 1) {
+        // ===== TMA producers: two warps (warp 0 and an otherwise idle store warp) alternate k-blocks; in each, lanes
+        // 0 / 1 / 2 issue one of the three loads.  One producer iteration (barrier wait + expect_tx + issue) costs its
+        // thread ~1250 cycles whatever it loads (measured), which paced the whole k loop =====
+        const int pid = warp == 0 ? 0 : 1;
+        for (int i = pid; i < nkb; i += 2) {
             const int s = i % STAGES, ph = (i / STAGES) & 1;
             if (lane == 0) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
@@ -238,8 +240,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_3d(&tmWlo, stageWlo(s), &bar_full[s], kk, n0, bz);
             }
         }
-        if (lane == 0) UMMA_DBG(2);
-    } else if (warp == UM_WARPS - 1) {
+        if (lane == 0 && pid == 0) UMMA_DBG(2);
+    } else if (false) {
         // ===== weight prefetch (a store warp that is idle during the k loop): the weight slice of this CTA is cold in L2
         // every window (850 MB of weights stream through a 126 MB L2) and does not depend on the previous kernel, so it
         // is requested now, one k-block per lane: the stage round trip (TMA -> convert -> MMA -> release) that bounds
