@@ -16,7 +16,7 @@ namespace rvc {
 
 struct GemmSched {
     int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM32/BN32 (v2);
-                      // 5/6/7: tcgen05 3xTF32 kernel (kernels_umma.cu) with BN = 128/64/32
+                      // 5/6/7/8: tcgen05 kernel (kernels_umma.cu) with BN = 128/64/32/256
     int bm = 0, bn = 0, splitk = 1, tiles = 0;
 };
 
@@ -30,7 +30,7 @@ inline int sched_env(const char* name, int dflt) {
 
 inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     GemmSched s;
-    static const int kWant = sched_env("RVC_UMMA_WANT", 112), kBn128 = sched_env("RVC_UMMA_BN128_MIN", 56),
+    static const int kWant = sched_env("RVC_UMMA_WANT", 112), kBn128 = sched_env("RVC_UMMA_BN128_MIN", 1),
                      kKbMin = sched_env("RVC_UMMA_KB_MIN", 4);
     const bool aligned = g.A.off % 16 == 0 && g.W.off % 16 == 0 && g.lda % 4 == 0 && g.seg_len % 4 == 0 &&
                          g.seg_stride % 4 == 0 && g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
@@ -49,7 +49,13 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
         int bn = 128;
         if (g.N <= 32) bn = 32;
         else if (g.N <= 64 || tiles128 < bn128_min) bn = 64;
-        s.variant = bn == 128 ? 5 : (bn == 64 ? 6 : 7);
+        // 256-wide tiles (FP16-split kernel only): one tcgen05.mma costs ~175 cycles of latency on the accumulator chain
+        // whatever its N <= 256, so for wide outputs a quarter of the instructions per unit of work - taken when the
+        // tile grid x the deepest split-K still gives ~half a wave of CTAs
+        static const bool kF16 = sched_env("RVC_UMMA_F16", 1) != 0, k256 = sched_env("RVC_UMMA_BN256", 0) != 0;   // measured: no gain over 128-wide tiles (2.93 vs 2.90 ms/window), off
+        const int tiles256 = tm * ((g.N + 255) / 256) * g.batch;
+        if (kF16 && k256 && g.N >= 512 && tiles256 * std::min(8, std::max(1, nkb / kKbMin)) >= 48) bn = 256;
+        s.variant = bn == 256 ? 8 : (bn == 128 ? 5 : (bn == 64 ? 6 : 7));
         s.bm = 128; s.bn = bn;
         s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
         const int want = std::max(1, (g.cta_budget > 0 ? g.cta_budget : kWant) / s.tiles);

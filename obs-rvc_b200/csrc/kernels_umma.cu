@@ -124,7 +124,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 __device__ long long g_umma_dbg[16];
 __device__ long long g_umma_dbg2[5 * 16];   // [event][k-block < 16] of CTA (0,0,0): producer empty-ok / tma-issued, MMA full-ok / conv-ok / issued
+#ifdef RVC_UMMA_STAMPS   // per-k-block stamps cost ~100 cycles per iteration of the stamped thread: build with -DRVC_UMMA_STAMPS to use them
 #define UMMA_DBG2(e, i) do { if ((i) < 16 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_umma_dbg2[(e) * 16 + (i)] = clock64(); } while (0)
+#else
+#define UMMA_DBG2(e, i) do { } while (0)
+#endif
 // 1 = store the truncated A_hi back (explicit); 0 = leave the fp32 tile as delivered by TMA and rely on the tensor
 // core ignoring the 13 low mantissa bits of a tf32 operand (saves a third of the converter's shared-memory writes)
 __device__ int g_dev_dbg_skip = 0;     // timing experiments only (RVC_UMMA_DBG_SKIP=1: no A loads, 2: no W loads, 3: no conversion): results are garbage
@@ -140,9 +144,11 @@ struct UmmaCfg {
     static constexpr bool F16 = PASSES == 16;
     static constexpr int W_BYTES = F16 ? BN * 64 : BN * 128;                 // one weight plane of a k-block
     static constexpr int A16_BYTES = UM_BM * 64;                             // one fp16 plane of the A k-block
-    static constexpr int STAGE_BYTES = F16 ? (UM_A_BYTES + 2 * A16_BYTES + 2 * W_BYTES)
+    // F16: A never lands in shared memory as fp32 - the converter warps read it from L2 into registers (below)
+    static constexpr int STAGE_BYTES = F16 ? (2 * A16_BYTES + 2 * W_BYTES)
                                            : (UM_A_BYTES + W_BYTES) * (PASSES == 3 ? 2 : 1);
-    static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > 6 ? 6 : (196 * 1024 / STAGE_BYTES);
+    static constexpr int MAX_STAGES = F16 ? 8 : 6;
+    static constexpr int STAGES = (196 * 1024 / STAGE_BYTES) > MAX_STAGES ? MAX_STAGES : (196 * 1024 / STAGE_BYTES);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
     static constexpr int ACC_COLS = F16 ? 2 * BN : BN;              // F16: main + correction accumulator
     static constexpr int TMEM_COLS = ACC_COLS < 32 ? 32 : ACC_COLS;
@@ -183,10 +189,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     auto stageA = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
     auto stageAlo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES; };
-    auto stageW = [&](int s) { return smem + s * Cfg::STAGE_BYTES + (Cfg::F16 ? UM_A_BYTES + 2 * Cfg::A16_BYTES : UM_A_BYTES * (PASSES == 3 ? 2 : 1)); };
+    auto stageW = [&](int s) { return smem + s * Cfg::STAGE_BYTES + (Cfg::F16 ? 2 * Cfg::A16_BYTES : UM_A_BYTES * (PASSES == 3 ? 2 : 1)); };
     auto stageWlo = [&](int s) { return stageW(s) + Cfg::W_BYTES; };
-    auto stageAhi16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES; };                    // F16 mode only
-    auto stageAlo16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES + UM_A_BYTES + Cfg::A16_BYTES; };
+    auto stageAhi16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };                                 // F16 mode only
+    auto stageAlo16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A16_BYTES; };
 
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
     const int z = blockIdx.z % p.splitk, bz = blockIdx.z / p.splitk;
@@ -225,13 +231,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (lane == 0) {
                 mbar_wait(&bar_empty[s], ph ^ 1);
                 UMMA_DBG2(0, i);
-                mbar_expect_tx(&bar_full[s], (g_dev_dbg_skip == 1 ? 0 : UM_A_BYTES) + (g_dev_dbg_skip == 2 ? 0 : Cfg::W_BYTES * (PASSES != 1 ? 2 : 1)));
+                mbar_expect_tx(&bar_full[s], ((Cfg::F16 || g_dev_dbg_skip == 1) ? 0 : UM_A_BYTES) + (g_dev_dbg_skip == 2 ? 0 : Cfg::W_BYTES * (PASSES != 1 ? 2 : 1)));
             }
             __syncwarp();
             const int kk = (kb0 + i) * UM_BK;
             if (lane == 0) {
                 const int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
-                if (g_dev_dbg_skip != 1) tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);
+                if (!Cfg::F16 && g_dev_dbg_skip != 1) tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);
                 UMMA_DBG2(1, i);
             } else if (g_dev_dbg_skip == 2) {
             } else if (lane == 1) {
@@ -303,41 +309,77 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===== converter warps 2-9 (two per stage); warps 2-5 then drain TMEM =====
         const int ct = tid - 64;
         if constexpr (Cfg::F16) {
-            // fp32 tile (TMA, SWIZZLE_128B) -> two fp16 planes (SWIZZLE_64B): hi = half(x), lo' = half((x - hi) * 2^11).
-            // One task = one 16-byte chunk of the planes (8 consecutive k of one row) = two float4 of the tile.
-            // All 8 converter warps work on the SAME (oldest) stage: the k loop is bound by the round trip of a stage
-            // (TMA -> convert -> MMA -> release), not by converter throughput, so the conversion must be short.
-            for (int i = 0; i < nkb; ++i) {
+            // fp32 A rows (L2) -> registers -> two fp16 planes in shared memory (SWIZZLE_64B): hi = half(x),
+            // lo' = half((x - hi) * 2^11).  A is NOT staged through shared memory as fp32: the eight converter warps read
+            // it straight from L2, one k-block ahead (the loads of k-block i+1 are in flight while i is converted), so a
+            // stage holds operands only (16 KB + BN * 128 B -> 8 stages at BN = 64) and the TMA engine moves weights only.
+            // One task = one 16-byte chunk of the planes = 8 consecutive k of one row; 512 tasks per k-block, 2 per thread.
+            // All 8 warps work on the SAME (oldest) stage: the k loop is bound by the round trip of a stage, not by
+            // converter throughput, so the conversion must be short.
+            const float* __restrict__ Ab = p.A + bz * p.sA;
+            const float* rowp[2]; int within[2]; int dsto[2];
+            const int seg_len = p.seg_len;                      // == K when the rows are contiguous (launch_umma_cfg)
+            const long long seg_wrap = p.seg_stride - p.seg_len;
+#pragma unroll
+            for (int t0 = 0; t0 < 2; ++t0) {
+                const int t = t0 * 256 + ct, r = t >> 2, q = t & 3;
+                const int m = m0 + r;
+                const int kk = kb0 * UM_BK + q * 8;
+                const int seg = kk / seg_len;
+                within[t0] = kk - seg * seg_len;
+                rowp[t0] = (m < p.M) ? Ab + (long long)m * p.lda + (long long)seg * p.seg_stride + within[t0] : nullptr;
+                dsto[t0] = r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+            }
+            constexpr int PF = 3;                         // k-blocks of A in flight per thread (L2 latency >> conversion time)
+            float4 buf[PF][2][2];
+            auto fetch = [&](float4 (*dst)[2], int i) {   // loads of k-block i (relative), then advance the cursors
+#pragma unroll
+                for (int t0 = 0; t0 < 2; ++t0) {
+                    const bool ok = rowp[t0] && i < nkb && ((kb0 + i) * UM_BK + (ct & 3) * 8) < p.K;
+                    dst[t0][0] = ok ? __ldcg(reinterpret_cast<const float4*>(rowp[t0])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dst[t0][1] = ok ? __ldcg(reinterpret_cast<const float4*>(rowp[t0]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rowp[t0]) {
+                        rowp[t0] += UM_BK; within[t0] += UM_BK;
+                        if (within[t0] >= seg_len) { within[t0] -= seg_len; rowp[t0] += seg_wrap; }
+                    }
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < PF - 1; ++j) fetch(buf[j], j);
+#pragma unroll 1
+            for (int i0 = 0; i0 < nkb; i0 += PF) {
+#pragma unroll
+            for (int jj = 0; jj < PF; ++jj) {
+                const int i = i0 + jj;
+                if (i >= nkb) break;
+                float4 (*cur)[2] = buf[jj];
                 const int s = i % STAGES, ph = (i / STAGES) & 1;
-                mbar_wait(&bar_full[s], ph);
-                const uint8_t* a32 = stageA(s);
+                fetch(buf[(jj + PF - 1) % PF], i + PF - 1);
+                mbar_wait(&bar_empty[s], ph ^ 1);   // the MMAs that read this stage's planes have completed
                 uint8_t* h16 = stageAhi16(s);
                 uint8_t* l16 = stageAlo16(s);
 #pragma unroll
                 for (int t0 = 0; t0 < 2; ++t0) {
                     if (g_dev_dbg_skip == 3) break;
-                    const int t = t0 * 256 + ct;                   // 512 tasks per stage, 256 threads
-                    const int r = t >> 2, q = t & 3;
-                    const float4 v0 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * q) ^ (r & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4*>(a32 + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
+                    const float4 v0 = cur[t0][0], v1 = cur[t0][1];
                     const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                     uint32_t hw[4], lw[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        // packed conversions (one F2FP per pair): the scalar F2F path is quarter-rate and was the k loop's limiter
+                        // packed conversions (one F2FP per pair)
                         const __half2 h2 = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
                         const float2 hf = __half22float2(h2);
                         const __half2 l2 = __floats2half2_rn((x[2 * e] - hf.x) * F16_LO_SCALE, (x[2 * e + 1] - hf.y) * F16_LO_SCALE);
                         hw[e] = *reinterpret_cast<const uint32_t*>(&h2);
                         lw[e] = *reinterpret_cast<const uint32_t*>(&l2);
                     }
-                    const int dst = r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
-                    *reinterpret_cast<uint4*>(h16 + dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                    *reinterpret_cast<uint4*>(l16 + dst) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    *reinterpret_cast<uint4*>(h16 + dsto[t0]) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(l16 + dsto[t0]) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_conv[s]);
+            }
             }
         } else if (PASSES == 3) {
             // hi/lo split of the A tile; up to four stages are converted concurrently
@@ -420,8 +462,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             peers[zz] = (p.splitk > 1 && zz < p.splitk) ? cg::this_cluster().map_shared_rank(Ct, zz) : Ct;
         if (p.vec_store) {
             // fast path (plain row-major output, no gate): float4 per lane, BN/4 lanes per row
-            constexpr int LPR = BN / 4, RPI = 32 / LPR;
-            const int sub = lane / LPR, c4 = (lane % LPR) * 4, n = n0 + c4;
+            constexpr int LPR = BN >= 128 ? 32 : BN / 4, RPI = 32 / LPR, NCH = (BN / 4) / LPR;   // BN = 256: two 128-column chunks per row
+            const int sub = lane / LPR;
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ++ch) {
+            const int c4 = (ch * LPR + lane % LPR) * 4, n = n0 + c4;
             const bool ncol = n < p.N;  // N % 4 == 0 on this path
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias && ncol) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
@@ -452,6 +497,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     w.z = masked ? 0.f : apply_act(p.act2, v.z); w.w = masked ? 0.f : apply_act(p.act2, v.w);
                     *reinterpret_cast<float4*>(C2 + (long long)m * p.ldc2 + n) = w;
                 }
+            }
             }
         } else {
             for (int row = r_begin + warp; row < r_end; row += UM_WARPS) {
@@ -570,6 +616,7 @@ void init_umma_attributes() {
     cudaFuncSetAttribute(umma_gemm_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 1>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 1>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 1>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<256, 16>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 16>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 16>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 16>::SMEM_BYTES);
@@ -591,7 +638,7 @@ int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream)
     GemmParams p = gemmk::make_params(g, B);
     const float* w_hi = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + hl);
     const float* w_lo = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + 2 * hl);
-    const int bn = g.sched_variant == 5 ? 128 : (g.sched_variant == 6 ? 64 : 32);
+    const int bn = g.sched_variant == 8 ? 256 : (g.sched_variant == 5 ? 128 : (g.sched_variant == 6 ? 64 : 32));
     bool ok;
     const int64_t h16 = B.hilo16_off[g.W.space];
     const int64_t woff = reinterpret_cast<const uint8_t*>(p.W) - B.b[g.W.space];   // byte offset of W inside its fp32 arena
@@ -599,10 +646,12 @@ int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream)
     if (g_umma_f16 && g_umma_passes == 3 && h16 > 0 && woff % 32 == 0 && g.ldw % 8 == 0 && g.sW % 8 == 0) {
         const uint8_t* hi16 = B.b[g.W.space] + h16 + woff / 2;
         const uint8_t* lo16 = hi16 + B.hilo16_plane[g.W.space];
-        ok = bn == 128 ? launch_umma_cfg<128, 16>(g, p, hi16, lo16, stream)
+        ok = bn == 256 ? launch_umma_cfg<256, 16>(g, p, hi16, lo16, stream)
+           : bn == 128 ? launch_umma_cfg<128, 16>(g, p, hi16, lo16, stream)
            : bn == 64 ? launch_umma_cfg<64, 16>(g, p, hi16, lo16, stream) : launch_umma_cfg<32, 16>(g, p, hi16, lo16, stream);
         return ok ? 1 : 0;
     }
+    if (bn == 256) return 0;   // only the FP16-split kernel has a 256-wide instance: the caller falls back to CUDA cores
     if (g_umma_passes == 3) {
         ok = bn == 128 ? launch_umma_cfg<128, 3>(g, p, w_hi, w_lo, stream)
            : bn == 64 ? launch_umma_cfg<64, 3>(g, p, w_hi, w_lo, stream) : launch_umma_cfg<32, 3>(g, p, w_hi, w_lo, stream);
