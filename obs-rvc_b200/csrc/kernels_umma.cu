@@ -122,6 +122,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// two 16-column TMEM loads (main + correction accumulator) behind ONE wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float* v, float* c) {
+    uint32_t r[16], q[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr0));
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]),
+          "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(taddr1));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r[i]); c[i] = __uint_as_float(q[i]); }
+}
+
 __device__ long long g_umma_dbg[16];
 __device__ long long g_umma_dbg2[5 * 16];   // [event][k-block < 16] of CTA (0,0,0): producer empty-ok / tma-issued, MMA full-ok / conv-ok / issued
 #ifdef RVC_UMMA_STAMPS   // per-k-block stamps cost ~100 cycles per iteration of the stamped thread: build with -DRVC_UMMA_STAMPS to use them
@@ -421,23 +439,37 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int row = q * 32 + lane;
         const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
-        float* ct_row = reinterpret_cast<float*>(smem) + row * CT_LD;
+        // split-K partial tiles are exchanged through L2 (per-lane scratch, ld/st.cg): pulling them out of the peers'
+        // shared memory over DSMEM ran at ~8 B/clk per SM and cost two cluster barriers (measured 12-15 k cycles per GEMM)
+        const bool via_l2 = p.splitk > 1 && p.scratch != nullptr;
+        const long long tile_lin = ((long long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        float* ct_row = via_l2 ? p.scratch + ((tile_lin * p.splitk + z) * UM_BM + row) * BN
+                               : reinterpret_cast<float*>(smem) + row * CT_LD;
+        const bool row_live = !via_l2 || (m0 + row) < p.M;   // rows past M are never read back
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];
             if (nkb > 0) {
-                tmem_ld16(trow + c0, v);
                 if constexpr (Cfg::F16) {
                     float c[16];
-                    tmem_ld16(trow + BN + c0, c);
+                    tmem_ld16x2(trow + c0, trow + BN + c0, v, c);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaf(c[j], 1.0f / F16_LO_SCALE, v[j]);
+                } else {
+                    tmem_ld16(trow + c0, v);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
+            if (via_l2) {
+                if (row_live) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(ct_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 16; j += 4) __stcg(reinterpret_cast<float4*>(ct_row + c0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(ct_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
         }
         if (ct == 0) UMMA_DBG(11);
         }
@@ -445,6 +477,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---- staged tile -> global: lanes along N (coalesced); split-K partial tiles are reduced across the
     //      cluster through distributed shared memory, each CTA finishing 128/splitk rows ----
     if (tid == 0) UMMA_DBG(8);
+    const bool via_l2 = p.splitk > 1 && p.scratch != nullptr;
+    if (via_l2) __threadfence();   // partial tile visible device-wide before the cluster barrier
     if (p.splitk > 1) cg::this_cluster().sync(); else __syncthreads();
     if (tid == 64) UMMA_DBG(12);
     {
@@ -457,9 +491,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r_begin = z * rows_per, r_end = r_begin + rows_per;
         const bool gate = p.act == ACT_GATE;
         const float* peers[8];
+        const long long tile_lin = ((long long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const int ldp = via_l2 ? BN : CT_LD;   // row pitch of a partial tile (global scratch / padded smem staging)
 #pragma unroll
-        for (int zz = 0; zz < 8; ++zz)
-            peers[zz] = (p.splitk > 1 && zz < p.splitk) ? cg::this_cluster().map_shared_rank(Ct, zz) : Ct;
+        for (int zz = 0; zz < 8; ++zz) {
+            if (via_l2) peers[zz] = p.scratch + ((tile_lin * p.splitk + (zz < p.splitk ? zz : 0)) * UM_BM) * BN;
+            else peers[zz] = (p.splitk > 1 && zz < p.splitk) ? cg::this_cluster().map_shared_rank(Ct, zz) : Ct;
+        }
         if (p.vec_store) {
             // fast path (plain row-major output, no gate): float4 per lane, BN/4 lanes per row
             constexpr int LPR = BN >= 128 ? 32 : BN / 4, RPI = 32 / LPR, NCH = (BN / 4) / LPR;   // BN = 256: two 128-column chunks per row
@@ -470,15 +508,48 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool ncol = n < p.N;  // N % 4 == 0 on this path
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias && ncol) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            // L2 path: the partial sums of up to RB rows of this warp are fetched together (the loop is bound by L2 latency,
+            // one row at a time left ~4 loads in flight per warp); pre[k] = sum over z, in z order, of row k of the batch
+            constexpr int RB = 3;
+            float4 pre[RB];
+            int pre_base = -1;   // first row of the batch held in pre[]
             for (int row = r_begin + warp * RPI + sub; row < r_end; row += UM_WARPS * RPI) {
                 const int m = m0 + row;
+                if (via_l2 && (pre_base < 0 || row >= pre_base + RB * UM_WARPS * RPI)) {
+                    pre_base = row;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {       // z = 0..3, then 4..7
+                        float4 t[RB][4];
+#pragma unroll
+                        for (int k = 0; k < RB; ++k) {
+                            const int rk = row + k * UM_WARPS * RPI;
+                            const bool okr = rk < r_end && (m0 + rk) < p.M && ncol;
+#pragma unroll
+                            for (int zz = 0; zz < 4; ++zz)
+                                t[k][zz] = (okr && (h * 4 + zz) < p.splitk) ? __ldcg(reinterpret_cast<const float4*>(peers[h * 4 + zz] + rk * BN + c4))
+                                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int k = 0; k < RB; ++k) {
+                            if (h == 0) pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int zz = 0; zz < 4; ++zz) { pre[k].x += t[k][zz].x; pre[k].y += t[k][zz].y; pre[k].z += t[k][zz].z; pre[k].w += t[k][zz].w; }
+                        }
+                        if (p.splitk <= 4) break;
+                    }
+                }
                 if (m >= p.M || !ncol) continue;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (via_l2) {
+                    const int k = (row - pre_base) / (UM_WARPS * RPI);
+                    a = k == 0 ? pre[0] : (k == 1 ? pre[1] : pre[2]);
+                } else {
 #pragma unroll
-                for (int zz = 0; zz < 8; ++zz) {
-                    if (zz < p.splitk) {
-                        const float4 t = *reinterpret_cast<const float4*>(peers[zz] + row * CT_LD + c4);
-                        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                    for (int zz = 0; zz < 8; ++zz) {
+                        if (zz < p.splitk) {
+                            const float4 t = *reinterpret_cast<const float4*>(peers[zz] + row * CT_LD + c4);
+                            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                        }
                     }
                 }
                 float4 v;
@@ -509,8 +580,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int zz = 0; zz < 8; ++zz) {
                         if (zz < p.splitk) {
-                            v += peers[zz][row * CT_LD + col];
-                            if (gate) vp += peers[zz][row * CT_LD + (col ^ 1)];
+                            if (via_l2) {
+                                v += __ldcg(peers[zz] + row * ldp + col);
+                                if (gate) vp += __ldcg(peers[zz] + row * ldp + (col ^ 1));
+                            } else {
+                                v += peers[zz][row * ldp + col];
+                                if (gate) vp += peers[zz][row * ldp + (col ^ 1)];
+                            }
                         }
                     }
                     if (n < p.N) epilogue_elem(p, bias, C, C2, R, m, n, v, vp);
@@ -519,7 +595,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
     if (tid == 64) UMMA_DBG(13);
-    if (p.splitk > 1) cg::this_cluster().sync();  // peers may still be reading this CTA's staging tile
+    if (p.splitk > 1 && !via_l2) cg::this_cluster().sync();  // DSMEM path: peers may still be reading this CTA's staging tile
     if (tid == 64) UMMA_DBG(9);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

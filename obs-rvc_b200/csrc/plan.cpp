@@ -502,11 +502,23 @@ void schedule_gemms(PB& b) {
         GemmOp& g = op.gemm;
         GemmSched s = gemm_schedule(g, b.allow_umma);
         g.sched_variant = s.variant; g.splitk = s.splitk;
-        if (s.variant > 0 && s.variant < 5 && s.splitk > 1) {  // v2 only: the tcgen05 kernel reduces over DSMEM
+        if (s.variant > 0 && s.variant < 5 && s.splitk > 1) {  // v2: partial tiles + one arrival counter per tile
             g.scratch = b.alloc("", int64_t(s.splitk) * g.batch * g.M * g.N);
             g.counters = b.alloc("", s.tiles, true);
         }
     }
+    // tcgen05 kernel: the split-K partial tiles of a cluster are exchanged through L2.  Ops of one lane run one after
+    // the other, so a lane needs one scratch area, sized for its largest op ([tiles][splitk][128][BN] floats).
+    int64_t need[8] = {0};
+    for (Op& op : b.plan.ops) {
+        if (op.kind != OP_GEMM || op.gemm.sched_variant < 5 || op.gemm.splitk <= 1 || op.lane >= 8) continue;
+        GemmSched s = gemm_schedule(op.gemm, b.allow_umma);
+        need[op.lane] = std::max(need[op.lane], int64_t(s.tiles) * s.splitk * 128 * s.bn);
+    }
+    Ref lane_scratch[8];
+    for (int l = 0; l < 8; ++l) if (need[l] > 0) lane_scratch[l] = b.alloc("", need[l]);
+    for (Op& op : b.plan.ops)
+        if (op.kind == OP_GEMM && op.gemm.sched_variant >= 5 && op.gemm.splitk > 1 && op.lane < 8) op.gemm.scratch = lane_scratch[op.lane];
 }
 
 // ------------------------------------------------------------------------------------------
