@@ -122,6 +122,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Activations: the cheap ones inline, the transcendental bodies (erff / tanhf / expf) out of line - inlined eight times
+// per row they made the epilogue loop several thousand instructions long and every pass streamed it through the
+// instruction cache (~950 cycles per row, measured)
+__device__ __noinline__ float umma_act_slow(int act, float v) { return apply_act(act, v); }
+__device__ __forceinline__ float umma_act(int act, float v) {
+    if (act == ACT_NONE) return v;
+    if (act == ACT_LRELU01) return v > 0.0f ? v : 0.1f * v;
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    return umma_act_slow(act, v);
+}
+
 // two 16-column TMEM loads (main + correction accumulator) behind ONE wait
 __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float* v, float* c) {
     uint32_t r[16], q[16];
@@ -508,6 +519,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool ncol = n < p.N;  // N % 4 == 0 on this path
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (bias && ncol) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+            if (tid == 64 && bv.x == 12345.678f) UMMA_DBG(15);   // (forces the bias load to complete before the next stamp)
+            if (tid == 64) UMMA_DBG(14);
             // L2 path: the partial sums of up to RB rows of this warp are fetched together (the loop is bound by L2 latency,
             // one row at a time left ~4 loads in flight per warp); pre[k] = sum over z, in z order, of row k of the batch
             constexpr int RB = 3;
@@ -526,7 +539,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             const bool okr = rk < r_end && (m0 + rk) < p.M && ncol;
 #pragma unroll
                             for (int zz = 0; zz < 4; ++zz)
-                                t[k][zz] = (okr && (h * 4 + zz) < p.splitk) ? __ldcg(reinterpret_cast<const float4*>(peers[h * 4 + zz] + rk * BN + c4))
+                                t[k][zz] = (okr && (h * 4 + zz) < p.splitk && g_dev_dbg_skip != 4) ? __ldcg(reinterpret_cast<const float4*>(peers[h * 4 + zz] + rk * BN + c4))
                                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
 #pragma unroll
@@ -538,6 +551,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (p.splitk <= 4) break;
                     }
                 }
+                if (tid == 64 && row == r_begin + warp * RPI + sub && pre[0].x != 12345.678f) UMMA_DBG(15);
                 if (m >= p.M || !ncol) continue;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (via_l2) {
@@ -553,19 +567,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
                 float4 v;
-                v.x = apply_act(p.act, fmaf(p.alpha, a.x, bv.x)); v.y = apply_act(p.act, fmaf(p.alpha, a.y, bv.y));
-                v.z = apply_act(p.act, fmaf(p.alpha, a.z, bv.z)); v.w = apply_act(p.act, fmaf(p.alpha, a.w, bv.w));
+                if (p.act == ACT_GELU) {   // the FFN's activation: four independent erff chains inline (ILP), not four calls
+                    v.x = gelu_f(fmaf(p.alpha, a.x, bv.x)); v.y = gelu_f(fmaf(p.alpha, a.y, bv.y));
+                    v.z = gelu_f(fmaf(p.alpha, a.z, bv.z)); v.w = gelu_f(fmaf(p.alpha, a.w, bv.w));
+                } else {
+                    v.x = umma_act(p.act, fmaf(p.alpha, a.x, bv.x)); v.y = umma_act(p.act, fmaf(p.alpha, a.y, bv.y));
+                    v.z = umma_act(p.act, fmaf(p.alpha, a.z, bv.z)); v.w = umma_act(p.act, fmaf(p.alpha, a.w, bv.w));
+                }
                 if (R) {
                     const float4 r = *reinterpret_cast<const float4*>(R + (long long)m * p.ldr + n);
                     v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
                 }
                 const bool masked = p.mask_period > 0 && (m % p.mask_period) >= p.mask_valid;
                 if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(C + (long long)m * p.ldc + n) = v;
+                if (g_dev_dbg_skip != 5) *reinterpret_cast<float4*>(C + (long long)m * p.ldc + n) = v;
                 if (C2) {
                     float4 w;
-                    w.x = masked ? 0.f : apply_act(p.act2, v.x); w.y = masked ? 0.f : apply_act(p.act2, v.y);
-                    w.z = masked ? 0.f : apply_act(p.act2, v.z); w.w = masked ? 0.f : apply_act(p.act2, v.w);
+                    w.x = masked ? 0.f : umma_act(p.act2, v.x); w.y = masked ? 0.f : umma_act(p.act2, v.y);
+                    w.z = masked ? 0.f : umma_act(p.act2, v.z); w.w = masked ? 0.f : umma_act(p.act2, v.w);
                     *reinterpret_cast<float4*>(C2 + (long long)m * p.ldc2 + n) = w;
                 }
             }

@@ -14,7 +14,7 @@ for name in sys.argv[1:] or ["cv.conv6", "cv.conv1", "cv.L0.fc2", "cv.L0.qkv", "
     out = (ctypes.c_longlong * 96)()
     rc = L.rvc_debug_umma_timing(eng.handle, name.encode(), out)
     t = np.array(list(out), dtype=np.int64)
-    print(name, rc, "cycles since start:", [int(v - t[0]) for v in t[:14]])
+    print(name, rc, "cycles since start:", [int(v - t[0]) for v in t[:16]])
     if not name.endswith("@v2"):
         ev = t[16:96].reshape(5, 16) - t[0]
         for lab, row in zip(("prod empty-ok", "prod tma-issued", "mma full-ok", "mma conv-ok", "mma issued"), ev):
