@@ -489,6 +489,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     //      cluster through distributed shared memory, each CTA finishing 128/splitk rows ----
     if (tid == 0) UMMA_DBG(8);
     const bool via_l2 = p.splitk > 1 && p.scratch != nullptr;
+    // bias of this lane's columns: requested BEFORE the barrier (parameter vectors are cold in L2 every window - an HBM
+    // round trip of ~900 cycles that used to sit at the head of the store loop)
+    float4 bv_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.vec_store && p.bias) {
+        constexpr int LPR0 = BN >= 128 ? 32 : BN / 4;
+        const int n_pre = n0 + (lane % LPR0) * 4;
+        if (n_pre < p.N) bv_pre = __ldg(reinterpret_cast<const float4*>(p.bias + bz * p.sBias + n_pre));
+    }
     if (via_l2) __threadfence();   // partial tile visible device-wide before the cluster barrier
     if (p.splitk > 1) cg::this_cluster().sync(); else __syncthreads();
     if (tid == 64) UMMA_DBG(12);
@@ -517,9 +525,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int ch = 0; ch < NCH; ++ch) {
             const int c4 = (ch * LPR + lane % LPR) * 4, n = n0 + c4;
             const bool ncol = n < p.N;  // N % 4 == 0 on this path
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias && ncol) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-            if (tid == 64 && bv.x == 12345.678f) UMMA_DBG(15);   // (forces the bias load to complete before the next stamp)
+            float4 bv = bv_pre;   // chunk 0 was requested before the barrier
+            if (ch > 0 && bias && ncol) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
             if (tid == 64) UMMA_DBG(14);
             // L2 path: the partial sums of up to RB rows of this warp are fetched together (the loop is bound by L2 latency,
             // one row at a time left ~4 loads in flight per warp); pre[k] = sum over z, in z order, of row k of the batch
