@@ -39,7 +39,10 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     // RMVPE (SP_F0) stays on exact-fp32 CUDA cores (its 360-bin argmax is a bit-exact parity item)
     const bool contiguous = g.seg_len >= g.K;
     if (allow_umma && (g.W.space == SP_CV || g.W.space == SP_SYN) && g.M >= 64 && g.N % 16 == 0 && g.N >= 32 &&
-        (contiguous || (g.seg_len % 32 == 0 && g.K % g.seg_len == 0)) && g.K >= 96) {
+        (contiguous || (g.seg_len % 32 == 0 && g.K % g.seg_len == 0) ||
+         (sched_env("RVC_UMMA_F16", 1) != 0 && g.seg_len % 8 == 0 && g.K % g.seg_len == 0)) && g.K >= 96) {
+        // (segments that are only a multiple of 8 long - ContentVec's grouped pos-conv, 48 channels per group - need the
+        //  FP16-split kernel, whose A path walks the segmented rows itself; the TMA box of the 3xTF32 path cannot)
         const int tm = (g.M + 127) / 128;
         const int nkb = (g.K + 31) / 32;
         // one CTA per SM (smem-limited) and clusters must pack into GPCs: aim for a single wave of

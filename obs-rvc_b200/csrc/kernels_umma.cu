@@ -754,6 +754,7 @@ int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream)
         return ok ? 1 : 0;
     }
     if (bn == 256) return 0;   // only the FP16-split kernel has a 256-wide instance: the caller falls back to CUDA cores
+    if (g.seg_len < g.K && g.seg_len % 32 != 0) return 0;   // odd segment lengths: FP16-split kernel only (see gemm_sched.h)
     if (g_umma_passes == 3) {
         ok = bn == 128 ? launch_umma_cfg<128, 3>(g, p, w_hi, w_lo, stream)
            : bn == 64 ? launch_umma_cfg<64, 3>(g, p, w_hi, w_lo, stream) : launch_umma_cfg<32, 3>(g, p, w_hi, w_lo, stream);

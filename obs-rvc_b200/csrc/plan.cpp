@@ -124,7 +124,7 @@ Ref build_contentvec(PB& b, const Packed* P, const CvInfo& info, Ref pcm, int N,
         GemmOp& g = b.gemm("cv.posconv", xpad, 768, 48, 768, W("pos.w"), 128 * 48, W("pos.b"), pc, 768, T, 48,
                            128 * 48, ACT_GELU);
         g.R = x; g.ldr = 768; g.batch = 16; g.sA = 48; g.sW = int64_t(48) * 128 * 48; g.sBias = 48; g.sC = 48;
-        g.sR = 48;
+        g.sR = 48; g.cta_budget = 128;   // 16 groups x split-K 8: 6144-deep contraction, 24 k-blocks per CTA
     }
     Ref cur = b.alloc("cv.enc_in", int64_t(T) * 768);
     b.layernorm("cv.enc_in", pc, 768, cur, 768, W("eln.g"), W("eln.b"), T, 768);
