@@ -454,9 +454,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // shared memory over DSMEM ran at ~8 B/clk per SM and cost two cluster barriers (measured 12-15 k cycles per GEMM)
         const bool via_l2 = p.splitk > 1 && p.scratch != nullptr;
         const long long tile_lin = ((long long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        float* ct_row = via_l2 ? p.scratch + ((tile_lin * p.splitk + z) * UM_BM + row) * BN
-                               : reinterpret_cast<float*>(smem) + row * CT_LD;
-        const bool row_live = !via_l2 || (m0 + row) < p.M;   // rows past M are never read back
+        // (the drain itself always goes to the padded smem staging tile: a lane owns a ROW, so writing global memory from
+        //  here would be 32 scattered 64-byte pieces per instruction; the coalesced copy to the scratch follows below)
+        float* ct_row = reinterpret_cast<float*>(smem) + row * CT_LD;
+        (void)tile_lin;
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];
             if (nkb > 0) {
@@ -472,15 +473,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
             }
-            if (via_l2) {
-                if (row_live) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) __stcg(reinterpret_cast<float4*>(ct_row + c0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(ct_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(ct_row + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         if (ct == 0) UMMA_DBG(11);
         }
@@ -497,7 +491,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n_pre = n0 + (lane % LPR0) * 4;
         if (n_pre < p.N) bv_pre = __ldg(reinterpret_cast<const float4*>(p.bias + bz * p.sBias + n_pre));
     }
-    if (via_l2) __threadfence();   // partial tile visible device-wide before the cluster barrier
+    if (via_l2) {
+        // staged partial tile -> this CTA's slot of the L2 scratch, coalesced (all 12 warps, float4 along the columns)
+        __syncthreads();
+        const long long tile_lin0 = ((long long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        float* dst = p.scratch + ((tile_lin0 * p.splitk + z) * UM_BM) * BN;
+        const float* src = reinterpret_cast<const float*>(smem);
+        const int live_rows = min(UM_BM, p.M - m0);   // rows past M are never read back
+        for (int e = tid; e < live_rows * (BN / 4); e += UM_THREADS) {
+            const int r = e / (BN / 4), c = (e - r * (BN / 4)) * 4;
+            __stcg(reinterpret_cast<float4*>(dst + r * BN + c), *reinterpret_cast<const float4*>(src + r * CT_LD + c));
+        }
+        __threadfence();   // partial tile visible device-wide before the cluster barrier
+    }
     if (p.splitk > 1) cg::this_cluster().sync(); else __syncthreads();
     if (tid == 64) UMMA_DBG(12);
     {
