@@ -721,11 +721,20 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     // that is emitted first was observed to start first (the other way round ContentVec began ~0.5 ms late).
     if (ml) b.wait(0, 1);
     int T = 0;
-    Ref x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
+    Ref x{};
+    F0Out fo{};
+    static const bool f0_first = sched_env("RVC_F0_FIRST", 1) != 0;
+    auto emit_f0 = [&]() {
+        if (ml) { b.lane = 1; b.sc_lane = 3; }
+        fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
+        b.lane = 0; b.sc_lane = -1;
+    };
+    // The lane whose ops are emitted (= whose graph nodes are created) first gets the SMs first when both lanes have
+    // work ready.  Since the tcgen05 GEMMs got faster the F0 chain is the longer branch: it goes first.
+    if (f0_first) emit_f0();
+    x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
     if (!b.ok) return false;
-    if (ml) { b.lane = 1; b.sc_lane = 3; }
-    F0Out fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
-    b.lane = 0; b.sc_lane = -1;
+    if (!f0_first) emit_f0();
     plan.f0_T = fo.T;
     const int C = cvi->out_dim;
     plan.hubert_T = T; plan.hubert_C = C;
