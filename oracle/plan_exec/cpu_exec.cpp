@@ -462,6 +462,7 @@ struct Exec {
     RunParams rp{};
     int index_k = 8;
     bool allow_umma = true;
+    int chain_main = 0, chain_side = 0, chain_max_m = 0;   // persistent chains off unless pe_set_chain asks
     Exec() : state(StateLayout::bytes, 0) { rp.uppower = 1.f; rp.noise_mode = 1; }
     Bases bases() {
         Bases B;
@@ -509,6 +510,7 @@ int pe_run(void* h, int kind, const float* pcm, int n, int sf16k, int pitch_shif
     Exec* e = static_cast<Exec*>(h);
     Geometry g{n, sf16k, skip_head, return_length};
     PlanOptions opt; opt.index_k = e->index_k; opt.allow_umma = e->allow_umma; opt.with_index = e->index_rows > 0; opt.index_rows = e->index_rows;
+    opt.chain_grid_main = e->chain_main; opt.chain_grid_side = e->chain_side; opt.chain_side_max_m = e->chain_max_m;
     if (!build_plan(PlanKind(kind), g, opt, e->has_cv ? &e->cv : nullptr, &e->cvi, e->has_f0 ? &e->f0 : nullptr, &e->f0i,
                     e->has_syn ? &e->syn : nullptr, &e->syi, e->plan, e->err)) return 1;
     e->work.assign(size_t(e->plan.work_bytes), 0);
@@ -516,8 +518,40 @@ int pe_run(void* h, int kind, const float* pcm, int n, int sf16k, int pitch_shif
     std::memcpy(e->state.data() + StateLayout::off_params, &e->rp, sizeof(RunParams));
     std::memcpy(e->state.data() + StateLayout::off_pcm, pcm, sizeof(float) * n);
     Bases B = e->bases();
-    for (const Op& op : e->plan.ops) run_op(op, B);
+    // Ops outside chains run in plan order.  A chain (chain.h) runs phase by phase, and INSIDE a phase in REVERSE plan
+    // order: the plan builder claims the ops of a phase are independent, so any order must give the same bits - a wrong
+    // dependency analysis shows up as a different result (tests/test_host_cpu.py).
+    const size_t n_ops = e->plan.ops.size();
+    for (size_t i = 0; i < n_ops;) {
+        const Op& op = e->plan.ops[i];
+        if (op.chain < 0) { run_op(op, B); ++i; continue; }
+        const ChainInfo& ci = e->plan.chains[size_t(op.chain)];
+        for (int ph = 0; ph < ci.n_phases; ++ph)
+            for (int k = ci.count - 1; k >= 0; --k)
+                if (ci.phase[size_t(k)] == ph) run_op(e->plan.ops[size_t(ci.first + k)], B);
+        i = size_t(ci.first + ci.count);
+    }
     if (kind == PLAN_INFER) e->rp.window++;
+    return 0;
+}
+
+// chains of the last plan: CTA budgets for lane 0 / side lanes and the largest M of a side-lane GEMM that may join
+void pe_set_chain(void* h, int grid_main, int grid_side, int side_max_m) {
+    Exec* e = static_cast<Exec*>(h);
+    e->chain_main = grid_main; e->chain_side = grid_side; e->chain_max_m = side_max_m;
+}
+int pe_chain_stats(void* h, int* out /* n_chains, n_phases, n_chain_ops, max ops in one phase */) {
+    Exec* e = static_cast<Exec*>(h);
+    int phases = 0, ops = 0, widest = 0;
+    for (const ChainInfo& ci : e->plan.chains) {
+        phases += ci.n_phases; ops += ci.count;
+        for (int ph = 0; ph < ci.n_phases; ++ph) {
+            int w = 0;
+            for (int k = 0; k < ci.count; ++k) w += ci.phase[size_t(k)] == ph;
+            widest = std::max(widest, w);
+        }
+    }
+    out[0] = int(e->plan.chains.size()); out[1] = phases; out[2] = ops; out[3] = widest;
     return 0;
 }
 

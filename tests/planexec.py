@@ -26,7 +26,7 @@ class PlanExec:
         L.pe_buf_name.restype = ctypes.c_char_p
         L.pe_get.restype = ctypes.c_long
         for f in (L.pe_destroy, L.pe_error, L.pe_load, L.pe_set_index, L.pe_set_params, L.pe_run,
-                  L.pe_num_ops, L.pe_num_bufs, L.pe_buf_name, L.pe_get, L.pe_plan_dims):
+                  L.pe_num_ops, L.pe_num_bufs, L.pe_buf_name, L.pe_get, L.pe_plan_dims, L.pe_set_chain, L.pe_chain_stats):
             f.argtypes = None
         self.L = L
         self.h = ctypes.c_void_p(L.pe_create(data_dir.encode()))
@@ -54,6 +54,16 @@ class PlanExec:
                                 ctypes.c_int(pcm.shape[0]), ctypes.c_int(sf16k),
                                 ctypes.c_int(pitch_shift), ctypes.c_int(skip_head),
                                 ctypes.c_int(return_length)))
+
+    def set_chain(self, grid_main=148, grid_side=32, side_max_m=8):
+        """Plans built from now on group small same-lane ops into persistent chains (chain.h); `run` then executes
+        every chain phase by phase with the ops of a phase in REVERSE order."""
+        self.L.pe_set_chain(self.h, ctypes.c_int(grid_main), ctypes.c_int(grid_side), ctypes.c_int(side_max_m))
+
+    def chain_stats(self):
+        out = (ctypes.c_int * 4)()
+        self.L.pe_chain_stats(self.h, out)
+        return dict(n_chains=out[0], n_phases=out[1], n_chain_ops=out[2], widest_phase=out[3])
 
     def names(self):
         return [self.L.pe_buf_name(self.h, ctypes.c_int(i)).decode()

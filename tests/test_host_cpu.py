@@ -85,6 +85,47 @@ def test_plan_on_cpu_matches_oracle(built, data):
     pe.close()
 
 
+def test_chain_phases_are_order_independent(built, data):
+    """Persistent chains (chain.h): plan.cpp groups runs of small same-lane ops into phases whose ops it claims are
+    independent.  The CPU interpreter runs each phase in REVERSE plan order: the window must come out bit-identical
+    to the plain in-order run, for the default grids and for a plan that chains the whole RMVPE U-Net."""
+    import planexec
+    from oracle import pipeline
+    g = pipeline.BASELINE_GEOM
+    x = pipeline.synthetic_pcm(g["n16k"], seed=3)
+    outs = {}
+    for name, cfg in (("off", None), ("default", (148, 32, 8)), ("wide", (96, 48, 0))):
+        pe = planexec.PlanExec(data["data"])
+        pe.load(0, data["contentvec"]); pe.load(1, data["f0"]); pe.load(2, data["model"])
+        pe.set_params(seed=0, noise_mode=1, index_k=8)
+        if cfg:
+            pe.set_chain(*cfg)
+        pe.run(planexec.PLAN_INFER, x, g["sf16k"], 12, g["skip_head"], g["return_length"])
+        outs[name] = (pe.get("audio"), pe.get("f0_argmax", np.int32), pe.get("rm.salience"), pe.chain_stats())
+        pe.close()
+    assert outs["off"][3]["n_chains"] == 0
+    st = outs["default"][3]
+    assert st["n_chains"] == 3 and st["n_chain_ops"] >= 100 and st["n_phases"] <= st["n_chain_ops"], st
+    assert outs["wide"][3]["n_chain_ops"] > st["n_chain_ops"] + 80, outs["wide"][3]      # the whole U-Net joined
+    for name in ("default", "wide"):
+        np.testing.assert_array_equal(outs[name][0], outs["off"][0])
+        np.testing.assert_array_equal(outs[name][1], outs["off"][1])
+        np.testing.assert_array_equal(outs[name][2], outs["off"][2])
+    # the single-lane pitch plan keeps the shortcut convs on the F0 lane: c1 and its shortcut share a phase there
+    sal = {}
+    for name, cfg in (("off", None), ("chained", (148, 32, 0))):
+        pe = planexec.PlanExec(data["data"])
+        pe.load(1, data["f0"])
+        if cfg:
+            pe.set_chain(*cfg)
+        pe.run(planexec.PLAN_PITCH, x, g["sf16k"], 12, 0, 0)
+        sal[name] = (pe.get("rm.salience"), pe.get("f0"), pe.chain_stats())
+        pe.close()
+    assert sal["chained"][2]["widest_phase"] >= 2 and sal["chained"][2]["n_chain_ops"] > 120, sal["chained"][2]
+    np.testing.assert_array_equal(sal["chained"][0], sal["off"][0])
+    np.testing.assert_array_equal(sal["chained"][1], sal["off"][1])
+
+
 def test_plan_shape_contract(built, data):
     """SURVEY 8b shape contract: violations are plan errors, not crashes."""
     import planexec
