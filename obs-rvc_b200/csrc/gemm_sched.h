@@ -30,7 +30,7 @@ inline int sched_env(const char* name, int dflt) {
 
 inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     GemmSched s;
-    static const int kWant = sched_env("RVC_UMMA_WANT", 112), kBn128 = sched_env("RVC_UMMA_BN128_MIN", 1),
+    static const int kWant = sched_env("RVC_UMMA_WANT", 96), kBn128 = sched_env("RVC_UMMA_BN128_MIN", 1),
                      kKbMin = sched_env("RVC_UMMA_KB_MIN", 4);
     const bool aligned = g.A.off % 16 == 0 && g.W.off % 16 == 0 && g.lda % 4 == 0 && g.seg_len % 4 == 0 &&
                          g.seg_stride % 4 == 0 && g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
