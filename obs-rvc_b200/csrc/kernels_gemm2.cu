@@ -266,8 +266,8 @@ void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
     constexpr size_t red_bytes = sizeof(float) * 8 * BM * BN;
     constexpr size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
     auto kern = gemm_v2_kernel<BM, BN, STAGES>;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); attr = true; }
+    static unsigned long long attr = 0;
+    if (first_time_on_device(attr)) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     const int nkt = (g.K + BK2 - 1) / BK2;
     p.kt_per_split = (nkt + g.splitk - 1) / g.splitk;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch * g.splitk);

@@ -243,8 +243,8 @@ void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaS
     auto kern = knn_scan_kernel<CV, QN, G, KK, RR>;
     const size_t q_bytes = sizeof(float) * size_t(G) * QN * o.C, m_bytes = size_t(8) * G * QN * KK * 8;
     const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    static unsigned long long attr = 0;
+    if (first_time_on_device(attr)) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     launch_k(kern, dim3(o.parts), dim3(256), smem, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
                                               B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k,
                                               B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
@@ -280,8 +280,8 @@ int launch_knn_scan(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
 }
 
 int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    static unsigned long long attr = 0;
+    if (first_time_on_device(attr)) cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int M = o.parts * o.k;
     const size_t need = size_t(M) * 8;
     const int staged = need <= 200 * 1024 ? 1 : 0;

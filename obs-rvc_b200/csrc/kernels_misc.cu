@@ -458,9 +458,8 @@ size_t relattn_smem(int T, int dim) { return sizeof(float) * (size_t(dim) + size
 }  // namespace
 
 void init_kernel_attributes() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static unsigned long long done = 0;
+    if (!first_time_on_device(done)) return;
     cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(relattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     init_gemm_v2_attributes();

@@ -50,7 +50,18 @@ void launch_envelop_mix(float* out, int n_out, const float* r1, const float* r2,
 void launch_sola(const float* x, const float* sola, int buf, int search, float* cor, int* offset, cudaStream_t s);
 void launch_sola_crossfade(float* out, const int* offset, float* sola_buffer, int buf, int frame, float* block_out, cudaStream_t s);
 
-// one-time per-process kernel attribute setup (dynamic shared memory opt-in)
+// Function attributes (dynamic shared memory opt-in) belong to a device: `mask` remembers the devices a call site has
+// already configured; returns true the first time it is reached with the calling thread's current device.
+inline bool first_time_on_device(unsigned long long& mask) {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 0 || d > 63) return true;
+    if ((mask >> d) & 1ull) return false;
+    mask |= 1ull << d;
+    return true;
+}
+
+// per-device kernel attribute setup (dynamic shared memory opt-in)
 void init_kernel_attributes();
 void init_gemm_v2_attributes();
 void init_umma_attributes();

@@ -175,8 +175,31 @@ def test_persistent_chains_match_separate_kernels(env, monkeypatch):
     np.testing.assert_array_equal(res["2"]["argmax"], res["0"]["argmax"])
     np.testing.assert_array_equal(res["2"]["pitch"], res["0"]["pitch"])
     for a, b in zip(res["2"]["audio"], res["0"]["audio"]):
-        np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
         assert _rms(a) > 0.01
+
+
+def test_two_devices_one_process(env):
+    """Contexts on different GPUs of one process are independent (kernel attributes are set per device, weights and
+    state live on the context's device): the same window on cuda:0 and cuda:1 gives the same integers and the same
+    audio up to fp32 summation order (the second context is not alone in the process, so it runs without chains)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rb = env["rvc_b200"]
+    g = env["pipeline"].BASELINE_GEOM
+    x = env["pipeline"].synthetic_pcm(g["n16k"], seed=13)
+    res = []
+    for dev in (0, 1):
+        e = rb.RvcInfer(env["paths"]["data"], device=dev, noise_seed=2)
+        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+        a = e.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+        res.append((a, e.get_last("f0_argmax", np.int32).copy(), e.get_last("pitch", np.int32).copy()))
+        e.close()
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=0, atol=1e-4)
+    assert _rms(res[0][0]) > 0.01
 
 
 def test_noise_modes_and_pitch_shift_quirk(env):
@@ -308,7 +331,7 @@ def test_rvc_rpc_wire_protocol(env):
             got = np.frombuffer(p.stdout.read(nb), dtype="<f4")
             # the child process is alone on the GPU and runs the persistent-chain plan; this process holds other
             # contexts and runs the same ops as separate kernels (engine.cu live_contexts): fp32 sums in another order
-            np.testing.assert_allclose(got, want[w], rtol=0, atol=2e-5)
+            np.testing.assert_allclose(got, want[w], rtol=0, atol=1e-4)
     finally:
         p.kill()
 
