@@ -310,9 +310,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int ks = 0; ks < UM_BK / 16; ++ks) {
                         const uint32_t off = ks * 32;
                         const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-                        umma_f16(tmem_base, umma_desc64(a_hi + off), umma_desc64(w_hi + off), idesc16, first);
-                        umma_f16(tmem_base + BN, umma_desc64(a_lo + off), umma_desc64(w_hi + off), idesc16, first);
-                        umma_f16(tmem_base + BN, umma_desc64(a_hi + off), umma_desc64(w_lo + off), idesc16, 1u);
+                        if constexpr (BN <= 128) {
+                            // the two weight planes of a stage are adjacent in shared memory: ONE instruction with N = 2 BN
+                            // gives A_hi.W_hi -> D0 (columns 0..BN) and A_hi.W_lo' -> D1 (columns BN..2BN); the issue cost
+                            // of a tcgen05.mma is the same whatever N <= 256, so 2 instructions per k-step instead of 3
+                            constexpr uint32_t idesc2n = (1u << 4) | (uint32_t((2 * BN) >> 3) << 17) | (uint32_t(UM_BM >> 4) << 24);
+                            umma_f16(tmem_base, umma_desc64(a_hi + off), umma_desc64(w_hi + off), idesc2n, first);
+                            umma_f16(tmem_base + BN, umma_desc64(a_lo + off), umma_desc64(w_hi + off), idesc16, 1u);
+                        } else {
+                            umma_f16(tmem_base, umma_desc64(a_hi + off), umma_desc64(w_hi + off), idesc16, first);
+                            umma_f16(tmem_base + BN, umma_desc64(a_lo + off), umma_desc64(w_hi + off), idesc16, first);
+                            umma_f16(tmem_base + BN, umma_desc64(a_hi + off), umma_desc64(w_lo + off), idesc16, 1u);
+                        }
                     }
                     umma_commit(&bar_empty[s]);
                     UMMA_DBG2(4, i);
