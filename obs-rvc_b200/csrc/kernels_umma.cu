@@ -235,7 +235,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
         if (PASSES != 1) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmWlo)) : "memory");
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_conv[s], 8); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&bar_full[s], Cfg::F16 ? 9 : 1); mbar_init(&bar_conv[s], 8); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -297,7 +297,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&bar_full[s], ph);
                 if (i == 0) UMMA_DBG(3);
                 UMMA_DBG2(2, i);
-                if (PASSES != 1) mbar_wait(&bar_conv[s], ph);
+                if (PASSES != 1 && !Cfg::F16) mbar_wait(&bar_conv[s], ph);
                 if (i == 0) UMMA_DBG(4);
                 UMMA_DBG2(3, i);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -416,7 +416,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_conv[s]);
+                if (lane == 0) mbar_arrive(&bar_full[s]);   // one barrier per stage: weights landed (tx) + planes written (8 arrivals)
             }
             }
         } else if (PASSES == 3) {
