@@ -10,6 +10,7 @@
 // a fixed order; ties resolve to the lowest row index.
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 #include "launch.h"
 #include "pdl.cuh"
@@ -22,8 +23,8 @@ namespace {
 // is used RR times (the scan is otherwise bound by shared-memory reads of the queries, not by HBM); only the Q
 // real queries of a padded group are evaluated.  The 8 per-warp top-k lists of a CTA are merged in shared
 // memory before they leave the SM: one candidate list per CTA (`parts` = gridDim.x).
-template <int CV, int QN, int G, int KK, int RR>
-__global__ void __launch_bounds__(256, 1)
+template <int CV, int QN, int G, int KK, int RR, int PF>
+__global__ void __launch_bounds__(256, PF ? 1 : 2)
 knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __restrict__ queries, long long ldq, int Q,
                 float* __restrict__ cand_d, int* __restrict__ cand_i, int parts, int k) {
     pdl_enter();
@@ -58,10 +59,13 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
     };
     const long long stride = (long long)parts * 8 * RR;
     long long base = ((long long)blockIdx.x * 8 + warp) * RR;
-    if (base < N) load_rows(y, base);
+    if (PF && base < N) load_rows(y, base);
     for (; base < N; base += stride) {
         const bool more = base + stride < N;
-        if (more) load_rows(yn, base + stride);  // next rows in flight while these are reduced
+        // PF = 1: next rows in flight while these are reduced (one CTA per SM); PF = 0: no register double buffer, two
+        // CTAs per SM - the second CTA's warps cover the load latency instead
+        if (PF) { if (more) load_rows(yn, base + stride); }
+        else load_rows(y, base);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             float v[RR][QN];
@@ -119,7 +123,7 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
                 }
             }
         }
-        if (more) {
+        if (PF && more) {
 #pragma unroll
             for (int r = 0; r < RR; ++r)
 #pragma unroll
@@ -240,7 +244,17 @@ knn_blend_kernel(const float* __restrict__ index, const int* __restrict__ idx, c
 
 template <int CV, int QN, int G, int KK, int RR>
 void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaStream_t s) {
-    auto kern = knn_scan_kernel<CV, QN, G, KK, RR>;
+    if (G == 1 && knn_two_ctas_per_sm(o.Q, o.C, o.k)) {
+        auto kern2 = knn_scan_kernel<CV, QN, G, KK, RR, 0>;
+        const size_t q_bytes2 = sizeof(float) * size_t(G) * QN * o.C, m_bytes2 = size_t(8) * G * QN * KK * 8;
+        const size_t smem2 = q_bytes2 > m_bytes2 ? q_bytes2 : m_bytes2;
+        static unsigned long long attr2 = 0;
+        if (first_time_on_device(attr2)) cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        launch_k(kern2, dim3(o.parts), dim3(256), smem2, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
+                 B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k, B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
+        return;
+    }
+    auto kern = knn_scan_kernel<CV, QN, G, KK, RR, 1>;
     const size_t q_bytes = sizeof(float) * size_t(G) * QN * o.C, m_bytes = size_t(8) * G * QN * KK * 8;
     const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
     static unsigned long long attr = 0;

@@ -187,6 +187,17 @@ struct RunParams {
 static const int NOISE_KIND_Z = 1;
 static const int NOISE_KIND_SINE = 2;
 static const int KNN_PARTS = 148;  // one candidate list per CTA (8 warp lists merged on chip), one CTA per SM
+// Few queries (the per-window case: 11 x 768): two CTAs per SM without the register double buffer of the index rows -
+// the second CTA's warps cover the load latency (scan 91 -> 66 us measured).  Needs the padded query block of a CTA
+// to fit twice into shared memory and the small top-k lists (k <= 8).
+inline bool knn_two_ctas_per_sm(int Q, int C, int k) {
+    const int qn = Q <= 8 ? 8 : (Q <= 16 ? 16 : 32);
+    return Q <= 32 && k <= 8 && int64_t(qn) * C * 4 <= 96 * 1024;
+}
+inline int knn_parts(int Q, int C, int k, int n_rows) {
+    const int p = knn_two_ctas_per_sm(Q, C, k) ? 2 * KNN_PARTS : KNN_PARTS;
+    return p < n_rows ? p : n_rows;
+}
 
 // A run of consecutive same-lane ops executed by one persistent cooperative kernel (chain.h).
 // phase[i] is the barrier phase of op first+i: ops of one phase touch disjoint buffers.

@@ -657,7 +657,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         // queries staged in the audio buffer region by the caller: [Q, C]; results -> work
         const int Q = g.n16k, C = g.sf16k, k = g.return_length, Nrows = opt.index_rows;
         if (Q <= 0 || C <= 0 || C % 4 != 0 || C > 1024 || k <= 0 || k > 16 || Nrows < k) { err = "bad kNN shape"; return false; }
-        const int parts = std::min(KNN_PARTS, Nrows);
+        const int parts = knn_parts(Q, C, k, Nrows);
         Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
         Op& a = b.add(OP_KNN_SCAN, "knn_scan");
@@ -750,7 +750,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     if (opt.with_index) {
         const int k = opt.index_k, Nrows = opt.index_rows;
         if (k <= 0 || k > 16 || Nrows < k || C % 4 != 0 || C > 1024) { err = "bad index / k"; return false; }
-        const int parts = std::min(KNN_PARTS, Nrows);
+        const int parts = knn_parts(Q, C, k, Nrows);
         Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
         Ref xb = b.alloc("knn_blend", int64_t(Q) * C);
