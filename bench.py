@@ -337,7 +337,7 @@ def main():
             roof_extra.append(roof_of(name, f))
         for r in roof_extra:
             if r["kernel"] == "knn_scan":
-                r["traffic"] = 123.0e6  # dram__bytes_read of profiles/r01_d_prof_knn2.md (algorithmic 122.9 MB)
+                r["traffic"] = 123.0e6  # dram__bytes_read of profiles/r01_d_prof_knn2.md (one-CTA-per-SM variant; algorithmic 122.9 MB)
         if args.profile_ops:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             json.dump({"step_us": step_us, "ops": prof}, open(os.path.join(ROOT, "gpurun_out", "profile_ops.json"), "w"))
