@@ -160,7 +160,14 @@ __device__ long long g_umma_dbg2[5 * 16];   // [event][k-block < 16] of CTA (0,0
 #endif
 // 1 = store the truncated A_hi back (explicit); 0 = leave the fp32 tile as delivered by TMA and rely on the tensor
 // core ignoring the 13 low mantissa bits of a tf32 operand (saves a third of the converter's shared-memory writes)
-__device__ int g_dev_dbg_skip = 0;     // timing experiments only (RVC_UMMA_DBG_SKIP=1: no A loads, 2: no W loads, 3: no conversion): results are garbage
+// Timing experiments only (results are garbage): RVC_UMMA_DBG_SKIP=1 no A loads, 2 no W loads, 3 no conversion, 4 no
+// partial loads in the epilogue, 5 no C stores.  Compiled in only with -DRVC_UMMA_STAMPS; otherwise the constant 0.
+#ifdef RVC_UMMA_STAMPS
+__device__ int g_dev_dbg_skip_v = 0;
+#define g_dev_dbg_skip g_dev_dbg_skip_v
+#else
+#define g_dev_dbg_skip 0
+#endif
 __device__ int g_dev_w_prefetch = 0;   // RVC_UMMA_WPREFETCH=1: up-front L2 prefetch of the CTA's weight slice (measured: no gain)
 __device__ int g_dev_write_hi = 0;   // RVC_UMMA_WRITE_HI=1 restores the explicit store
 #define UMMA_DBG(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_umma_dbg[i] = clock64(); } while (0)
@@ -738,7 +745,9 @@ void init_umma_attributes() {
     cudaFuncSetAttribute(umma_gemm_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 16>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 16>::SMEM_BYTES);
     { const char* f = getenv("RVC_UMMA_F16"); g_umma_f16 = !(f && f[0] == '0'); }
-    { const char* w = getenv("RVC_UMMA_DBG_SKIP"); int v = w ? atoi(w) : 0; cudaMemcpyToSymbol(g_dev_dbg_skip, &v, sizeof(int)); }
+#ifdef RVC_UMMA_STAMPS
+    { const char* w = getenv("RVC_UMMA_DBG_SKIP"); int v = w ? atoi(w) : 0; cudaMemcpyToSymbol(g_dev_dbg_skip_v, &v, sizeof(int)); }
+#endif
     { const char* w = getenv("RVC_UMMA_WPREFETCH"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_dev_w_prefetch, &v, sizeof(int)); }
     { const char* w = getenv("RVC_UMMA_WRITE_HI"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_dev_write_hi, &v, sizeof(int)); }
     const char* e = getenv("RVC_UMMA_PASSES");
