@@ -104,11 +104,32 @@ int rvc_infer(rvc_ctx* ctx, const float* pcm, size_t n, uint32_t sample_frame_16
 int rvc_infer_dev(rvc_ctx* ctx, const float* pcm_dev, size_t n, uint32_t sample_frame_16k_size,
                   int32_t pitch_shift, uint32_t skip_head, uint32_t return_length,
                   float* out_dev, size_t cap, size_t* out_len);
-/* Independent streams in one call (the path shards by stream).  Windows are
- * enqueued on every context's stream first and synchronised afterwards. */
+/* Independent live streams in one call (the path shards by stream; BASELINE configs[3]:
+ * 8 streams per GPU).  When the contexts sit on one device and share their models / index (weights are
+ * shared by path) the windows run as ONE batched plan - every kernel processes all streams, weights are
+ * read once per round - with per-stream state (pitch cache rvc.rs:26,168-179, call counter, noise seed)
+ * kept in each context; otherwise each window is enqueued on its own context stream.  Results are
+ * identical to n_ctx separate rvc_infer calls. */
 int rvc_infer_batch(rvc_ctx* const* ctxs, size_t n_ctx, const float* const* pcm, size_t n,
                     uint32_t sample_frame_16k_size, int32_t pitch_shift, uint32_t skip_head,
                     uint32_t return_length, float* const* out, size_t cap, size_t* out_len);
+/* Same with device-resident PCM / audio pointers; asynchronous on ctxs[0]'s stream (rvc_sync(ctxs[0])).
+ * Fails with RVC_ERR_INVALID_ARG when the streams cannot share one batched plan. */
+int rvc_infer_batch_dev(rvc_ctx* const* ctxs, size_t n_ctx, const float* const* pcm_dev, size_t n,
+                        uint32_t sample_frame_16k_size, int32_t pitch_shift, uint32_t skip_head,
+                        uint32_t return_length, float* const* out_dev, size_t cap, size_t* out_len);
+/* Offline conversion of ONE stream (BASELINE configs[2]: batch = 32): `n_windows` consecutive windows,
+ * window w = pcm[w * sample_frame_16k_size, w * sample_frame_16k_size + n) - exactly what n_windows
+ * successive RvcInfer::infer calls of the reference's streaming loop see (obs-rvc/src/lib.rs:659-707) -
+ * processed `max_batch` (<= 32, 0 = 32) windows per launch: each kernel runs over the whole group, the
+ * weights are read once per group, the pitch cache is updated window by window inside the plan.
+ * out: n_windows x audio_len samples; results identical to the n_windows single calls. */
+int rvc_infer_windows(rvc_ctx* ctx, const float* pcm, size_t n_pcm, size_t n, uint32_t sample_frame_16k_size,
+                      size_t n_windows, int32_t pitch_shift, uint32_t skip_head, uint32_t return_length,
+                      float* out, size_t cap, size_t* audio_len, int32_t max_batch);
+int rvc_infer_windows_dev(rvc_ctx* ctx, const float* pcm_dev, size_t n_pcm, size_t n, uint32_t sample_frame_16k_size,
+                          size_t n_windows, int32_t pitch_shift, uint32_t skip_head, uint32_t return_length,
+                          float* out_dev, size_t cap, size_t* audio_len, int32_t max_batch);
 
 /* MelSpectrogram::mel_extract - rmvpe.rs:159-205. out: (128, T) row-major, T = 1 + n/160. */
 int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap,
@@ -137,6 +158,8 @@ int rvc_sola_crossfade(rvc_ctx* ctx, const float* infer_out, size_t n, float* so
  * "f0_argmax" (i32[T]), "salience" (f32[T*360]), "pitch" (i32[R]), "pitchf" (f32[R]),
  * "phone" (f32[R*C]), "knn_idx" (i32[Q*k]), "knn_d2" (f32[Q*k]), "mel" (f32[T*128], (T,128)). */
 int rvc_get_last(rvc_ctx* ctx, const char* name, void* out, size_t cap_bytes, size_t* out_bytes);
+/* Same for window `window` of the last batched call (rvc_infer_windows / batched rvc_infer_batch). */
+int rvc_get_last_window(rvc_ctx* ctx, int32_t window, const char* name, void* out, size_t cap_bytes, size_t* out_bytes);
 /* Any intermediate buffer by plan name (needs debug_keep=1; testing only). */
 int rvc_debug_tensor(rvc_ctx* ctx, const char* name, float* out, size_t cap, size_t* out_len);
 int rvc_debug_list(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes);

@@ -87,9 +87,12 @@ void cache_store(const std::string& key, const std::shared_ptr<ModelData>& d) {
 struct PlanKey {
     int kind; Geometry g; int with_index; int index_rows; int k;
     int chains = 1;   // persistent chains on (single live stream on the device) or off (several streams share it)
+    int nb = 1, sequential = 0;   // batched plans: windows per launch; consecutive windows of one stream or independent streams
     bool operator<(const PlanKey& o) const {
         if (kind != o.kind) return kind < o.kind;
         if (chains != o.chains) return chains < o.chains;
+        if (nb != o.nb) return nb < o.nb;
+        if (sequential != o.sequential) return sequential < o.sequential;
         if (g < o.g) return true;
         if (o.g < g) return false;
         if (with_index != o.with_index) return with_index < o.with_index;
@@ -101,6 +104,7 @@ struct PlanKey {
 struct PlanEntry {
     Plan plan;
     DevBuf work;
+    DevBuf bstate;   // batched plans: nb state blocks (params | pitch cache | pcm | audio), plan.state_block bytes apart
     std::vector<ChainDev> chains;   // device tables of plan.chains (pointers resolved against this entry's arenas)
     cudaGraphExec_t exec = nullptr;
     cudaGraph_t graph = nullptr;
@@ -110,7 +114,7 @@ struct PlanEntry {
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
         for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); }
-        work.release();
+        work.release(); bstate.release();
     }
 };
 
@@ -120,6 +124,39 @@ __global__ void set_params_kernel(RunParams* p, float uppower, float index_rate,
                                   unsigned long long window, int noise_mode) {
     pdl_enter();
     p->uppower = uppower; p->index_rate = index_rate; p->noise_seed = seed; p->window = window; p->noise_mode = noise_mode;
+}
+
+// Batched plans: one parameter block per window.  Windows of one stream (sequential) count the call counter up;
+// independent streams bring their own seed and counter.
+struct BatchSeeds { unsigned long long seed[64]; unsigned long long window[64]; };
+__global__ void set_params_batch_kernel(uint8_t* state, long long block_bytes, int nb, float uppower, float index_rate, int noise_mode,
+                                        BatchSeeds bs) {
+    pdl_enter();
+    const int w = threadIdx.x;
+    if (w >= nb) return;
+    RunParams* p = reinterpret_cast<RunParams*>(state + w * block_bytes + StateLayout::off_params);
+    p->uppower = uppower; p->index_rate = index_rate; p->noise_seed = bs.seed[w]; p->window = bs.window[w]; p->noise_mode = noise_mode;
+}
+
+// window w of a batched offline call = src[w * hop, w * hop + n) (the reference's streaming geometry: every call sees the
+// last n samples, advanced by hop): copied into the pcm slot of state block w
+__global__ void gather_windows_kernel(const float* __restrict__ src, uint8_t* state, long long block_bytes, long long off_pcm, int n, int hop) {
+    pdl_enter();
+    const int w = blockIdx.y;
+    const float* s = src + (long long)w * hop;
+    float* d = reinterpret_cast<float*>(state + w * block_bytes + off_pcm);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+// pitch caches of nb independent streams <-> the cache slots of the state blocks (dir 0: stream -> block, 1: block -> stream)
+struct CachePtrs { float* p[64]; };
+__global__ void move_caches_kernel(CachePtrs cp, uint8_t* state, long long block_bytes, int dir) {
+    pdl_enter();
+    float* blk = reinterpret_cast<float*>(state + blockIdx.x * block_bytes + StateLayout::off_cache);
+    float* own = cp.p[blockIdx.x];
+    for (int i = threadIdx.x; i < int(StateLayout::CACHE_LEN); i += blockDim.x) {
+        if (dir == 0) blk[i] = own[i]; else own[i] = blk[i];
+    }
 }
 
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
@@ -164,7 +201,12 @@ struct rvc_ctx {
         B.b[SP_CV] = cv.d ? cv.d->dev.d : nullptr; B.b[SP_F0] = f0.d ? f0.d->dev.d : nullptr;
         B.b[SP_SYN] = syn.d ? syn.d->dev.d : nullptr; B.b[SP_IDX] = index.d ? index.d->dev.d : nullptr;
         B.b[SP_WORK] = e.work.d; B.b[SP_STATE] = state.d;
+        if (e.plan.nb > 1) {
+            B.nb = e.plan.nb; B.b[SP_STATE] = e.bstate.d;
+            B.bstride[SP_WORK] = e.plan.work_bytes; B.bstride[SP_STATE] = e.plan.state_block;
+        }
         B.hilo_stride[SP_CV] = cv.d ? cv.d->hilo_stride : 0; B.hilo_stride[SP_SYN] = syn.d ? syn.d->hilo_stride : 0;
+        B.hilo_stride[SP_F0] = f0.d ? f0.d->hilo_stride : 0; B.hilo16_off[SP_F0] = f0.d ? f0.d->hilo16_off : 0; B.hilo16_plane[SP_F0] = f0.d ? f0.d->hilo16_plane : 0;
         B.hilo16_off[SP_CV] = cv.d ? cv.d->hilo16_off : 0; B.hilo16_off[SP_SYN] = syn.d ? syn.d->hilo16_off : 0;
         B.hilo16_plane[SP_CV] = cv.d ? cv.d->hilo16_plane : 0; B.hilo16_plane[SP_SYN] = syn.d ? syn.d->hilo16_plane : 0;
         return B;
@@ -340,9 +382,10 @@ int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
     return RVC_OK;
 }
 
-int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
+int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, int nb = 1, bool sequential = false) {
     PlanKey key{int(kind), g, (ctx->index.loaded && kind == PLAN_INFER) ? 1 : 0, ctx->index_rows, ctx->cfg.index_k};
-    key.chains = (ctx->chain_force || live_contexts(ctx->cfg.device) <= 1) ? 1 : 0;
+    key.chains = (nb <= 1 && (ctx->chain_force || live_contexts(ctx->cfg.device) <= 1)) ? 1 : 0;
+    key.nb = nb > 1 ? nb : 1; key.sequential = (nb > 1 && sequential) ? 1 : 0;
     auto it = ctx->plans.find(key);
     if (it != ctx->plans.end()) { *out = it->second.get(); return RVC_OK; }
     PlanOptions opt;
@@ -351,15 +394,26 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out) {
     opt.allow_umma = ctx->allow_umma;
     opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
     opt.chain_side_max_m = ctx->chain_side_max_m;
+    opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;
+    {   // RVC_F0_UMMA: 0 never, 1 always, default = batched plans only
+        const char* ev = getenv("RVC_F0_UMMA");
+        const bool want = ev ? ev[0] == '1' : key.nb > 1;
+        opt.f0_umma = want && ctx->allow_umma && ctx->f0.loaded && ctx->f0.d->hilo16_off > 0;
+    }
     auto e = std::make_unique<PlanEntry>();
     std::string err;
     if (!build_plan(kind, g, opt, ctx->cv.loaded ? &ctx->cv.d->packed : nullptr, &ctx->cvi, ctx->f0.loaded ? &ctx->f0.d->packed : nullptr,
                     &ctx->f0i, ctx->syn.loaded ? &ctx->syn.d->packed : nullptr, &ctx->syi, e->plan, err))
         return ctx->fail(RVC_ERR_BAD_SHAPE, err);
     if (e->plan.n_lanes > MAX_LANES) return ctx->fail(RVC_ERR_INVALID_ARG, "too many lanes");
-    CK(cudaMalloc(&e->work.d, size_t(e->plan.work_bytes)));
-    e->work.bytes = size_t(e->plan.work_bytes);
+    CK(cudaMalloc(&e->work.d, size_t(e->plan.work_bytes) * size_t(e->plan.nb)));
+    e->work.bytes = size_t(e->plan.work_bytes) * size_t(e->plan.nb);
     CK(cudaMemsetAsync(e->work.d, 0, e->work.bytes, ctx->streams[0]));  // establishes the zero halos once
+    if (e->plan.nb > 1) {
+        CK(cudaMalloc(&e->bstate.d, size_t(e->plan.state_block) * size_t(e->plan.nb)));
+        e->bstate.bytes = size_t(e->plan.state_block) * size_t(e->plan.nb);
+        CK(cudaMemsetAsync(e->bstate.d, 0, e->bstate.bytes, ctx->streams[0]));
+    }
     { int rc = build_chain_tables(ctx, *e); if (rc != RVC_OK) return rc; }
     *out = e.get();
     ctx->plans[key] = std::move(e);
@@ -394,9 +448,8 @@ int run_plan(rvc_ctx* ctx, PlanEntry& e) {
 }
 
 int set_params(rvc_ctx* ctx, int32_t pitch_shift) {
-    float up;
-    if (ctx->cfg.upstream_pitch_shift) up = std::pow(2.0f, float(pitch_shift) / 12.0f);
-    else up = std::ldexp(1.0f, pitch_shift / 12);  // 2.0f32.powi(pitch_shift / 12): i32 division (rvc.rs:121)
+    const float up = ctx->cfg.upstream_pitch_shift ? std::pow(2.0f, float(pitch_shift) / 12.0f)
+                                                   : std::ldexp(1.0f, pitch_shift / 12);  // 2.0f32.powi(pitch_shift / 12): i32 division (rvc.rs:121)
     launch_k(set_params_kernel, dim3(1), dim3(1), size_t(0), ctx->streams[0],
              reinterpret_cast<RunParams*>(ctx->state.d + StateLayout::off_params), up, ctx->index_rate,
              (unsigned long long)ctx->cfg.noise_seed, (unsigned long long)ctx->window, ctx->cfg.noise_mode);
@@ -436,16 +489,156 @@ int enqueue_infer(rvc_ctx* ctx, const float* pcm, size_t n, bool pcm_on_device, 
     return RVC_OK;
 }
 
-int copy_named(rvc_ctx* ctx, const PlanEntry& e, const std::string& name, void* out, size_t cap_bytes, size_t* out_bytes) {
+constexpr int MAX_BATCH = 32;   // windows per launch of a batched plan (BASELINE configs[2]: 32)
+
+float uppower_of(const rvc_ctx* ctx, int32_t pitch_shift) {
+    if (ctx->cfg.upstream_pitch_shift) return std::pow(2.0f, float(pitch_shift) / 12.0f);
+    return std::ldexp(1.0f, pitch_shift / 12);  // 2.0f32.powi(pitch_shift / 12): i32 division (rvc.rs:121)
+}
+
+int check_infer_ready(rvc_ctx* ctx) {
+    if (!ctx->syn.loaded) return ctx->fail(RVC_ERR_MODEL_NOT_LOADED, "ModelNotLoaded");          // rvc.rs:141
+    if (!ctx->cv.loaded) return ctx->fail(RVC_ERR_CONTENTVEC_NOT_LOADED, "ContentvecNotLoaded");  // rvc.rs:85
+    if (!ctx->f0.loaded) return ctx->fail(RVC_ERR_F0_NOT_LOADED, "F0NotLoaded");
+    return RVC_OK;
+}
+
+// `nb` consecutive windows of THIS stream through one execution of a batched plan: window w is pcm[w * sf16k, w * sf16k + n)
+// (what nb successive rvc_infer calls of the reference's streaming loop would see, obs-rvc/src/lib.rs:659-707); the pitch
+// cache is updated window by window inside the plan, the call counter advances by nb.  Weights are read once per nb windows.
+int enqueue_windows(rvc_ctx* ctx, const float* pcm, bool on_device, size_t n, uint32_t sf16k, int nb, int32_t shift, uint32_t skip_head,
+                    uint32_t return_length, float* out, size_t* audio_len) {
+    Geometry g{int32_t(n), int32_t(sf16k), int32_t(skip_head), int32_t(return_length)};
+    PlanEntry* e = nullptr;
+    int rc = get_plan(ctx, PLAN_INFER, g, &e, nb, true);
+    if (rc != RVC_OK) return rc;
+    cudaStream_t s = ctx->streams[0];
+    const size_t span = n + size_t(nb - 1) * sf16k;
+    const float* src = pcm;
+    if (!on_device) {
+        if (span > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "window span exceeds the staging buffer");
+        CK(cudaMemcpyAsync(state_pcm(ctx), pcm, span * sizeof(float), cudaMemcpyHostToDevice, s));
+        src = state_pcm(ctx);
+    }
+    uint8_t* blocks = e->bstate.d;
+    const long long blk = e->plan.state_block;
+    launch_k(gather_windows_kernel, dim3(8, unsigned(nb)), dim3(256), size_t(0), s, src, blocks, blk, (long long)e->plan.pcm.off, int(n), int(sf16k));
+    CK(cudaMemcpyAsync(blocks + StateLayout::off_cache, ctx->state.d + StateLayout::off_cache, StateLayout::CACHE_LEN * 4, cudaMemcpyDeviceToDevice, s));
+    BatchSeeds bs{};
+    for (int w = 0; w < nb; ++w) { bs.seed[w] = ctx->cfg.noise_seed; bs.window[w] = ctx->window + uint64_t(w); }
+    launch_k(set_params_batch_kernel, dim3(1), dim3(64), size_t(0), s, blocks, blk, nb, uppower_of(ctx, shift), ctx->index_rate, ctx->cfg.noise_mode, bs);
+    ctx->total_launches += 2;
+    rc = run_plan(ctx, *e);
+    if (rc != RVC_OK) return rc;
+    ctx->window += uint64_t(nb);
+    CK(cudaMemcpyAsync(ctx->state.d + StateLayout::off_cache, blocks + StateLayout::off_cache, StateLayout::CACHE_LEN * 4, cudaMemcpyDeviceToDevice, s));
+    const size_t al = size_t(e->plan.audio_len);
+    CK(cudaMemcpy2DAsync(out, al * 4, blocks + e->plan.audio.off, size_t(blk), al * 4, size_t(nb),
+                         on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    if (audio_len) *audio_len = al;
+    return RVC_OK;
+}
+
+// whole-buffer driver of enqueue_windows: n_windows windows in groups of up to MAX_BATCH
+int infer_windows(rvc_ctx* ctx, const float* pcm, bool on_device, size_t n_pcm, size_t n, uint32_t sf16k, size_t n_windows, int32_t shift,
+                  uint32_t skip_head, uint32_t return_length, float* out, size_t cap, size_t* audio_len, int max_batch) {
+    int rc = check_infer_ready(ctx); if (rc) return rc;
+    if (!pcm || !out || n == 0 || n_windows == 0 || sf16k == 0) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    if (n + (n_windows - 1) * size_t(sf16k) > n_pcm) return ctx->fail(RVC_ERR_BAD_SHAPE, "pcm shorter than n + (n_windows - 1) * sf16k");
+    if (max_batch <= 0 || max_batch > MAX_BATCH) max_batch = MAX_BATCH;
+    size_t al = 0, done = 0;
+    while (done < n_windows) {
+        const int nb = int(std::min<size_t>(size_t(max_batch), n_windows - done));
+        if (nb == 1) {
+            if (al == 0) {   // geometry check + output length before anything is written
+                PlanEntry* e1 = nullptr;
+                rc = get_plan(ctx, PLAN_INFER, Geometry{int32_t(n), int32_t(sf16k), int32_t(skip_head), int32_t(return_length)}, &e1); if (rc) return rc;
+                al = size_t(e1->plan.audio_len);
+            }
+            if ((done + 1) * al > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+            size_t ol = 0;
+            rc = enqueue_infer(ctx, pcm + done * sf16k, n, on_device, sf16k, shift, skip_head, return_length, out + done * al, on_device, al, &ol);
+            if (rc) return rc;
+        } else {
+            if (al == 0) {
+                PlanEntry* eb = nullptr;
+                rc = get_plan(ctx, PLAN_INFER, Geometry{int32_t(n), int32_t(sf16k), int32_t(skip_head), int32_t(return_length)}, &eb, nb, true); if (rc) return rc;
+                al = size_t(eb->plan.audio_len);
+            }
+            if ((done + size_t(nb)) * al > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+            rc = enqueue_windows(ctx, pcm + done * sf16k, on_device, n, sf16k, nb, shift, skip_head, return_length, out + done * al, nullptr);
+            if (rc) return rc;
+        }
+        done += size_t(nb);
+    }
+    if (audio_len) *audio_len = al;
+    return RVC_OK;
+}
+
+// several live streams of one GPU through ONE batched plan (BASELINE configs[3]: 8 per GPU): possible when the contexts
+// sit on the same device and share every model (weights are shared by path, engine.cu cache_lookup) and the settings
+// that shape the plan.  Stream state (pitch cache, call counter, noise seed) stays per context.
+bool batchable(rvc_ctx* const* ctxs, size_t n_ctx) {
+    if (n_ctx < 2 || n_ctx > size_t(MAX_BATCH)) return false;
+    const rvc_ctx* a = ctxs[0];
+    for (size_t i = 0; i < n_ctx; ++i) {
+        const rvc_ctx* c = ctxs[i];
+        if (!c || !c->syn.loaded || !c->cv.loaded || !c->f0.loaded) return false;
+        for (size_t j = 0; j < i; ++j) if (ctxs[j] == c) return false;
+        if (c->cfg.device != a->cfg.device || c->cv.d != a->cv.d || c->f0.d != a->f0.d || c->syn.d != a->syn.d || c->index.d != a->index.d ||
+            c->index_rate != a->index_rate || c->cfg.index_k != a->cfg.index_k || c->cfg.noise_mode != a->cfg.noise_mode ||
+            c->cfg.upstream_cents_window != a->cfg.upstream_cents_window || c->cfg.upstream_pitch_shift != a->cfg.upstream_pitch_shift)
+            return false;
+    }
+    return true;
+}
+
+int enqueue_streams(rvc_ctx* const* ctxs, int nb, const float* const* pcm, bool on_device, size_t n, uint32_t sf16k, int32_t shift,
+                    uint32_t skip_head, uint32_t return_length, float* const* out, size_t cap, size_t* out_len) {
+    rvc_ctx* ctx = ctxs[0];
+    if (n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    for (int w = 0; w < nb; ++w) if (!pcm[w] || !out[w]) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
+    Geometry g{int32_t(n), int32_t(sf16k), int32_t(skip_head), int32_t(return_length)};
+    PlanEntry* e = nullptr;
+    int rc = get_plan(ctx, PLAN_INFER, g, &e, nb, false);
+    if (rc != RVC_OK) return rc;
+    const size_t al = size_t(e->plan.audio_len);
+    if (al > cap) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    for (int w = 1; w < nb; ++w) CK(cudaStreamSynchronize(ctxs[w]->streams[0]));   // their own pending work touches their caches
+    uint8_t* blocks = e->bstate.d;
+    const long long blk = e->plan.state_block;
+    CachePtrs cp{}; BatchSeeds bs{};
+    for (int w = 0; w < nb; ++w) {
+        cp.p[w] = reinterpret_cast<float*>(ctxs[w]->state.d + StateLayout::off_cache);
+        bs.seed[w] = ctxs[w]->cfg.noise_seed; bs.window[w] = ctxs[w]->window;
+        CK(cudaMemcpyAsync(blocks + w * blk + e->plan.pcm.off, pcm[w], n * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    }
+    launch_k(move_caches_kernel, dim3(unsigned(nb)), dim3(256), size_t(0), s, cp, blocks, blk, 0);
+    launch_k(set_params_batch_kernel, dim3(1), dim3(64), size_t(0), s, blocks, blk, nb, uppower_of(ctx, shift), ctx->index_rate, ctx->cfg.noise_mode, bs);
+    rc = run_plan(ctx, *e);
+    if (rc != RVC_OK) return rc;
+    launch_k(move_caches_kernel, dim3(unsigned(nb)), dim3(256), size_t(0), s, cp, blocks, blk, 1);
+    ctx->total_launches += 3;
+    for (int w = 0; w < nb; ++w) {
+        ctxs[w]->window++;
+        CK(cudaMemcpyAsync(out[w], blocks + w * blk + e->plan.audio.off, al * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+    }
+    if (out_len) *out_len = al;
+    return RVC_OK;
+}
+
+int copy_named(rvc_ctx* ctx, const PlanEntry& e, const std::string& name, void* out, size_t cap_bytes, size_t* out_bytes, int window = 0) {
     const NamedBuf* nb = e.plan.find(name);
     if (!nb) return ctx->fail(RVC_ERR_INVALID_ARG, "no such buffer: " + name);
+    if (window < 0 || window >= e.plan.nb) return ctx->fail(RVC_ERR_INVALID_ARG, "no such window in the last call");
     size_t bytes = size_t(nb->elems) * 4;
     if (out_bytes) *out_bytes = bytes;
     if (!out) return RVC_OK;
     if (bytes > cap_bytes) return ctx->fail(RVC_ERR_INVALID_ARG, "buffer too small for " + name);
     ctx->sync_all();
     const DeviceBases B = ctx->bases(e);
-    CK(cudaMemcpy(out, B.b[nb->ref.space] + nb->ref.off, bytes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, B.b[nb->ref.space] + nb->ref.off + int64_t(window) * B.bstride[nb->ref.space], bytes, cudaMemcpyDeviceToHost));
     return RVC_OK;
 }
 
@@ -557,14 +750,14 @@ int rvc_load_f0(rvc_ctx* ctx, int32_t pitch_algorithm) {
     int rc = enter(ctx); if (rc) return rc;
     (void)pitch_algorithm;  // enums.rs:106-113: every value maps to Rmvpe
     std::string path = ctx->data_path + "/f0/rmvpe.rvcw";
-    const std::string key = model_key(ctx->cfg.device, path, false);
+    const std::string key = model_key(ctx->cfg.device, path, ctx->allow_umma);
     std::shared_ptr<ModelData> d = cache_lookup(key);
     if (!d) {
         RvcwFile f; std::string err;
         if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
         d = std::make_shared<ModelData>();
         if (!pack_rmvpe(f, d->packed, d->f0i, err)) return ctx->fail(RVC_ERR_IO, err);
-        rc = upload(ctx, *d, false); if (rc) return rc;
+        rc = upload(ctx, *d, ctx->allow_umma); if (rc) return rc;   // weight planes: batched plans run the wide U-Net levels on the tcgen05 kernel
         cache_store(key, d);
     }
     ctx->drop_plans(); ctx->f0.unload();
@@ -597,6 +790,10 @@ int rvc_unload_model(rvc_ctx* ctx) {
 }
 
 static int attach_index(rvc_ctx* ctx, const std::shared_ptr<ModelData>& d, float index_rate) {
+    // the index may be loaded before the ContentVec: the width is checked again when an infer plan is built
+    if (ctx->cv.loaded && d->cols != ctx->cvi.out_dim)
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "retrieval index is " + std::to_string(d->cols) + " wide, the loaded ContentVec produces " +
+                                                std::to_string(ctx->cvi.out_dim) + "-wide features");
     ctx->drop_plans(); ctx->index.unload();
     ctx->index.d = d; ctx->index.loaded = true; ctx->index_rows = d->rows; ctx->index_c = d->cols; ctx->index_rate = index_rate;
     return RVC_OK;
@@ -666,6 +863,14 @@ int rvc_infer_dev(rvc_ctx* ctx, const float* pcm_dev, size_t n, uint32_t sf16k, 
 int rvc_infer_batch(rvc_ctx* const* ctxs, size_t n_ctx, const float* const* pcm, size_t n, uint32_t sf16k, int32_t pitch_shift,
                     uint32_t skip_head, uint32_t return_length, float* const* out, size_t cap, size_t* out_len) {
     if (!ctxs || !pcm || !out) return RVC_ERR_INVALID_ARG;
+    if (batchable(ctxs, n_ctx)) {   // one batched plan for all streams (weights read once per round of windows)
+        rvc_ctx* ctx = ctxs[0];
+        int rc = enter(ctx); if (rc) return rc;
+        rc = enqueue_streams(ctxs, int(n_ctx), pcm, false, n, sf16k, pitch_shift, skip_head, return_length, out, cap, out_len);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->streams[0]));
+        return RVC_OK;
+    }
     for (size_t i = 0; i < n_ctx; ++i) {
         int rc = enter(ctxs[i]); if (rc) return rc;
         rc = enqueue_infer(ctxs[i], pcm[i], n, false, sf16k, pitch_shift, skip_head, return_length, out[i], false, cap, out_len);
@@ -677,6 +882,30 @@ int rvc_infer_batch(rvc_ctx* const* ctxs, size_t n_ctx, const float* const* pcm,
         CK(cudaStreamSynchronize(ctx->streams[0]));
     }
     return RVC_OK;
+}
+
+int rvc_infer_batch_dev(rvc_ctx* const* ctxs, size_t n_ctx, const float* const* pcm_dev, size_t n, uint32_t sf16k, int32_t pitch_shift,
+                        uint32_t skip_head, uint32_t return_length, float* const* out_dev, size_t cap, size_t* out_len) {
+    if (!ctxs || !pcm_dev || !out_dev || n_ctx == 0 || !ctxs[0]) return RVC_ERR_INVALID_ARG;
+    rvc_ctx* ctx = ctxs[0];
+    int rc = enter(ctx); if (rc) return rc;
+    if (!batchable(ctxs, n_ctx)) return ctx->fail(RVC_ERR_INVALID_ARG, "streams cannot share one batched plan (different device / models / settings)");
+    return enqueue_streams(ctxs, int(n_ctx), pcm_dev, true, n, sf16k, pitch_shift, skip_head, return_length, out_dev, cap, out_len);
+}
+
+int rvc_infer_windows(rvc_ctx* ctx, const float* pcm, size_t n_pcm, size_t n, uint32_t sf16k, size_t n_windows, int32_t pitch_shift,
+                      uint32_t skip_head, uint32_t return_length, float* out, size_t cap, size_t* audio_len, int32_t max_batch) {
+    int rc = enter(ctx); if (rc) return rc;
+    rc = infer_windows(ctx, pcm, false, n_pcm, n, sf16k, n_windows, pitch_shift, skip_head, return_length, out, cap, audio_len, max_batch);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    return RVC_OK;
+}
+
+int rvc_infer_windows_dev(rvc_ctx* ctx, const float* pcm_dev, size_t n_pcm, size_t n, uint32_t sf16k, size_t n_windows, int32_t pitch_shift,
+                          uint32_t skip_head, uint32_t return_length, float* out_dev, size_t cap, size_t* audio_len, int32_t max_batch) {
+    int rc = enter(ctx); if (rc) return rc;
+    return infer_windows(ctx, pcm_dev, true, n_pcm, n, sf16k, n_windows, pitch_shift, skip_head, return_length, out_dev, cap, audio_len, max_batch);
 }
 
 int rvc_hubert(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap, size_t* out_c, size_t* out_t) {
@@ -785,6 +1014,16 @@ int rvc_get_last(rvc_ctx* ctx, const char* name, void* out, size_t cap_bytes, si
     return copy_named(ctx, *ctx->last, nm, out, cap_bytes, out_bytes);
 }
 
+int rvc_get_last_window(rvc_ctx* ctx, int32_t window, const char* name, void* out, size_t cap_bytes, size_t* out_bytes) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!name) return ctx->fail(RVC_ERR_INVALID_ARG, "null name");
+    if (!ctx->last) return ctx->fail(RVC_ERR_INVALID_ARG, "nothing has run yet");
+    std::string nm(name);
+    if (nm == "salience") nm = "rm.salience";
+    if (nm == "hubert") nm = "cv.out";
+    return copy_named(ctx, *ctx->last, nm, out, cap_bytes, out_bytes, window);
+}
+
 int rvc_debug_tensor(rvc_ctx* ctx, const char* name, float* out, size_t cap, size_t* out_len) {
     size_t bytes = 0;
     int rc = rvc_get_last(ctx, name, out, cap * 4, &bytes);
@@ -830,9 +1069,9 @@ int rvc_plan_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) 
     char buf[512];
     int n = std::snprintf(buf, sizeof(buf),
                           "{\"ops\": %zu, \"kernels_per_run\": %d, \"lanes\": %d, \"work_bytes\": %lld, \"hubert_T\": %d, \"hubert_C\": %d, "
-                          "\"f0_T\": %d, \"audio_len\": %d, \"knn_q\": %d, \"graph\": %d}",
+                          "\"f0_T\": %d, \"audio_len\": %d, \"knn_q\": %d, \"graph\": %d, \"windows\": %d, \"chains\": %zu}",
                           p.ops.size(), ctx->last->launches, p.n_lanes, (long long)p.work_bytes, p.hubert_T, p.hubert_C, p.f0_T,
-                          p.audio_len, p.knn_q, ctx->last->exec ? 1 : 0);
+                          p.audio_len, p.knn_q, ctx->last->exec ? 1 : 0, p.nb, p.chains.size());
     if (out_bytes) *out_bytes = size_t(n);
     if (out && cap_bytes > 0) { size_t m = size_t(n) < cap_bytes - 1 ? size_t(n) : cap_bytes - 1; std::memcpy(out, buf, m); out[m] = 0; }
     return RVC_OK;

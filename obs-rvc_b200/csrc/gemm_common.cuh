@@ -20,7 +20,28 @@ struct GemmParams {
     int vec_store;
     // split-K (v2 kernel): partial tiles in scratch[z][M][N] per batch, one counter per output tile
     float* scratch; unsigned int* counters; int splitk, kt_per_split;
+    // batched plans: the grid's batch index runs over windows x groups; `batch` = groups per window (the op's own
+    // batch count, e.g. the 16 groups of ContentVec's pos-conv), w* = per-window element strides (0 for weights)
+    int batch;
+    long long wA, wC, wC2, wR, wScratch, wCounters;
 };
+
+// batch index -> (window, group) and the operand bases of that pair
+struct GemmBases { const float* A; const float* W; const float* bias; float* C; float* C2; const float* R; float* scratch; unsigned int* counters; int grp; };
+__device__ __forceinline__ GemmBases gemm_bases(const GemmParams& p, int bz) {
+    const int win = bz / p.batch, grp = bz - win * p.batch;
+    GemmBases b;
+    b.A = p.A + grp * p.sA + win * p.wA;
+    b.W = p.W + grp * p.sW;
+    b.bias = p.bias ? p.bias + grp * p.sBias : nullptr;
+    b.C = p.C + grp * p.sC + win * p.wC;
+    b.C2 = p.C2 ? p.C2 + grp * p.sC + win * p.wC2 : nullptr;
+    b.R = p.R ? p.R + grp * p.sR + win * p.wR : nullptr;
+    b.scratch = p.scratch ? p.scratch + win * p.wScratch : nullptr;
+    b.counters = p.counters ? p.counters + win * p.wCounters : nullptr;
+    b.grp = grp;
+    return b;
+}
 
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -86,6 +107,8 @@ inline GemmParams make_params(const GemmOp& g, const DeviceBases& B) {
     p.out_mode = g.out_mode; p.om_a = g.om_a; p.om_b = g.om_b; p.om_c = g.om_c; p.om_d = g.om_d;
     p.vec_store = 0;
     p.scratch = B.p<float>(g.scratch); p.counters = B.p<unsigned int>(g.counters); p.splitk = g.splitk; p.kt_per_split = 0;
+    p.batch = g.batch;
+    p.wA = B.ws(g.A); p.wC = B.ws(g.C); p.wC2 = B.ws(g.C2); p.wR = B.ws(g.R); p.wScratch = B.ws(g.scratch); p.wCounters = B.ws(g.counters);
     return p;
 }
 

@@ -16,7 +16,7 @@ namespace rvc {
 
 struct GemmSched {
     int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM32/BN32 (v2);
-                      // 5/6/7/8: tcgen05 kernel (kernels_umma.cu) with BN = 128/64/32/256
+                      // 5/6/7/8/9: tcgen05 kernel (kernels_umma.cu) with BN = 128/64/32/256/16
     int bm = 0, bn = 0, splitk = 1, tiles = 0;
 };
 
@@ -28,7 +28,10 @@ inline int sched_env(const char* name, int dflt) {
     return (e && *e) ? std::atoi(e) : dflt;
 }
 
-inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
+// nb = windows per launch (batched plans): the grid is nb x larger.  Batched plans also put RMVPE's wide levels and the
+// small-M ops (enc_p / flow, 21 rows per window) on the tensor-core kernel: with nb windows per launch they are
+// throughput- not latency-bound, and the 2-term FP16 split is fp32-grade (argmax / pitch parity is asserted by the tests).
+inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma, int nb = 1, bool f0_umma = false) {
     GemmSched s;
     static const int kWant = sched_env("RVC_UMMA_WANT", 96), kBn128 = sched_env("RVC_UMMA_BN128_MIN", 1),
                      kKbMin = sched_env("RVC_UMMA_KB_MIN", 4);
@@ -38,7 +41,8 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     // tensor-core path: dense contractions of ContentVec / synthesizer with at least half a 128-row tile;
     // RMVPE (SP_F0) stays on exact-fp32 CUDA cores (its 360-bin argmax is a bit-exact parity item)
     const bool contiguous = g.seg_len >= g.K;
-    if (allow_umma && (g.W.space == SP_CV || g.W.space == SP_SYN) && g.M >= 64 && g.N % 16 == 0 && g.N >= 32 &&
+    const int min_m = nb > 1 ? 16 : 64;
+    if (allow_umma && (g.W.space == SP_CV || g.W.space == SP_SYN || (f0_umma && g.W.space == SP_F0)) && g.M >= min_m && g.N % 16 == 0 && g.N >= 16 &&
         (contiguous || (g.seg_len % 32 == 0 && g.K % g.seg_len == 0) ||
          (sched_env("RVC_UMMA_F16", 1) != 0 && g.seg_len % 8 == 0 && g.K % g.seg_len == 0)) && g.K >= 96) {
         // (segments that are only a multiple of 8 long - ContentVec's grouped pos-conv, 48 channels per group - need the
@@ -47,21 +51,22 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
         const int nkb = (g.K + 31) / 32;
         // one CTA per SM (smem-limited) and clusters must pack into GPCs: aim for a single wave of
         // <= ~112 CTAs; prefer 128-wide tiles (less operand traffic per flop) when that still fills it
-        const int tiles128 = tm * ((g.N + 127) / 128) * g.batch;
+        const int tiles128 = tm * ((g.N + 127) / 128) * g.batch * nb;
         const int bn128_min = g.cta_budget > 0 ? std::max(1, kBn128 * g.cta_budget / kWant) : kBn128;
         int bn = 128;
-        if (g.N <= 32) bn = 32;
+        if (g.N <= 16) bn = 16;
+        else if (g.N <= 32) bn = 32;
         else if (g.N <= 64 || tiles128 < bn128_min) bn = 64;
         // 256-wide tiles (FP16-split kernel only): one tcgen05.mma costs ~175 cycles of latency on the accumulator chain
         // whatever its N <= 256, so for wide outputs a quarter of the instructions per unit of work - taken when the
         // tile grid x the deepest split-K still gives ~half a wave of CTAs
         static const bool kF16 = sched_env("RVC_UMMA_F16", 1) != 0, k256 = sched_env("RVC_UMMA_BN256", 0) != 0;   // measured: no gain over 128-wide tiles (2.93 vs 2.90 ms/window), off
-        const int tiles256 = tm * ((g.N + 255) / 256) * g.batch;
+        const int tiles256 = tm * ((g.N + 255) / 256) * g.batch * nb;
         if (kF16 && k256 && g.N >= 512 && tiles256 * std::min(8, std::max(1, nkb / kKbMin)) >= 48) bn = 256;
-        s.variant = bn == 256 ? 8 : (bn == 128 ? 5 : (bn == 64 ? 6 : 7));
+        s.variant = bn == 256 ? 8 : (bn == 128 ? 5 : (bn == 64 ? 6 : (bn == 32 ? 7 : 9)));
         s.bm = 128; s.bn = bn;
         s.tiles = tm * ((g.N + bn - 1) / bn) * g.batch;
-        const int want = std::max(1, (g.cta_budget > 0 ? g.cta_budget : kWant) / s.tiles);
+        const int want = std::max(1, (g.cta_budget > 0 ? g.cta_budget : kWant) / (s.tiles * nb));
         const int maxsplit = std::max(1, nkb / kKbMin);
         // split-K group = one thread-block cluster (partials reduced over DSMEM): power of two <= 8
         s.splitk = 1;
@@ -80,7 +85,7 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma) {
     const int tm = (g.M + s.bm - 1) / s.bm, tn = (g.N + s.bn - 1) / s.bn;
     s.tiles = tm * tn * g.batch;
     const int nkt = (g.K + GEMM2_BK - 1) / GEMM2_BK;
-    int want = (2 * NUM_SMS + s.tiles - 1) / s.tiles;          // ~2 CTAs per SM in total
+    int want = (2 * NUM_SMS + s.tiles * nb - 1) / (s.tiles * nb);   // ~2 CTAs per SM in total
     int maxsplit = std::max(1, nkt / 4);                        // at least 4 k-tiles per split
     // every extra split costs a partial-tile round trip through L2 in the last CTA: keep the group small
     s.splitk = std::max(1, std::min(std::min(want, maxsplit), 8));

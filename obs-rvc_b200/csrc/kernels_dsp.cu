@@ -21,8 +21,11 @@ __global__ void __launch_bounds__(256)
 stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restrict__ window,
                     const int* __restrict__ band_start, const int* __restrict__ band_count,
                     const int* __restrict__ band_off, const float* __restrict__ band_w, float* __restrict__ mel,
-                    float* __restrict__ out2, long long out2_pitch, float scale, float shift, float clamp) {
+                    float* __restrict__ out2, long long out2_pitch, float scale, float shift, float clamp,
+                    long long wPcm, long long wMel, long long wOut2) {
     pdl_enter();
+    pcm += blockIdx.z * wPcm; mel += blockIdx.z * wMel;
+    if (out2) out2 += blockIdx.z * wOut2;
     __shared__ float2 buf[1024];
     __shared__ float2 tw[512];
     __shared__ float mag[513];
@@ -71,8 +74,11 @@ stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restric
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 f0_decode_kernel(const float* __restrict__ sal, float* __restrict__ f0, int* __restrict__ argmax,
-                 const RunParams* __restrict__ rp, int bins, float threshold, int upstream_window) {
+                 const RunParams* __restrict__ rp, int bins, float threshold, int upstream_window,
+                 long long wSal, long long wF0, long long wArg, long long wRp) {
     pdl_enter();
+    sal += blockIdx.z * wSal; f0 += blockIdx.z * wF0; argmax += blockIdx.z * wArg;
+    rp = reinterpret_cast<const RunParams*>(reinterpret_cast<const float*>(rp) + blockIdx.z * wRp);
     const int t = blockIdx.x, tid = threadIdx.x;
     const float* s = sal + (long long)t * bins;
     float bv = -FLT_MAX; int bi = 0x7fffffff;
@@ -114,25 +120,37 @@ f0_decode_kernel(const float* __restrict__ sal, float* __restrict__ f0, int* __r
 __global__ void __launch_bounds__(1024)
 f0_post_kernel(const float* __restrict__ f0, float* __restrict__ cache, int* __restrict__ pitch,
                float* __restrict__ pitchf, int pitch_len, int shift, int hubert_length, int skip_head,
-               int return_length, int n, float mel_min, float mel_max) {
+               int return_length, int n, float mel_min, float mel_max,
+               int seq_windows, long long wF0, long long wCache, long long wPitch, long long wPitchf) {
     pdl_enter();
+    // Batched plans: independent streams (grid.z = windows, one cache each) or `seq_windows` consecutive windows of
+    // ONE stream (grid.z = 1): they update the single cache of window 0 one after the other, as the reference would.
+    cache += blockIdx.z * wCache;
     const int i = threadIdx.x;
-    float keep = 0.f;
-    if (i + shift < n) keep = cache[i + shift];
-    __syncthreads();
-    if (i + shift < n) cache[i] = keep;  // copy_within(shift.., 0); the tail keeps its old values
-    __syncthreads();
-    const int start = n + 4 - pitch_len;
-    if (i >= 3 && i < pitch_len - 1) cache[start + i - 3] = f0[i];
-    __syncthreads();
-    const int a = n - hubert_length + skip_head;
-    for (int r = i; r < return_length; r += blockDim.x) {
-        const float f = cache[a + r];
-        float m = logf(f / 700.0f + 1.0f) * 1127.0f;
-        if (!(m <= 0.f)) m = __fadd_rn(__fdiv_rn(__fmul_rn(m - mel_min, 254.0f), mel_max - mel_min), 1.0f);
-        m = fminf(fmaxf(m, 1.0f), 255.0f);
-        pitch[r] = int(floor(double(m) + 0.5));  // Rust round(): half away from zero
-        pitchf[r] = f;
+    const int w0 = seq_windows > 0 ? 0 : blockIdx.z, w1 = seq_windows > 0 ? seq_windows : blockIdx.z + 1;
+    for (int w = w0; w < w1; ++w) {
+        const float* f0w = f0 + w * wF0;
+        int* pitchw = pitch + w * wPitch;
+        float* pitchfw = pitchf + w * wPitchf;
+        float keep = 0.f;
+        if (i + shift < n) keep = cache[i + shift];
+        __syncthreads();
+        if (i + shift < n) cache[i] = keep;  // copy_within(shift.., 0); the tail keeps its old values
+        __syncthreads();
+        const int start = n + 4 - pitch_len;
+        for (int j = i; j < pitch_len - 1; j += blockDim.x)
+            if (j >= 3) cache[start + j - 3] = f0w[j];
+        __syncthreads();
+        const int a = n - hubert_length + skip_head;
+        for (int r = i; r < return_length; r += blockDim.x) {
+            const float f = cache[a + r];
+            float m = logf(f / 700.0f + 1.0f) * 1127.0f;
+            if (!(m <= 0.f)) m = __fadd_rn(__fdiv_rn(__fmul_rn(m - mel_min, 254.0f), mel_max - mel_min), 1.0f);
+            m = fminf(fmaxf(m, 1.0f), 255.0f);
+            pitchw[r] = int(floor(double(m) + 0.5));  // Rust round(): half away from zero
+            pitchfw[r] = f;
+        }
+        __syncthreads();
     }
 }
 
@@ -143,8 +161,12 @@ f0_post_kernel(const float* __restrict__ f0, float* __restrict__ cache, int* __r
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 sinegen_kernel(const float* __restrict__ f0, float* __restrict__ out, float* __restrict__ dbg,
-               const RunParams* __restrict__ rp, int T, int upp, float sr, float lin_w, float lin_b) {
+               const RunParams* __restrict__ rp, int T, int upp, float sr, float lin_w, float lin_b,
+               long long wF0, long long wOut, long long wDbg, long long wRp) {
     pdl_enter();
+    f0 += blockIdx.z * wF0; out += blockIdx.z * wOut;
+    if (dbg) dbg += blockIdx.z * wDbg;
+    rp = reinterpret_cast<const RunParams*>(reinterpret_cast<const float*>(rp) + blockIdx.z * wRp);
     extern __shared__ __align__(16) unsigned char smraw[];
     double* part = reinterpret_cast<double*>(smraw);        // [1024] chunk sums -> exclusive offsets
     float* rad = reinterpret_cast<float*>(part + 1024);     // [T]
@@ -213,28 +235,30 @@ sinegen_kernel(const float* __restrict__ f0, float* __restrict__ out, float* __r
 }  // namespace
 
 int launch_stftmel(const StftMelOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(stft_mel_log_kernel, dim3(o.T), dim3(256), size_t(0), s, B.p<float>(o.pcm), o.L, B.p<float>(o.window), B.p<int>(o.band_start),
+    launch_k(stft_mel_log_kernel, dim3(o.T, 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.pcm), o.L, B.p<float>(o.window), B.p<int>(o.band_start),
                                             B.p<int>(o.band_count), B.p<int>(o.band_off), B.p<float>(o.band_w), B.p<float>(o.mel),
-                                            B.p<float>(o.out2), o.out2_pitch, o.scale, o.shift, o.clamp);
+                                            B.p<float>(o.out2), o.out2_pitch, o.scale, o.shift, o.clamp, B.ws(o.pcm), B.ws(o.mel), B.ws(o.out2));
     return 1;
 }
 
 int launch_f0decode(const F0DecodeOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(f0_decode_kernel, dim3(o.T), dim3(128), size_t(0), s, B.p<float>(o.salience), B.p<float>(o.f0), B.p<int>(o.argmax), B.p<RunParams>(o.params),
-                                         o.bins, o.threshold, o.upstream_window);
+    launch_k(f0_decode_kernel, dim3(o.T, 1, B.nb), dim3(128), size_t(0), s, B.p<float>(o.salience), B.p<float>(o.f0), B.p<int>(o.argmax), B.p<RunParams>(o.params),
+                                         o.bins, o.threshold, o.upstream_window, B.ws(o.salience), B.ws(o.f0), B.ws(o.argmax), B.ws(o.params));
     return 1;
 }
 
 int launch_f0post(const F0PostOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(f0_post_kernel, dim3(1), dim3(1024), size_t(0), s, B.p<float>(o.f0), B.p<float>(o.cache), B.p<int>(o.pitch), B.p<float>(o.pitchf), o.pitch_len,
-                                      o.shift, o.hubert_length, o.skip_head, o.return_length, o.cache_len, o.mel_min, o.mel_max);
+    const bool seq = o.sequential != 0 && B.nb > 1;
+    launch_k(f0_post_kernel, dim3(1, 1, seq ? 1 : B.nb), dim3(1024), size_t(0), s, B.p<float>(o.f0), B.p<float>(o.cache), B.p<int>(o.pitch), B.p<float>(o.pitchf), o.pitch_len,
+                                      o.shift, o.hubert_length, o.skip_head, o.return_length, o.cache_len, o.mel_min, o.mel_max,
+                                      seq ? B.nb : 0, B.ws(o.f0), B.ws(o.cache), B.ws(o.pitch), B.ws(o.pitchf));
     return 1;
 }
 
 int launch_sinegen(const SineGenOp& o, const DeviceBases& B, cudaStream_t s) {
     size_t smem = sizeof(double) * 1024 + sizeof(float) * 2 * o.R;
-    launch_k(sinegen_kernel, dim3(1), dim3(1024), size_t(smem), s, B.p<float>(o.pitchf), B.p<float>(o.out), B.p<float>(o.sine_dbg), B.p<RunParams>(o.params),
-                                         o.R, o.upp, o.sr, o.lin_w, o.lin_b);
+    launch_k(sinegen_kernel, dim3(1, 1, B.nb), dim3(1024), size_t(smem), s, B.p<float>(o.pitchf), B.p<float>(o.out), B.p<float>(o.sine_dbg), B.p<RunParams>(o.params),
+                                         o.R, o.upp, o.sr, o.lin_w, o.lin_b, B.ws(o.pitchf), B.ws(o.out), B.ws(o.sine_dbg), B.ws(o.params));
     return 1;
 }
 

@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int bz = blockIdx.z;
-    const float* __restrict__ A = p.A + bz * p.sA;
-    const float* __restrict__ W = p.W + bz * p.sW;
+    const GemmBases gb = gemm_bases(p, bz);
+    const float* __restrict__ A = gb.A;
+    const float* __restrict__ W = gb.W;
 
     float acc[TM][TN];
 #pragma unroll
@@ -151,11 +152,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmParams p) {
     }
 
     // ---- epilogue -------------------------------------------------------------------------
-    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
+    const float* __restrict__ bias = gb.bias;
     // C / C2 / R may alias (in-place accumulation: R == C): plain loads, no __restrict__
-    float* C = p.C + bz * p.sC;
-    float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
-    const float* R = p.R ? p.R + bz * p.sR : nullptr;
+    float* C = gb.C;
+    float* C2 = gb.C2;
+    const float* R = gb.R;
     const int nbase = n0 + tx * TN;
     float bv[TN];
 #pragma unroll
@@ -249,12 +250,13 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(GemmParams p) {
     const int ncols = p.N;
     const long long total = (long long)p.M * ncols;
     const int bz = blockIdx.y;
-    const float* __restrict__ A = p.A + bz * p.sA;
-    const float* __restrict__ W = p.W + bz * p.sW;
-    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
-    float* C = p.C + bz * p.sC;
-    float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
-    const float* R = p.R ? p.R + bz * p.sR : nullptr;
+    const GemmBases gb = gemm_bases(p, bz);
+    const float* __restrict__ A = gb.A;
+    const float* __restrict__ W = gb.W;
+    const float* __restrict__ bias = gb.bias;
+    float* C = gb.C;
+    float* C2 = gb.C2;
+    const float* R = gb.R;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int m = int(e / ncols), n = int(e - (long long)m * ncols);
         float acc = 0.f, accp = 0.f;
@@ -292,16 +294,16 @@ int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
     if (g.K <= 32) {
         const long long total = (long long)g.M * g.N;
         const int blocks = int(std::min<long long>((total + 255) / 256, 148 * 16));
-        launch_k(gemm_smallk_kernel, dim3(blocks, g.batch), dim3(256), size_t(0), stream, p);
+        launch_k(gemm_smallk_kernel, dim3(blocks, g.batch * B.nb), dim3(256), size_t(0), stream, p);
         return 1;
     }
     const bool vec = al16(p.A) && al16(p.W) && g.lda % 4 == 0 && g.seg_len % 4 == 0 && g.seg_stride % 4 == 0 &&
                      g.K % 4 == 0 && g.ldw % 4 == 0 && g.sA % 4 == 0 && g.sW % 4 == 0;
     p.vec_store = (g.out_mode == OUT_PLAIN && g.act != ACT_GATE && al16(p.C) && g.ldc % 4 == 0 && g.sC % 4 == 0 &&
                    (!p.C2 || (al16(p.C2) && g.ldc2 % 4 == 0))) ? 1 : 0;
-    if (g.M >= 1024) launch_cfg<128, 64, 8, 4>(p, g.batch, vec, stream);
-    else if (g.M > 32) launch_cfg<64, 64, 4, 4>(p, g.batch, vec, stream);
-    else launch_cfg<16, 64, 1, 4>(p, g.batch, vec, stream);
+    if (g.M >= 1024) launch_cfg<128, 64, 8, 4>(p, g.batch * B.nb, vec, stream);
+    else if (g.M > 32) launch_cfg<64, 64, 4, 4>(p, g.batch * B.nb, vec, stream);
+    else launch_cfg<16, 64, 1, 4>(p, g.batch * B.nb, vec, stream);
     return 1;
 }
 

@@ -61,8 +61,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm_v2_kernel(GemmParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int z = blockIdx.z % p.splitk, bz = blockIdx.z / p.splitk;
-    const float* __restrict__ A = p.A + bz * p.sA;
-    const float* __restrict__ W = p.W + bz * p.sW;
+    const GemmBases gb = gemm_bases(p, bz);
+    const float* __restrict__ A = gb.A;
+    const float* __restrict__ W = gb.W;
     const int nkt_total = (p.K + BK2 - 1) / BK2;
     const int kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split);
     const int nkt = max(0, kt1 - kt0);
@@ -177,14 +178,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm_v2_kernel(GemmParams p) {
         v[i] = s;
     }
 
-    const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
-    float* C = p.C + bz * p.sC;
-    float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
-    const float* R = p.R ? p.R + bz * p.sR : nullptr;
+    const float* __restrict__ bias = gb.bias;
+    float* C = gb.C;
+    float* C2 = gb.C2;
+    const float* R = gb.R;
     const int n = n0 + col;
 
     if (p.splitk > 1) {
-        float* part = p.scratch + ((long long)(bz * p.splitk + z) * p.M) * p.N;
+        float* part = gb.scratch + ((long long)(gb.grp * p.splitk + z) * p.M) * p.N;
 #pragma unroll
         for (int i = 0; i < OPT; ++i) {
             const int m = m0 + r0 + i * RS;
@@ -192,17 +193,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm_v2_kernel(GemmParams p) {
         }
         __threadfence();
         __syncthreads();
-        const int tile = (bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        const int tile = (gb.grp * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         if (tid == 0) {
-            const unsigned ticket = atomicAdd(p.counters + tile, 1u);
+            const unsigned ticket = atomicAdd(gb.counters + tile, 1u);
             s_last = (ticket == unsigned(p.splitk - 1)) ? 1 : 0;
-            if (s_last) p.counters[tile] = 0;  // self-cleaning for the next launch / graph replay
+            if (s_last) gb.counters[tile] = 0;  // self-cleaning for the next launch / graph replay
         }
         __syncthreads();
         V2_DBG(6);
         if (!s_last) return;
         __threadfence();
-        const float* base = p.scratch + ((long long)(bz * p.splitk) * p.M) * p.N;
+        const float* base = gb.scratch + ((long long)(gb.grp * p.splitk) * p.M) * p.N;
 #pragma unroll
         for (int i = 0; i < OPT; ++i) v[i] = 0.f;
         // partials are summed in z order; 8 splits x 4 rows = 32 independent L2 loads in flight per thread
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) gemm_v2_kernel(GemmParams p) {
 }
 
 template <int BM, int BN, int STAGES>
-void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
+void launch_v2(const GemmOp& g, GemmParams& p, int nb, cudaStream_t s) {
     constexpr size_t stage_bytes = sizeof(float) * size_t(STAGES) * (BM + BN) * LDS2;
     constexpr size_t red_bytes = sizeof(float) * 8 * BM * BN;
     constexpr size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
@@ -270,7 +271,7 @@ void launch_v2(const GemmOp& g, GemmParams& p, cudaStream_t s) {
     if (first_time_on_device(attr)) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     const int nkt = (g.K + BK2 - 1) / BK2;
     p.kt_per_split = (nkt + g.splitk - 1) / g.splitk;
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.batch * g.splitk);
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nb * g.batch * g.splitk);
     launch_k(kern, grid, dim3(V2_THREADS), smem, s, p);
 }
 
@@ -280,10 +281,10 @@ int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
     GemmParams p = gemmk::make_params(g, B);
     switch (g.sched_variant) {
         // (deeper rings were measured slower: profiles/README.md)
-        case 1: launch_v2<8, 256, 3>(g, p, stream); break;
-        case 2: launch_v2<16, 128, 4>(g, p, stream); break;
-        case 4: launch_v2<32, 32, 4>(g, p, stream); break;
-        default: launch_v2<32, 64, 4>(g, p, stream); break;
+        case 1: launch_v2<8, 256, 3>(g, p, B.nb, stream); break;
+        case 2: launch_v2<16, 128, 4>(g, p, B.nb, stream); break;
+        case 4: launch_v2<32, 32, 4>(g, p, B.nb, stream); break;
+        default: launch_v2<32, 64, 4>(g, p, B.nb, stream); break;
     }
     return 1;
 }

@@ -26,14 +26,18 @@ namespace {
 template <int CV, int QN, int G, int KK, int RR, int PF>
 __global__ void __launch_bounds__(256, PF ? 1 : 2)
 knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __restrict__ queries, long long ldq, int Q,
-                float* __restrict__ cand_d, int* __restrict__ cand_i, int parts, int k) {
+                float* __restrict__ cand_d, int* __restrict__ cand_i, int parts, int k,
+                int q0, int Qw, long long wQ, long long wCandD, long long wCandI) {
     pdl_enter();
+    // Q queries of this launch = global queries q0 .. q0+Q; global query g belongs to window g / Qw of a batched plan
+    // (row g % Qw of that window's query block): ONE pass over the index serves every window of the batch
     extern __shared__ __align__(16) float qs[];  // [G*QN][C], zero padded; reused for the CTA merge at the end
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C4 = C >> 2;
     for (int e = tid; e < G * QN * C; e += 256) {
         int q = e / C, c = e - q * C;
-        qs[e] = q < Q ? queries[(long long)q * ldq + c] : 0.f;
+        const int gq = q0 + q;
+        qs[e] = q < Q ? queries[(long long)(gq / Qw) * wQ + (long long)(gq % Qw) * ldq + c] : 0.f;
     }
     __syncthreads();
 
@@ -170,8 +174,9 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
             for (int u = 0; u < CPL; ++u)
                 if (ci_[u] == bi && bi != INT_MAX) { cd_[u] = FLT_MAX; ci_[u] = INT_MAX; }   // row ids are unique: taken
             if (lane == 0) {
-                cand_d[((long long)q * parts + blockIdx.x) * k + r] = bd;
-                cand_i[((long long)q * parts + blockIdx.x) * k + r] = bi == INT_MAX ? -1 : bi;
+                const int gq = q0 + q, w = gq / Qw, j = gq - w * Qw;
+                cand_d[w * wCandD + ((long long)j * parts + blockIdx.x) * k + r] = bd;
+                cand_i[w * wCandI + ((long long)j * parts + blockIdx.x) * k + r] = bi == INT_MAX ? -1 : bi;
             }
         }
     }
@@ -181,8 +186,9 @@ knn_scan_kernel(const float* __restrict__ index, int N, int C, const float* __re
 // The candidate list is staged once in shared memory when it fits (it does for 2368 parts x k <= 8).
 __global__ void __launch_bounds__(256)
 knn_select_kernel(const float* __restrict__ cand_d, const int* __restrict__ cand_i, int* __restrict__ idx,
-                  float* __restrict__ d2, int M, int k, int staged) {
+                  float* __restrict__ d2, int M, int k, int staged, long long wCandD, long long wCandI, long long wIdx, long long wD2) {
     pdl_enter();
+    cand_d += blockIdx.z * wCandD; cand_i += blockIdx.z * wCandI; idx += blockIdx.z * wIdx; d2 += blockIdx.z * wD2;
     extern __shared__ __align__(16) float sel_sm[];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* cd = cand_d + (long long)q * M;
@@ -224,17 +230,25 @@ knn_select_kernel(const float* __restrict__ cand_d, const int* __restrict__ cand
 __global__ void __launch_bounds__(256)
 knn_blend_kernel(const float* __restrict__ index, const int* __restrict__ idx, const float* __restrict__ d2,
                  const float* __restrict__ x, long long ldx, float* __restrict__ out, const RunParams* __restrict__ rp,
-                 int C, int k) {
+                 int C, int k, long long wIdx, long long wD2, long long wX, long long wOut, long long wRp) {
     pdl_enter();
+    idx += blockIdx.z * wIdx; d2 += blockIdx.z * wD2; x += blockIdx.z * wX; out += blockIdx.z * wOut;
+    rp = reinterpret_cast<const RunParams*>(reinterpret_cast<const float*>(rp) + blockIdx.z * wRp);
     const int q = blockIdx.x;
+    const float rate = rp->index_rate;
+    if (rate == 0.0f) {   // retrieval switched off: the features pass through untouched (no NaN can leak in from a degenerate hit)
+        for (int c = threadIdx.x; c < C; c += 256) out[(long long)q * C + c] = x[(long long)q * ldx + c];
+        return;
+    }
     __shared__ float w[32]; __shared__ int id[32];
     if (threadIdx.x == 0) {
+        // weights (1/d)^2 normalised (upstream RVC).  An exact hit (d == 0: replayed training audio, duplicate rows) would
+        // give inf/inf: the distance is floored at the smallest normal float, which makes such a hit dominate the blend.
         float ws = 0.f;
-        for (int i = 0; i < k; ++i) { float r = 1.0f / d2[q * k + i]; w[i] = r * r; ws += w[i]; id[i] = idx[q * k + i]; }
+        for (int i = 0; i < k; ++i) { float r = 1.0f / fmaxf(d2[q * k + i], 1e-30f); r = fminf(r, 1e18f); w[i] = r * r; ws += w[i]; id[i] = idx[q * k + i]; }
         for (int i = 0; i < k; ++i) w[i] /= ws;
     }
     __syncthreads();
-    const float rate = rp->index_rate;
     for (int c = threadIdx.x; c < C; c += 256) {
         float a = 0.f;
         for (int i = 0; i < k; ++i) a = fmaf(w[i], __ldg(index + (long long)id[i] * C + c), a);
@@ -244,14 +258,15 @@ knn_blend_kernel(const float* __restrict__ index, const int* __restrict__ idx, c
 
 template <int CV, int QN, int G, int KK, int RR>
 void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaStream_t s) {
-    if (G == 1 && knn_two_ctas_per_sm(o.Q, o.C, o.k)) {
+    const long long wQ = B.ws(o.queries), wCD = B.ws(o.cand_d), wCI = B.ws(o.cand_i);
+    if (G == 1 && knn_two_ctas_per_sm(nq, o.C, o.k) && (o.parts > KNN_PARTS || o.parts == o.N)) {
         auto kern2 = knn_scan_kernel<CV, QN, G, KK, RR, 0>;
         const size_t q_bytes2 = sizeof(float) * size_t(G) * QN * o.C, m_bytes2 = size_t(8) * G * QN * KK * 8;
         const size_t smem2 = q_bytes2 > m_bytes2 ? q_bytes2 : m_bytes2;
         static unsigned long long attr2 = 0;
         if (first_time_on_device(attr2)) cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        launch_k(kern2, dim3(o.parts), dim3(256), smem2, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
-                 B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k, B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
+        launch_k(kern2, dim3(o.parts), dim3(256), smem2, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries), o.ldq, nq,
+                 B.p<float>(o.cand_d), B.p<int>(o.cand_i), o.parts, o.k, q0, o.Q, wQ, wCD, wCI);
         return;
     }
     auto kern = knn_scan_kernel<CV, QN, G, KK, RR, 1>;
@@ -259,17 +274,17 @@ void scan_launch(const KnnScanOp& o, const DeviceBases& B, int q0, int nq, cudaS
     const size_t smem = q_bytes > m_bytes ? q_bytes : m_bytes;
     static unsigned long long attr = 0;
     if (first_time_on_device(attr)) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    launch_k(kern, dim3(o.parts), dim3(256), smem, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries) + (long long)q0 * o.ldq, o.ldq, nq,
-                                              B.p<float>(o.cand_d) + (long long)q0 * o.parts * o.k,
-                                              B.p<int>(o.cand_i) + (long long)q0 * o.parts * o.k, o.parts, o.k);
+    launch_k(kern, dim3(o.parts), dim3(256), smem, s, B.p<float>(o.index), o.N, o.C, B.p<float>(o.queries), o.ldq, nq,
+                                              B.p<float>(o.cand_d), B.p<int>(o.cand_i), o.parts, o.k, q0, o.Q, wQ, wCD, wCI);
 }
 
 template <int CV, int KK>
 int scan_dispatch_q(const KnnScanOp& o, const DeviceBases& B, cudaStream_t s) {
     const int maxq = (KK > 8 || o.C > 384) ? 32 : 128;  // per launch: register (top-k lists) and smem (queries) budget
     int launches = 0;
-    for (int q0 = 0; q0 < o.Q; q0 += maxq) {
-        int nq = o.Q - q0 < maxq ? o.Q - q0 : maxq;
+    const int Qall = o.Q * B.nb;   // every window's queries in the same pass over the index
+    for (int q0 = 0; q0 < Qall; q0 += maxq) {
+        int nq = Qall - q0 < maxq ? Qall - q0 : maxq;
         if (nq <= 8) scan_launch<CV, 8, 1, KK, (CV <= 2 ? 4 : 2)>(o, B, q0, nq, s);
         else if (nq <= 16) scan_launch<CV, 16, 1, KK, 2>(o, B, q0, nq, s);
         else if (nq <= 32) scan_launch<CV, 32, 1, KK, (CV <= 2 ? 2 : 1)>(o, B, q0, nq, s);
@@ -299,14 +314,14 @@ int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t s
     const int M = o.parts * o.k;
     const size_t need = size_t(M) * 8;
     const int staged = need <= 200 * 1024 ? 1 : 0;
-    launch_k(knn_select_kernel, dim3(o.Q), dim3(256), staged ? need : size_t(0), s, B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx),
-             B.p<float>(o.d2), M, o.k, staged);
+    launch_k(knn_select_kernel, dim3(o.Q, 1, B.nb), dim3(256), staged ? need : size_t(0), s, B.p<float>(o.cand_d), B.p<int>(o.cand_i), B.p<int>(o.idx),
+             B.p<float>(o.d2), M, o.k, staged, B.ws(o.cand_d), B.ws(o.cand_i), B.ws(o.idx), B.ws(o.d2));
     return 1;
 }
 
 int launch_knn_blend(const KnnBlendOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(knn_blend_kernel, dim3(o.Q), dim3(256), size_t(0), s, B.p<float>(o.index), B.p<int>(o.idx), B.p<float>(o.d2), B.p<float>(o.x), o.ldx, B.p<float>(o.out),
-                                         B.p<RunParams>(o.params), o.C, o.k);
+    launch_k(knn_blend_kernel, dim3(o.Q, 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.index), B.p<int>(o.idx), B.p<float>(o.d2), B.p<float>(o.x), o.ldx, B.p<float>(o.out),
+                                         B.p<RunParams>(o.params), o.C, o.k, B.ws(o.idx), B.ws(o.d2), B.ws(o.x), B.ws(o.out), B.ws(o.params));
     return 1;
 }
 

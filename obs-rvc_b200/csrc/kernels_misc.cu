@@ -42,10 +42,11 @@ constexpr int LN_MAXV = 32;  // up to 1024 columns
 
 __global__ void layernorm_kernel(const float* __restrict__ X, long long ldx, float* __restrict__ Y, long long ldy,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int cols,
-                                 float eps) {
+                                 float eps, long long wX, long long wY) {
     pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows) return;
+    X += blockIdx.z * wX; Y += blockIdx.z * wY;   // window of a batched plan
     const float* x = X + (long long)warp * ldx;
     float v[LN_MAXV];
     float s = 0.f;
@@ -80,11 +81,13 @@ __global__ void layernorm_kernel(const float* __restrict__ X, long long ldx, flo
 constexpr int ATT_WARPS = 8, ATT_D = 64;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo, int T, int heads) {
+attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo, int T, int heads,
+            long long wQkv, long long wOut, int rows_per_cta) {
     pdl_enter();
+    qkv += blockIdx.z * wQkv; out += blockIdx.z * wOut;
     extern __shared__ __align__(16) float sm[];
     constexpr int D = ATT_D;
-    const int h = blockIdx.x, q0 = blockIdx.y * ATT_WARPS;
+    const int h = blockIdx.x, qbase = blockIdx.y * rows_per_cta;
     const int HD = heads * D, Tp = (T | 1) + 2;          // odd pitch
     float* Vs = sm;                                       // [T][D]
     float* Kt = Vs + (size_t)T * D;                       // [D][Tp]
@@ -98,17 +101,16 @@ attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out
         reinterpret_cast<float4*>(Vs + (size_t)t * D)[d4] = v;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = q0 + warp;
-    float q[D];
-    if (qi < T) {
-#pragma unroll
-        for (int d4 = 0; d4 < D / 4; ++d4) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi * ld + h * D) + d4);
-            q[d4 * 4] = t4.x; q[d4 * 4 + 1] = t4.y; q[d4 * 4 + 2] = t4.z; q[d4 * 4 + 3] = t4.w;
-        }
-    }
     __syncthreads();
-    if (qi >= T) return;
+    // K / V of the head are staged once per CTA; a warp takes query rows qbase + warp, + 8, ... (batched plans give a
+    // CTA many rows so the staging is amortised; a single window keeps 8 rows per CTA for the widest grid)
+    for (int qi = qbase + warp; qi < min(T, qbase + rows_per_cta); qi += ATT_WARPS) {
+    float q[D];
+#pragma unroll
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi * ld + h * D) + d4);
+        q[d4 * 4] = t4.x; q[d4 * 4 + 1] = t4.y; q[d4 * 4 + 2] = t4.z; q[d4 * 4 + 3] = t4.w;
+    }
     float* ps = Ps + warp * Tp;
     float mx = -FLT_MAX;
     for (int j = lane; j < T; j += 32) {
@@ -136,13 +138,17 @@ attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out
     }
     out[(long long)qi * ldo + h * D + lane] = o0 * inv;
     out[(long long)qi * ldo + h * D + lane + 32] = o1 * inv;
+    __syncwarp();
+    }
 }
 
 // VITS windowed relative-position attention (enc_p): one CTA per (head, query row), 128 threads.
 __global__ void __launch_bounds__(128)
 relattn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out, long long ldo,
-               const float* __restrict__ rel_k, const float* __restrict__ rel_v, int T, int heads, int dim, int window) {
+               const float* __restrict__ rel_k, const float* __restrict__ rel_v, int T, int heads, int dim, int window,
+               long long wQkv, long long wOut) {
     pdl_enter();
+    qkv += blockIdx.z * wQkv; out += blockIdx.z * wOut;
     extern __shared__ float sm[];
     const int h = blockIdx.x / T, i = blockIdx.x - h * T;
     const int HD = heads * dim, nrel = 2 * window + 1;
@@ -191,8 +197,9 @@ constexpr int C0_CH = 4;  // channels per CTA in the stats pass
 
 __global__ void __launch_bounds__(256)
 conv0_stats_kernel(const float* __restrict__ pcm, const float* __restrict__ w, float* __restrict__ stats, int T, int C,
-                   int k, int stride, float eps) {
+                   int k, int stride, float eps, long long wPcm, long long wStats) {
     pdl_enter();
+    pcm += blockIdx.z * wPcm; stats += blockIdx.z * wStats;
     const int c0 = blockIdx.x * C0_CH;
     float wr[C0_CH][10];
 #pragma unroll
@@ -237,8 +244,9 @@ constexpr int C0_TB = 16;  // time steps per CTA in the apply pass
 __global__ void __launch_bounds__(256)
 conv0_apply_kernel(const float* __restrict__ pcm, const float* __restrict__ w, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, int T, int C,
-                   int k, int stride) {
+                   int k, int stride, long long wPcm, long long wStats, long long wY) {
     pdl_enter();
+    pcm += blockIdx.z * wPcm; stats += blockIdx.z * wStats; Y += blockIdx.z * wY;
     __shared__ float xs[C0_TB * 5 + 16];
     const int t0 = blockIdx.x * C0_TB;
     const int nx = (min(C0_TB, T - t0) - 1) * stride + k;
@@ -261,8 +269,10 @@ conv0_apply_kernel(const float* __restrict__ pcm, const float* __restrict__ w, c
 // ------------------------------------------------------------------------------------------
 // 2x2 average pool on halo-padded NHWC
 // ------------------------------------------------------------------------------------------
-__global__ void avgpool_kernel(const float* __restrict__ in, long long ldin, float* __restrict__ out, int T, int F, int C) {
+__global__ void avgpool_kernel(const float* __restrict__ in, long long ldin, float* __restrict__ out, int T, int F, int C,
+                               long long wIn, long long wOut) {
     pdl_enter();
+    in += blockIdx.z * wIn; out += blockIdx.z * wOut;
     const int To = T / 2, Fo = F / 2;
     const long long n = (long long)To * Fo * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -286,8 +296,9 @@ constexpr int GRU_CL = 8, GRU_H = 256, GRU_UNITS = GRU_H / GRU_CL;  // 32 hidden
 
 __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(768)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t, const float* __restrict__ bhh,
-                   float* __restrict__ out, int T) {
+                   float* __restrict__ out, int T, long long wGi, long long wOut) {
     pdl_enter();
+    gi += blockIdx.z * wGi; out += blockIdx.z * wOut;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int H = GRU_H, G = 3 * GRU_H;
     __shared__ __align__(16) float hbuf[2][H];
@@ -341,8 +352,9 @@ gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t
 __global__ void __launch_bounds__(256)
 embed_kernel(const float* __restrict__ phone, const int* __restrict__ pitch, const float* __restrict__ wp,
              const float* __restrict__ bp, const float* __restrict__ emb_pitch, float* __restrict__ out, long long ldo,
-             int Cin, int H) {
+             int Cin, int H, long long wPhone, long long wPitch, long long wOut) {
     pdl_enter();
+    phone += blockIdx.z * wPhone; pitch += blockIdx.z * wPitch; out += blockIdx.z * wOut;
     extern __shared__ float xs[];
     const int r = blockIdx.x;
     for (int i = threadIdx.x; i < Cin; i += blockDim.x) xs[i] = phone[(long long)r * Cin + i];
@@ -372,8 +384,10 @@ embed_kernel(const float* __restrict__ phone, const int* __restrict__ pitch, con
 }
 
 __global__ void zp_kernel(const float* __restrict__ stats, float* __restrict__ out, long long ldo,
-                          const RunParams* __restrict__ rp, int R, int H) {
+                          const RunParams* __restrict__ rp, int R, int H, long long wStats, long long wOut, long long wRp) {
     pdl_enter();
+    stats += blockIdx.z * wStats; out += blockIdx.z * wOut;
+    rp = reinterpret_cast<const RunParams*>(reinterpret_cast<const float*>(rp) + blockIdx.z * wRp);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= R * H) return;
     const int r = e / H, c = e - r * H;
@@ -385,8 +399,10 @@ __global__ void zp_kernel(const float* __restrict__ stats, float* __restrict__ o
 
 __global__ void avg3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                             long long ld, float* __restrict__ out, long long ldo, float* __restrict__ raw, long long ldraw,
-                            int T, int C, float slope) {
+                            int T, int C, float slope, long long wIn, long long wOut, long long wRaw) {
     pdl_enter();
+    a += blockIdx.z * wIn; b += blockIdx.z * wIn; c += blockIdx.z * wIn; out += blockIdx.z * wOut;
+    if (raw) raw += blockIdx.z * wRaw;
     const long long n = (long long)T * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         int ch = int(e % C);
@@ -400,8 +416,10 @@ __global__ void avg3_kernel(const float* __restrict__ a, const float* __restrict
 
 // conv_post: tanh(conv1d(C -> 1, k)); thread per output sample, weights in smem
 __global__ void __launch_bounds__(256)
-convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, int T, int C, int k) {
+convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, int T, int C, int k,
+                long long wIn, long long wOut) {
     pdl_enter();
+    in += blockIdx.z * wIn; out += blockIdx.z * wOut;
     extern __shared__ float ws[];
     const int n = k * C;
     for (int i = threadIdx.x; i < n; i += blockDim.x) ws[i] = w[i];
@@ -419,8 +437,9 @@ convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ out, int T, int C,
-                                   int skip, int R, int row0) {
+                                   int skip, int R, int row0, long long wSrc, long long wOut) {
     pdl_enter();
+    src += blockIdx.z * wSrc; out += blockIdx.z * wOut;
     const long long n = (long long)R * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         int c = int(e % C), r = int(e / C);
@@ -477,76 +496,81 @@ void launch_split_hilo(const float* src, float* dst_hi, float* dst_lo, size_t n,
 
 int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t s) {
     const int wpb = 4;
-    launch_k(layernorm_kernel, dim3((o.rows + wpb - 1) / wpb), dim3(wpb * 32), size_t(0), s, B.p<float>(o.X), o.ldx, B.p<float>(o.Y), o.ldy,
-                                                                  B.p<float>(o.gamma), B.p<float>(o.beta), o.rows, o.cols, o.eps);
+    launch_k(layernorm_kernel, dim3((o.rows + wpb - 1) / wpb, 1, B.nb), dim3(wpb * 32), size_t(0), s, B.p<float>(o.X), o.ldx, B.p<float>(o.Y), o.ldy,
+                                                                  B.p<float>(o.gamma), B.p<float>(o.beta), o.rows, o.cols, o.eps, B.ws(o.X), B.ws(o.Y));
     return 1;
 }
 
 int launch_attn(const AttnOp& o, const DeviceBases& B, cudaStream_t s) {
     // head dim is 64 for every ContentVec variant (validated by the plan builder)
-    dim3 grid(o.heads, (o.T + ATT_WARPS - 1) / ATT_WARPS);
-    launch_k(attn_kernel, grid, dim3(ATT_WARPS * 32), attn_smem(o.T), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T, o.heads);
+    const int rows = B.nb >= 8 ? 8 * ATT_WARPS : (B.nb > 1 ? 2 * ATT_WARPS : ATT_WARPS);
+    dim3 grid(o.heads, (o.T + rows - 1) / rows, B.nb);
+    launch_k(attn_kernel, grid, dim3(ATT_WARPS * 32), attn_smem(o.T), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo, o.T, o.heads,
+             B.ws(o.qkv), B.ws(o.out), rows);
     return 1;
 }
 
 int launch_relattn(const RelAttnOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(relattn_kernel, dim3(o.heads * o.T), dim3(128), relattn_smem(o.T, o.dim), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
-             B.p<float>(o.rel_k), B.p<float>(o.rel_v), o.T, o.heads, o.dim, o.window);
+    launch_k(relattn_kernel, dim3(o.heads * o.T, 1, B.nb), dim3(128), relattn_smem(o.T, o.dim), s, B.p<float>(o.qkv), o.ldqkv, B.p<float>(o.out), o.ldo,
+             B.p<float>(o.rel_k), B.p<float>(o.rel_v), o.T, o.heads, o.dim, o.window, B.ws(o.qkv), B.ws(o.out));
     return 1;
 }
 
 int launch_conv0_stats(const Conv0StatsOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(conv0_stats_kernel, dim3((o.C + C0_CH - 1) / C0_CH), dim3(256), size_t(0), s, B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats), o.T, o.C,
-                                                                 o.k, o.stride, o.eps);
+    launch_k(conv0_stats_kernel, dim3((o.C + C0_CH - 1) / C0_CH, 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats), o.T, o.C,
+                                                                 o.k, o.stride, o.eps, B.ws(o.pcm), B.ws(o.stats));
     return 1;
 }
 
 int launch_conv0_apply(const Conv0ApplyOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(conv0_apply_kernel, dim3((o.T + C0_TB - 1) / C0_TB), dim3(256), size_t(0), s, B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats),
+    launch_k(conv0_apply_kernel, dim3((o.T + C0_TB - 1) / C0_TB, 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.pcm), B.p<float>(o.w), B.p<float>(o.stats),
                                                                  B.p<float>(o.gamma), B.p<float>(o.beta), B.p<float>(o.Y), o.T, o.C,
-                                                                 o.k, o.stride);
+                                                                 o.k, o.stride, B.ws(o.pcm), B.ws(o.stats), B.ws(o.Y));
     return 1;
 }
 
 int launch_avgpool(const AvgPoolOp& o, const DeviceBases& B, cudaStream_t s) {
     long long n = (long long)(o.T / 2) * (o.F / 2) * o.C;
-    launch_k(avgpool_kernel, dim3(grid_for(n, 256)), dim3(256), size_t(0), s, B.p<float>(o.in), o.ldin, B.p<float>(o.out), o.T, o.F, o.C);
+    launch_k(avgpool_kernel, dim3(grid_for(n, 256), 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.in), o.ldin, B.p<float>(o.out), o.T, o.F, o.C,
+             B.ws(o.in), B.ws(o.out));
     return 1;
 }
 
 int launch_gru(const GruOp& o, const DeviceBases& B, cudaStream_t s) {
     // H is fixed by the RMVPE architecture (BiGRU(384, 256)); validated when the model is packed
-    launch_k(gru_cluster_kernel, dim3(2 * GRU_CL), dim3(768), size_t(0), s, B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out), o.T);
+    launch_k(gru_cluster_kernel, dim3(2 * GRU_CL, 1, B.nb), dim3(768), size_t(0), s, B.p<float>(o.gi), B.p<float>(o.whh_t), B.p<float>(o.bhh), B.p<float>(o.out), o.T,
+             B.ws(o.gi), B.ws(o.out));
     return 1;
 }
 
 int launch_embed(const EmbedOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(embed_kernel, dim3(o.R), dim3(256), size_t(sizeof(float) * o.Cin), s, B.p<float>(o.phone), B.p<int>(o.pitch), B.p<float>(o.wp), B.p<float>(o.bp),
-                                                         B.p<float>(o.emb_pitch), B.p<float>(o.out), o.ldo, o.Cin, o.H);
+    launch_k(embed_kernel, dim3(o.R, 1, B.nb), dim3(256), size_t(sizeof(float) * o.Cin), s, B.p<float>(o.phone), B.p<int>(o.pitch), B.p<float>(o.wp), B.p<float>(o.bp),
+                                                         B.p<float>(o.emb_pitch), B.p<float>(o.out), o.ldo, o.Cin, o.H, B.ws(o.phone), B.ws(o.pitch), B.ws(o.out));
     return 1;
 }
 
 int launch_zp(const ZpOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(zp_kernel, dim3((o.R * o.H + 255) / 256), dim3(256), size_t(0), s, B.p<float>(o.stats), B.p<float>(o.out), o.ldo, B.p<RunParams>(o.params), o.R, o.H);
+    launch_k(zp_kernel, dim3((o.R * o.H + 255) / 256, 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.stats), B.p<float>(o.out), o.ldo, B.p<RunParams>(o.params), o.R, o.H,
+             B.ws(o.stats), B.ws(o.out), B.ws(o.params));
     return 1;
 }
 
 int launch_avg3(const Avg3Op& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(avg3_kernel, dim3(grid_for((long long)o.T * o.C, 256)), dim3(256), size_t(0), s, B.p<float>(o.a), B.p<float>(o.b), B.p<float>(o.c), o.ld,
+    launch_k(avg3_kernel, dim3(grid_for((long long)o.T * o.C, 256), 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.a), B.p<float>(o.b), B.p<float>(o.c), o.ld,
                                                                     B.p<float>(o.out), o.ldo, B.p<float>(o.raw), o.ldraw, o.T, o.C,
-                                                                    o.slope);
+                                                                    o.slope, B.ws(o.a), B.ws(o.out), B.ws(o.raw));
     return 1;
 }
 
 int launch_convpost(const ConvPostOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(convpost_kernel, dim3((o.T + 255) / 256), dim3(256), size_t(sizeof(float) * o.k * o.C), s, B.p<float>(o.in), B.p<float>(o.w), B.p<float>(o.out), o.T,
-                                                                              o.C, o.k);
+    launch_k(convpost_kernel, dim3((o.T + 255) / 256, 1, B.nb), dim3(256), size_t(sizeof(float) * o.k * o.C), s, B.p<float>(o.in), B.p<float>(o.w), B.p<float>(o.out), o.T,
+                                                                              o.C, o.k, B.ws(o.in), B.ws(o.out));
     return 1;
 }
 
 int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t s) {
-    launch_k(gather_rows_kernel, dim3(grid_for((long long)o.R * o.C, 256)), dim3(256), size_t(0), s, B.p<float>(o.src), o.lds, B.p<float>(o.out), o.T, o.C,
-                                                                          o.skip, o.R, o.row0);
+    launch_k(gather_rows_kernel, dim3(grid_for((long long)o.R * o.C, 256), 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.src), o.lds, B.p<float>(o.out), o.T, o.C,
+                                                                          o.skip, o.R, o.row0, B.ws(o.src), B.ws(o.out));
     return 1;
 }
 

@@ -3,21 +3,26 @@
 // Serves the FLOP-heavy GEMMs of the path (ContentVec conv stem + transformer, pos-conv, HiFiGAN
 // convs / transposed convs): CUDA-core fp32 tops out near 25 TFLOP/s on B200, the 5th-gen tensor
 // cores do not.  Parity demands fp32-grade results (F0/kNN bit-exact decisions downstream, 1e-3
-// waveform RMS), so the kernel runs the 3xTF32 error-compensated scheme:
-//     A = A_hi + A_lo,  W = W_hi + W_lo   (hi = fp32 with the 13 low mantissa bits cleared)
-//     D += A_hi.W_hi + A_lo.W_hi + A_hi.W_lo        (dropped term ~2^-22 relative)
-// W_hi / W_lo are precomputed once per model and live in HBM next to the fp32 weights; A_hi / A_lo
-// are produced in shared memory by the (otherwise idle) epilogue warps from the fp32 tile that TMA
-// delivered.  Accumulation is fp32 in TMEM.
+// waveform RMS), so the kernel runs an error-compensated split:
+//   default, PASSES = 16 (2-term FP16 split, kind::f16, fp32 accumulation in TMEM):
+//     x = hi + lo' * 2^-11,  hi = half(x),  lo' = half((x - hi) * 2^11)
+//     D0 += A_hi.W_hi ;  D1 += A_lo'.W_hi + A_hi.W_lo' ;  D = D0 + 2^-11 D1      (dropped term ~2^-22)
+//     A_hi x [W_hi ; W_lo'] is ONE instruction with N = 2 BN (the planes of a stage are adjacent).
+//   RVC_UMMA_F16=0, PASSES = 3 (3xTF32): hi = fp32 word (the tensor core ignores 13 mantissa bits), lo = x - hi.
+// The weight planes are built once per model and live in HBM next to the fp32 weights.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   : TMA producer - cp.async.bulk.tensor loads of A (4-D map: the segmented / overlapping
-//              im2col rows of ops.h), W_hi, W_lo into a 3-4 stage SWIZZLE_128B ring, mbarrier tx;
-//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=BN, K=8),
-//              tcgen05.commit releases smem stages / publishes the accumulator;
-//   warps 2-5: hi/lo split of each A stage (generic -> async proxy fence), then the epilogue:
-//              tcgen05.ld 32 lanes x 16 columns, optional split-K (partials to scratch, last CTA per
-//              tile reduces in fixed order), bias / activation / residual / masks / scatter modes.
+// Structure (one 128 x BN output tile per CTA, 384 threads = 12 warps):
+//   warps 0, 11 : TMA producers (alternate k-blocks): cp.async.bulk.tensor 3-D loads of the two weight
+//                 planes into a 6-8 stage ring, mbarrier expect_tx;
+//   warp 1      : TMEM allocation + single-thread tcgen05.mma issue (M = 128, K = 16 halves per instruction),
+//                 tcgen05.commit releases a stage / publishes the accumulator;
+//   warps 2-9   : A path (FP16 mode): the segmented / overlapping im2col rows of ops.h are read from L2
+//                 (ld.global.cg, three k-blocks ahead in registers), split into the two fp16 planes and written
+//                 in the SWIZZLE_64B layout the descriptors expect (fence.proxy.async, then the stage barrier);
+//   warps 2-5   : then drain TMEM (tcgen05.ld 32 lanes x 16 columns) into a padded staging tile;
+//   all warps   : epilogue - split-K partial tiles of a thread-block cluster are exchanged through an L2 scratch
+//                 (one cluster barrier) and summed in z order; bias / activation / residual / masks / scatter modes.
+// Batched plans (several windows per launch): grid.z = windows x groups x split-K, weights shared between windows.
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -231,7 +236,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto stageAlo16 = [&](int s) { return smem + s * Cfg::STAGE_BYTES + Cfg::A16_BYTES; };
 
     const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
-    const int z = blockIdx.z % p.splitk, bz = blockIdx.z / p.splitk;
+    const int z = blockIdx.z % p.splitk, bzw = blockIdx.z / p.splitk;
+    const int win = bzw / p.batch, bz = bzw - win * p.batch;   // window of a batched plan, group (the op's own batch index)
     const int nkb_total = (p.K + UM_BK - 1) / UM_BK;
     const int kb0 = z * p.kt_per_split, kb1 = min(nkb_total, kb0 + p.kt_per_split);
     const int nkb = max(0, kb1 - kb0);
@@ -273,7 +279,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int kk = (kb0 + i) * UM_BK;
             if (lane == 0) {
                 const int seg = kk / p.seg_len, within = kk - seg * p.seg_len;
-                if (!Cfg::F16 && g_dev_dbg_skip != 1) tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);
+                if (!Cfg::F16 && g_dev_dbg_skip != 1) tma_load_4d(&tmA, stageA(s), &bar_full[s], within, seg, m0, bz);   // (3xTF32 path: nb == 1 only, see launch_gemm_umma)
                 UMMA_DBG2(1, i);
             } else if (g_dev_dbg_skip == 2) {
             } else if (lane == 1) {
@@ -361,7 +367,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // One task = one 16-byte chunk of the planes = 8 consecutive k of one row; 512 tasks per k-block, 2 per thread.
             // All 8 warps work on the SAME (oldest) stage: the k loop is bound by the round trip of a stage, not by
             // converter throughput, so the conversion must be short.
-            const float* __restrict__ Ab = p.A + bz * p.sA;
+            const float* __restrict__ Ab = p.A + bz * p.sA + win * p.wA;
             const float* rowp[2]; int within[2]; int dsto[2];
             const int seg_len = p.seg_len;                      // == K when the rows are contiguous (launch_umma_cfg)
             const long long seg_wrap = p.seg_stride - p.seg_len;
@@ -511,7 +517,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // staged partial tile -> this CTA's slot of the L2 scratch, coalesced (all 12 warps, float4 along the columns)
         __syncthreads();
         const long long tile_lin0 = ((long long)bz * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        float* dst = p.scratch + ((tile_lin0 * p.splitk + z) * UM_BM) * BN;
+        float* dst = p.scratch + win * p.wScratch + ((tile_lin0 * p.splitk + z) * UM_BM) * BN;
         const float* src = reinterpret_cast<const float*>(smem);
         const int live_rows = min(UM_BM, p.M - m0);   // rows past M are never read back
         for (int e = tid; e < live_rows * (BN / 4); e += UM_THREADS) {
@@ -524,9 +530,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (tid == 64) UMMA_DBG(12);
     {
         const float* __restrict__ bias = p.bias ? p.bias + bz * p.sBias : nullptr;
-        float* C = p.C + bz * p.sC;
-        float* C2 = p.C2 ? p.C2 + bz * p.sC : nullptr;
-        const float* R = p.R ? p.R + bz * p.sR : nullptr;
+        float* C = p.C + bz * p.sC + win * p.wC;
+        float* C2 = p.C2 ? p.C2 + bz * p.sC + win * p.wC2 : nullptr;
+        const float* R = p.R ? p.R + bz * p.sR + win * p.wR : nullptr;
         const float* Ct = reinterpret_cast<const float*>(smem);
         const int rows_per = UM_BM / p.splitk;
         const int r_begin = z * rows_per, r_end = r_begin + rows_per;
@@ -536,7 +542,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ldp = via_l2 ? BN : CT_LD;   // row pitch of a partial tile (global scratch / padded smem staging)
 #pragma unroll
         for (int zz = 0; zz < 8; ++zz) {
-            if (via_l2) peers[zz] = p.scratch + ((tile_lin * p.splitk + (zz < p.splitk ? zz : 0)) * UM_BM) * BN;
+            if (via_l2) peers[zz] = p.scratch + win * p.wScratch + ((tile_lin * p.splitk + (zz < p.splitk ? zz : 0)) * UM_BM) * BN;
             else peers[zz] = (p.splitk > 1 && zz < p.splitk) ? cg::this_cluster().map_shared_rank(Ct, zz) : Ct;
         }
         if (p.vec_store) {
@@ -685,7 +691,7 @@ bool encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims
 }
 
 template <int BN, int PASSES>
-bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const void* w_hi, const void* w_lo, cudaStream_t s) {
+bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const void* w_hi, const void* w_lo, int nb, cudaStream_t s) {
     using Cfg = UmmaCfg<BN, PASSES>;
     constexpr int WB = Cfg::F16 ? 2 : 4;   // bytes per weight element of the planes
     CUtensorMap tmA, tmW, tmWlo;
@@ -714,7 +720,7 @@ bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const void* w_hi, const voi
                    (!p.bias || (al16(p.bias) && g.sBias % 4 == 0))) ? 1 : 0;
     auto kern = umma_gemm_kernel<BN, PASSES>;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + UM_BM - 1) / UM_BM, g.batch * g.splitk);
+    cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + UM_BM - 1) / UM_BM, nb * g.batch * g.splitk);
     cfg.blockDim = dim3(UM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = s;
@@ -744,6 +750,7 @@ void init_umma_attributes() {
     cudaFuncSetAttribute(umma_gemm_kernel<128, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<128, 16>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<64, 16>::SMEM_BYTES);
     cudaFuncSetAttribute(umma_gemm_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<32, 16>::SMEM_BYTES);
+    cudaFuncSetAttribute(umma_gemm_kernel<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg<16, 16>::SMEM_BYTES);
     { const char* f = getenv("RVC_UMMA_F16"); g_umma_f16 = !(f && f[0] == '0'); }
 #ifdef RVC_UMMA_STAMPS
     { const char* w = getenv("RVC_UMMA_DBG_SKIP"); int v = w ? atoi(w) : 0; cudaMemcpyToSymbol(g_dev_dbg_skip_v, &v, sizeof(int)); }
@@ -764,7 +771,7 @@ int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream)
     GemmParams p = gemmk::make_params(g, B);
     const float* w_hi = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + hl);
     const float* w_lo = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(p.W) + 2 * hl);
-    const int bn = g.sched_variant == 8 ? 256 : (g.sched_variant == 5 ? 128 : (g.sched_variant == 6 ? 64 : 32));
+    const int bn = g.sched_variant == 8 ? 256 : (g.sched_variant == 5 ? 128 : (g.sched_variant == 6 ? 64 : (g.sched_variant == 9 ? 16 : 32)));
     bool ok;
     const int64_t h16 = B.hilo16_off[g.W.space];
     const int64_t woff = reinterpret_cast<const uint8_t*>(p.W) - B.b[g.W.space];   // byte offset of W inside its fp32 arena
@@ -772,19 +779,21 @@ int launch_gemm_umma(const GemmOp& g, const DeviceBases& B, cudaStream_t stream)
     if (g_umma_f16 && g_umma_passes == 3 && h16 > 0 && woff % 32 == 0 && g.ldw % 8 == 0 && g.sW % 8 == 0) {
         const uint8_t* hi16 = B.b[g.W.space] + h16 + woff / 2;
         const uint8_t* lo16 = hi16 + B.hilo16_plane[g.W.space];
-        ok = bn == 256 ? launch_umma_cfg<256, 16>(g, p, hi16, lo16, stream)
-           : bn == 128 ? launch_umma_cfg<128, 16>(g, p, hi16, lo16, stream)
-           : bn == 64 ? launch_umma_cfg<64, 16>(g, p, hi16, lo16, stream) : launch_umma_cfg<32, 16>(g, p, hi16, lo16, stream);
+        ok = bn == 256 ? launch_umma_cfg<256, 16>(g, p, hi16, lo16, B.nb, stream)
+           : bn == 128 ? launch_umma_cfg<128, 16>(g, p, hi16, lo16, B.nb, stream)
+           : bn == 64 ? launch_umma_cfg<64, 16>(g, p, hi16, lo16, B.nb, stream)
+           : bn == 32 ? launch_umma_cfg<32, 16>(g, p, hi16, lo16, B.nb, stream) : launch_umma_cfg<16, 16>(g, p, hi16, lo16, B.nb, stream);
         return ok ? 1 : 0;
     }
-    if (bn == 256) return 0;   // only the FP16-split kernel has a 256-wide instance: the caller falls back to CUDA cores
+    if (B.nb > 1) return 0;   // the 3xTF32 / single-pass instances move A with a 4-D tensor map: one window per launch only
+    if (bn == 256 || bn == 16) return 0;   // only the FP16-split kernel has 256- / 16-wide instances: the caller falls back to CUDA cores
     if (g.seg_len < g.K && g.seg_len % 32 != 0) return 0;   // odd segment lengths: FP16-split kernel only (see gemm_sched.h)
     if (g_umma_passes == 3) {
-        ok = bn == 128 ? launch_umma_cfg<128, 3>(g, p, w_hi, w_lo, stream)
-           : bn == 64 ? launch_umma_cfg<64, 3>(g, p, w_hi, w_lo, stream) : launch_umma_cfg<32, 3>(g, p, w_hi, w_lo, stream);
+        ok = bn == 128 ? launch_umma_cfg<128, 3>(g, p, w_hi, w_lo, 1, stream)
+           : bn == 64 ? launch_umma_cfg<64, 3>(g, p, w_hi, w_lo, 1, stream) : launch_umma_cfg<32, 3>(g, p, w_hi, w_lo, 1, stream);
     } else {
-        ok = bn == 128 ? launch_umma_cfg<128, 1>(g, p, p.W, p.W, stream)
-           : bn == 64 ? launch_umma_cfg<64, 1>(g, p, p.W, p.W, stream) : launch_umma_cfg<32, 1>(g, p, p.W, p.W, stream);
+        ok = bn == 128 ? launch_umma_cfg<128, 1>(g, p, p.W, p.W, 1, stream)
+           : bn == 64 ? launch_umma_cfg<64, 1>(g, p, p.W, p.W, 1, stream) : launch_umma_cfg<32, 1>(g, p, p.W, p.W, 1, stream);
     }
     return ok ? 1 : 0;
 }

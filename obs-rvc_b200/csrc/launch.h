@@ -15,9 +15,16 @@ struct DeviceBases {
     // fp16 split planes of a weight space: byte offset of the hi plane from the fp32 arena, byte size of one plane
     // (element i of the arena sits at hi16_off + 2 i, its scaled residual one plane further); 0 = none
     int64_t hilo16_off[SP_COUNT] = {0}, hilo16_plane[SP_COUNT] = {0};
+    // Batched plans (several windows per launch - offline conversion, or several live streams of one GPU): every
+    // kernel processes `nb` windows; window w finds its activations / state `bstride[space]` bytes after window
+    // w-1's (work arena and state block are replicated per window, weights and index are shared: stride 0).
+    int32_t nb = 1;
+    int64_t bstride[SP_COUNT] = {0};
     template <typename T> T* p(const Ref& r) const {
         return r.null() ? nullptr : reinterpret_cast<T*>(b[r.space] + r.off);
     }
+    // window stride of a buffer in 4-byte elements (every plan buffer is f32 / i32)
+    long long ws(const Ref& r) const { return r.null() ? 0 : (long long)(bstride[r.space] / 4); }
 };
 
 // Each launcher enqueues exactly the kernels of one op on `stream` and returns how many kernels

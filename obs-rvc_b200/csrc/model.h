@@ -68,6 +68,14 @@ struct PlanOptions {
     // on a side lane (shares the GPU with the tcgen05 GEMMs of lane 0); 0 disables chains
     int32_t chain_grid_main = 0, chain_grid_side = 0;
     int32_t chain_side_max_m = 0;  // side-lane GEMMs join a chain only up to this many rows (0 = no limit)
+    // Batched plans (PLAN_INFER only): `nb` windows per launch.  Work arena and state block are replicated per window
+    // (Plan::work_bytes / Plan::state_block apart), weights and index are shared.  sequential = the windows are
+    // consecutive windows of ONE stream (offline conversion): one pitch cache, updated in window order; otherwise they
+    // belong to nb independent streams with their own caches.
+    int32_t nb = 1;
+    bool sequential = false;
+    int32_t index_cols = 0;        // width of the loaded retrieval index (must equal the ContentVec width)
+    bool f0_umma = false;          // RMVPE's wide levels on the tcgen05 FP16-split kernel (batched plans; needs the f0 weight planes)
 };
 
 struct Plan {
@@ -79,6 +87,8 @@ struct Plan {
     // well-known buffers
     Ref pcm, audio, params, cache;
     int32_t hubert_T = 0, hubert_C = 0, f0_T = 0, audio_len = 0, knn_q = 0;
+    int32_t nb = 1;               // windows per launch
+    int64_t state_block = 0;      // bytes between the state blocks of consecutive windows (batched plans; 0 = the context's own state arena)
     const NamedBuf* find(const std::string& name) const;
 };
 

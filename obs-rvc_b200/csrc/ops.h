@@ -112,6 +112,7 @@ struct F0DecodeOp {  // rmvpe.rs:118-133,243-248 (+ rvc.rs:121 uppower from the 
 struct F0PostOp {  // rvc.rs:167-181 + f0/mod.rs:7-12
     Ref f0; Ref cache; Ref pitch; Ref pitchf; int32_t pitch_len = 0, shift = 0, hubert_length = 0,
         skip_head = 0, return_length = 0, cache_len = 1024; float mel_min = 0, mel_max = 0;
+    int32_t sequential = 0;  // batched plans: the windows are consecutive windows of ONE stream (single pitch cache, updated in order)
 };
 
 struct EmbedOp {  // lrelu_0.1((phone Wp^T + bp + emb_pitch[pitch]) * sqrt(H))

@@ -25,6 +25,7 @@ struct PB {
     int lane = 0;
     int sc_lane = -1;   // >= 0: the 1x1 shortcut convs of RMVPE's residual blocks run on this lane, beside c1
     bool allow_umma = true;
+    bool f0_umma = false;
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
 
@@ -496,11 +497,11 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
 }
 
 // chooses the kernel variant / split-K factor of every GEMM and allocates its scratch
-void schedule_gemms(PB& b) {
+void schedule_gemms(PB& b, int nb = 1) {
     for (Op& op : b.plan.ops) {
         if (op.kind != OP_GEMM) continue;
         GemmOp& g = op.gemm;
-        GemmSched s = gemm_schedule(g, b.allow_umma);
+        GemmSched s = gemm_schedule(g, b.allow_umma, nb, b.f0_umma);
         g.sched_variant = s.variant; g.splitk = s.splitk;
         if (s.variant > 0 && s.variant < 5 && s.splitk > 1) {  // v2: partial tiles + one arrival counter per tile
             g.scratch = b.alloc("", int64_t(s.splitk) * g.batch * g.M * g.N);
@@ -512,7 +513,7 @@ void schedule_gemms(PB& b) {
     int64_t need[8] = {0};
     for (Op& op : b.plan.ops) {
         if (op.kind != OP_GEMM || op.gemm.sched_variant < 5 || op.gemm.splitk <= 1 || op.lane >= 8) continue;
-        GemmSched s = gemm_schedule(op.gemm, b.allow_umma);
+        GemmSched s = gemm_schedule(op.gemm, b.allow_umma, nb, b.f0_umma);
         need[op.lane] = std::max(need[op.lane], int64_t(s.tiles) * s.splitk * 128 * s.bn);
     }
     Ref lane_scratch[8];
@@ -645,12 +646,25 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     plan = Plan{};
     PB b{plan, err};
     b.allow_umma = opt.allow_umma;
+    b.f0_umma = opt.f0_umma;
     plan.params = Ref{SP_STATE, StateLayout::off_params};
     plan.cache = Ref{SP_STATE, StateLayout::off_cache};
     plan.pcm = Ref{SP_STATE, StateLayout::off_pcm};
     plan.audio = Ref{SP_STATE, StateLayout::off_audio};
     plan.n_lanes = 1;
+    plan.nb = opt.nb > 1 ? opt.nb : 1;
     const int N = g.n16k;
+    if (plan.nb > 1) {
+        // compact per-window state block: params | pitch cache | pcm window | audio out
+        if (kind != PLAN_INFER || !syi) { err = "batched plans exist for infer only"; return false; }
+        if (plan.nb > 64) { err = "at most 64 windows per launch"; return false; }
+        auto up = [](int64_t v) { return (v + 255) & ~int64_t(255); };
+        const int64_t off_pcm = StateLayout::off_cache + StateLayout::CACHE_LEN * 4;
+        const int64_t off_audio = off_pcm + up(int64_t(N > 0 ? N : 0) * 4);
+        plan.pcm = Ref{SP_STATE, off_pcm};
+        plan.audio = Ref{SP_STATE, off_audio};
+        plan.state_block = off_audio + up(int64_t(g.return_length > 0 ? g.return_length : 0) * (syi->sr / 100) * 4);
+    }
     if (kind != PLAN_KNN && (N <= 0 || N > StateLayout::PCM_CAP)) { err = "bad input length"; return false; }
 
     if (kind == PLAN_KNN) {
@@ -668,7 +682,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         plan.knn_q = Q;
         schedule_gemms(b);
     form_chains(b, opt);
-        plan.work_bytes = b.work + 256;
+        plan.work_bytes = (b.work + 256 + 255) & ~int64_t(255);
         return b.ok;
     }
     if (kind == PLAN_MEL) {
@@ -678,7 +692,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         plan.f0_T = o.T;
         schedule_gemms(b);
     form_chains(b, opt);
-        plan.work_bytes = b.work + 256;
+        plan.work_bytes = (b.work + 256 + 255) & ~int64_t(255);
         return b.ok;
     }
     if (kind == PLAN_HUBERT || kind == PLAN_FEATURE) {
@@ -694,7 +708,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         }
         schedule_gemms(b);
     form_chains(b, opt);
-        plan.work_bytes = b.work + 256;
+        plan.work_bytes = (b.work + 256 + 255) & ~int64_t(255);
         return b.ok;
     }
     // PLAN_PITCH / PLAN_INFER need the f0 window
@@ -706,7 +720,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         plan.f0_T = o.T;
         schedule_gemms(b);
     form_chains(b, opt);
-        plan.work_bytes = b.work + 256;
+        plan.work_bytes = (b.work + 256 + 255) & ~int64_t(255);
         return b.ok;
     }
     // ---- PLAN_INFER (rvc.rs:133-220) ---------------------------------------------------------
@@ -750,6 +764,10 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     if (opt.with_index) {
         const int k = opt.index_k, Nrows = opt.index_rows;
         if (k <= 0 || k > 16 || Nrows < k || C % 4 != 0 || C > 1024) { err = "bad index / k"; return false; }
+        if (opt.index_cols != C) {
+            err = "retrieval index is " + std::to_string(opt.index_cols) + " wide, the ContentVec features are " + std::to_string(C);
+            return false;
+        }
         const int parts = knn_parts(Q, C, k, Nrows);
         Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
@@ -778,7 +796,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         F0PostOp& p = op.f0p;
         p.f0 = fo.f0; p.cache = plan.cache; p.pitch = pitch; p.pitchf = pitchf; p.pitch_len = fo.T;
         p.shift = g.sf16k / 160; p.hubert_length = hubert_length; p.skip_head = skip; p.return_length = R;
-        p.cache_len = 1024;
+        p.cache_len = 1024; p.sequential = opt.sequential ? 1 : 0;
         p.mel_min = std::log(50.0f / 700.0f + 1.0f) * 1127.0f;   // rvc.rs:31-34 (f32)
         p.mel_max = std::log(500.0f / 700.0f + 1.0f) * 1127.0f;
     }
@@ -786,9 +804,9 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     if (audio_len > StateLayout::AUDIO_CAP) { err = "output too long"; return false; }
     build_synth(b, syn, *syi, phone, pitch, pitchf, plan.params, plan.audio, R, ml);
     plan.audio_len = audio_len;
-    schedule_gemms(b);
+    schedule_gemms(b, plan.nb);
     form_chains(b, opt);
-    plan.work_bytes = b.work + 256;
+    plan.work_bytes = (b.work + 256 + 255) & ~int64_t(255);
     return b.ok;
 }
 

@@ -221,6 +221,37 @@ class RvcInfer:
                      c_void_p(out_ptr), c_size_t(cap), byref(ln)))
         return ln.value
 
+    def infer_windows(self, pcm, n: int, sample_frame_16k_size: int, n_windows: int, pitch_shift, skip_head: int,
+                      return_length: int, max_batch: int = 0) -> np.ndarray:
+        """Offline conversion of this stream (BASELINE configs[2]): window w = pcm[w*sf16k, w*sf16k + n), `max_batch`
+        (<= 32) windows per launch; same results as n_windows successive infer() calls.  -> (n_windows, audio_len)."""
+        pcm = _f32(pcm)
+        out = np.empty(n_windows * (return_length * 480 + 16), np.float32)
+        al = c_size_t()
+        self._chk(self._L.rvc_infer_windows(self._h, pcm.ctypes.data_as(c_void_p), c_size_t(pcm.shape[0]), c_size_t(n),
+                                            c_uint32(sample_frame_16k_size), c_size_t(n_windows),
+                                            c_int32(0 if pitch_shift is None else int(pitch_shift)), c_uint32(skip_head),
+                                            c_uint32(return_length), out.ctypes.data_as(c_void_p), c_size_t(out.shape[0]),
+                                            byref(al), c_int32(max_batch)))
+        return out[:n_windows * al.value].reshape(n_windows, al.value)
+
+    def infer_windows_ptr(self, pcm_ptr: int, n_pcm: int, n: int, sample_frame_16k_size: int, n_windows: int, pitch_shift: int,
+                          skip_head: int, return_length: int, out_ptr: int, cap: int, device: bool, max_batch: int = 0) -> int:
+        al = c_size_t()
+        fn = self._L.rvc_infer_windows_dev if device else self._L.rvc_infer_windows
+        self._chk(fn(self._h, c_void_p(pcm_ptr), c_size_t(n_pcm), c_size_t(n), c_uint32(sample_frame_16k_size), c_size_t(n_windows),
+                     c_int32(pitch_shift), c_uint32(skip_head), c_uint32(return_length), c_void_p(out_ptr), c_size_t(cap),
+                     byref(al), c_int32(max_batch)))
+        return al.value
+
+    def get_last_window(self, window: int, name: str, dtype=np.float32) -> np.ndarray:
+        nb = c_size_t()
+        self._chk(self._L.rvc_get_last_window(self._h, c_int32(window), name.encode(), None, c_size_t(0), byref(nb)))
+        out = np.empty(nb.value // 4, dtype)
+        self._chk(self._L.rvc_get_last_window(self._h, c_int32(window), name.encode(), out.ctypes.data_as(c_void_p),
+                                              c_size_t(nb.value), byref(nb)))
+        return out
+
     # ------------------------------------------------------------------ extras
     def mel_extract(self, pcm) -> np.ndarray:
         """rmvpe.rs:159-205 -> (128, T)."""
@@ -344,3 +375,41 @@ class RvcInfer:
         n = c_uint64()
         self._chk(self._L.rvc_kernel_launches(self._h, byref(n)))
         return n.value
+
+
+def infer_batch(engines, pcms, sample_frame_16k_size: int, pitch_shift: int, skip_head: int, return_length: int):
+    """rvc_infer_batch: one window of each of `engines` (independent live streams, BASELINE configs[3]) in one call.
+    Streams of one device that share their models run as ONE batched plan.  -> list of audio arrays."""
+    L = lib()
+    n_ctx = len(engines)
+    pcms = [_f32(p) for p in pcms]
+    n = pcms[0].shape[0]
+    assert all(p.shape[0] == n for p in pcms)
+    cap = return_length * 480 + 16
+    outs = [np.empty(cap, np.float32) for _ in engines]
+    H = (c_void_p * n_ctx)(*[e.handle for e in engines])
+    P = (c_void_p * n_ctx)(*[p.ctypes.data_as(c_void_p) for p in pcms])
+    O = (c_void_p * n_ctx)(*[o.ctypes.data_as(c_void_p) for o in outs])
+    ln = c_size_t()
+    rc = L.rvc_infer_batch(H, c_size_t(n_ctx), P, c_size_t(n), c_uint32(sample_frame_16k_size), c_int32(pitch_shift),
+                           c_uint32(skip_head), c_uint32(return_length), O, c_size_t(cap), byref(ln))
+    if rc != 0:
+        raise _ERRORS.get(rc, RvcInferError)(L.rvc_last_error(engines[0].handle).decode())
+    return [o[:ln.value] for o in outs]
+
+
+def infer_batch_ptr(engines, pcm_ptrs, n: int, sample_frame_16k_size: int, pitch_shift: int, skip_head: int, return_length: int,
+                    out_ptrs, cap: int, device: bool) -> int:
+    """Raw-pointer form of rvc_infer_batch / rvc_infer_batch_dev (bench.py)."""
+    L = lib()
+    n_ctx = len(engines)
+    H = (c_void_p * n_ctx)(*[e.handle for e in engines])
+    P = (c_void_p * n_ctx)(*[c_void_p(p) for p in pcm_ptrs])
+    O = (c_void_p * n_ctx)(*[c_void_p(o) for o in out_ptrs])
+    ln = c_size_t()
+    fn = L.rvc_infer_batch_dev if device else L.rvc_infer_batch
+    rc = fn(H, c_size_t(n_ctx), P, c_size_t(n), c_uint32(sample_frame_16k_size), c_int32(pitch_shift), c_uint32(skip_head),
+            c_uint32(return_length), O, c_size_t(cap), byref(ln))
+    if rc != 0:
+        raise _ERRORS.get(rc, RvcInferError)(L.rvc_last_error(engines[0].handle).decode())
+    return ln.value

@@ -269,38 +269,90 @@ def test_knn_search_exact(env, n, c, q, k):
     e.close()
 
 
-def test_independent_streams_batch(env):
-    """streams shard with no shared state - two contexts on one GPU driven through
-    rvc_infer_batch give the same audio as each alone."""
-    import ctypes
+def _fresh_engine(env, seed, index_rate=None):
+    rb = env["rvc_b200"]
+    e = rb.RvcInfer(env["paths"]["data"], noise_seed=seed)
+    e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
+    if index_rate is not None:
+        e.load_index(env["paths"]["index"], index_rate)
+    return e
+
+
+BATCH_AUDIO_TOL = 1e-4   # batched vs single plans differ only in fp32 summation order (split-K factors, chains)
+
+
+@pytest.mark.parametrize("n_streams", [2, 8])
+def test_independent_streams_batch(env, n_streams):
+    """SURVEY 8e / BASELINE configs[3]: independent live streams of one GPU driven through rvc_infer_batch (ONE batched
+    plan: every kernel processes all streams) give what each stream gives alone - integers exact, audio to 1e-4 RMS -
+    over consecutive windows (per-stream pitch cache and call counter stay with their context)."""
     rb = env["rvc_b200"]
     g = env["pipeline"].BASELINE_GEOM
-    xs = [env["pipeline"].synthetic_pcm(g["n16k"], seed=20 + i) for i in range(2)]
-    solo = []
-    for i in range(2):
-        e = rb.RvcInfer(env["paths"]["data"], noise_seed=i)
-        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
-        solo.append(e.infer(xs[i], g["sf16k"], 12, g["skip_head"], g["return_length"]).copy())
+    nwin = 3
+    pcms = [env["pipeline"].synthetic_pcm(g["n16k"] + g["sf16k"] * nwin, seed=20 + i) for i in range(n_streams)]
+    solo, solo_pitch, solo_arg = [], [], []
+    for i in range(n_streams):
+        e = _fresh_engine(env, i, 0.5)
+        outs, ps, am = [], [], []
+        for w in range(nwin):
+            x = pcms[i][w * g["sf16k"]: w * g["sf16k"] + g["n16k"]]
+            outs.append(e.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy())
+            ps.append(e.get_last("pitch", np.int32)); am.append(e.get_last("f0_argmax", np.int32))
+        solo.append(outs); solo_pitch.append(ps); solo_arg.append(am)
         e.close()
-    es = []
-    for i in range(2):
-        e = rb.RvcInfer(env["paths"]["data"], noise_seed=i)
-        e.load_contentvec(2); e.load_f0(1); e.load_model(env["paths"]["model"])
-        es.append(e)
-    L = rb.lib()
-    n_out = g["return_length"] * 400
-    outs = [np.empty(n_out, np.float32) for _ in range(2)]
-    ctxs = (ctypes.c_void_p * 2)(*[e.handle for e in es])
-    pin = (ctypes.c_void_p * 2)(*[x.ctypes.data for x in xs])
-    pout = (ctypes.c_void_p * 2)(*[o.ctypes.data for o in outs])
-    ln = ctypes.c_size_t()
-    rc = L.rvc_infer_batch(ctxs, ctypes.c_size_t(2), pin, ctypes.c_size_t(g["n16k"]), ctypes.c_uint32(g["sf16k"]),
-                           ctypes.c_int32(12), ctypes.c_uint32(g["skip_head"]), ctypes.c_uint32(g["return_length"]),
-                           pout, ctypes.c_size_t(n_out), ctypes.byref(ln))
-    assert rc == 0 and ln.value == n_out
-    for i in range(2):
-        np.testing.assert_array_equal(outs[i], solo[i])
-        es[i].close()
+    es = [_fresh_engine(env, i, 0.5) for i in range(n_streams)]
+    for w in range(nwin):
+        xs = [pcms[i][w * g["sf16k"]: w * g["sf16k"] + g["n16k"]] for i in range(n_streams)]
+        outs = rb.infer_batch(es, xs, g["sf16k"], 12, g["skip_head"], g["return_length"])
+        assert es[0].plan_info()["windows"] == n_streams          # really one batched plan
+        for i in range(n_streams):
+            assert outs[i].shape == solo[i][w].shape
+            np.testing.assert_array_equal(es[0].get_last_window(i, "pitch", np.int32), solo_pitch[i][w])
+            np.testing.assert_array_equal(es[0].get_last_window(i, "f0_argmax", np.int32), solo_arg[i][w])
+            assert _rms(outs[i] - solo[i][w]) < BATCH_AUDIO_TOL, (w, i)
+            assert _rms(solo[i][w]) > 0.05
+    for e in es:
+        e.close()
+
+
+@pytest.mark.parametrize("n_windows,max_batch", [(6, 4), (32, 32)])
+def test_offline_windows_equal_single_calls(env, n_windows, max_batch):
+    """BASELINE configs[2] (offline, 32 windows per launch): rvc_infer_windows == the same windows through successive
+    rvc_infer calls (the reference's streaming loop, obs-rvc/src/lib.rs:659-707): coarse pitch and F0 argmax exact
+    (the pitch cache is updated window by window inside the plan), kNN indices equal, audio to 1e-4 RMS."""
+    g = env["pipeline"].BASELINE_GEOM
+    pcm = env["pipeline"].synthetic_pcm(g["n16k"] + g["sf16k"] * n_windows, seed=5)
+    e1 = _fresh_engine(env, 3, 0.5)
+    singles, pitch, arg, idx = [], [], [], []
+    for w in range(n_windows):
+        x = pcm[w * g["sf16k"]: w * g["sf16k"] + g["n16k"]]
+        singles.append(e1.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy())
+        pitch.append(e1.get_last("pitch", np.int32)); arg.append(e1.get_last("f0_argmax", np.int32)); idx.append(e1.get_last("knn_idx", np.int32))
+    e1.close()
+    e2 = _fresh_engine(env, 3, 0.5)
+    got = e2.infer_windows(pcm, g["n16k"], g["sf16k"], n_windows, 12, g["skip_head"], g["return_length"], max_batch)
+    assert got.shape == (n_windows, g["return_length"] * 400)
+    last_group = n_windows - ((n_windows - 1) // max_batch) * max_batch
+    base = n_windows - last_group
+    same_idx = []
+    for b in range(last_group if last_group > 1 else 0):
+        np.testing.assert_array_equal(e2.get_last_window(b, "pitch", np.int32), pitch[base + b])
+        np.testing.assert_array_equal(e2.get_last_window(b, "f0_argmax", np.int32), arg[base + b])
+        same_idx.append((e2.get_last_window(b, "knn_idx", np.int32) == idx[base + b]).mean())
+    if same_idx:
+        assert np.mean(same_idx) > 0.99
+    for w in range(n_windows):
+        assert _rms(got[w] - singles[w]) < BATCH_AUDIO_TOL, w
+    # the stream continues seamlessly after the batched call (cache + call counter carried over)
+    x = pcm[n_windows * g["sf16k"]: n_windows * g["sf16k"] + g["n16k"]]
+    e3 = _fresh_engine(env, 3, 0.5)
+    for w in range(n_windows):
+        e3.infer(pcm[w * g["sf16k"]: w * g["sf16k"] + g["n16k"]], g["sf16k"], 12, g["skip_head"], g["return_length"])
+    want = e3.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+    nxt = e2.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+    np.testing.assert_array_equal(e2.get_last("pitch", np.int32), e3.get_last("pitch", np.int32))
+    assert _rms(nxt - want) < BATCH_AUDIO_TOL
+    e2.close(); e3.close()
 
 
 def test_rvc_rpc_wire_protocol(env):
