@@ -137,6 +137,10 @@ int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t
 /* Exact brute-force L2 top-k on the loaded index (stress config 5). d2/idx: (q, k). */
 int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32_t k,
                    float* d2, int32_t* idx);
+/* Index widths C % 64 == 0, C <= 256 (v1 features, configs[4]) with k <= 8 run a tcgen05 candidate pass followed by an exact
+ * fp32 re-rank whose guard proves the top-k; a query whose guard fails is recomputed by an exact scan of all rows.
+ * Counts those recomputations since the index was set (0 on every test and bench input). */
+int rvc_knn_fallbacks(rvc_ctx* ctx, uint64_t* total);
 
 /* ---- streaming glue around the call ("next" row) ---------------------------------
  * rt_utils::envelop_mixing(input, output, sample_rate, mix_rate) - obs-rvc/src/rt_utils.rs:119-132.

@@ -53,6 +53,7 @@ struct ModelData {
     int64_t hilo16_off = 0, hilo16_plane = 0;  // fp16 split planes (launch.h DeviceBases)
     CvInfo cvi; F0Info f0i; SynInfo syi;
     int rows = 0, cols = 0;   // retrieval index only
+    int64_t planes_off = 0; float ymax2 = 0.f;   // retrieval index: fp16 planes behind the fp32 rows (kernels_knn_umma.cu)
     ~ModelData() { dev.release(); }
 };
 
@@ -188,6 +189,7 @@ struct rvc_ctx {
     int chain_grid_main = 0, chain_grid_side = 0, chain_side_max_m = 8;
     int f0_priority = 0;        // launch priority of the F0 lanes' kernels (highest stream priority of the device; RVC_F0_PRIO=0 disables)
     bool chain_force = false;   // RVC_CHAIN=2: keep chains even when several contexts share the device
+    bool knn_umma = true;       // RVC_KNN_UMMA=0: retrieval always on the fp32 scan (kernels_knn.cu)
 
     int fail(int code, const std::string& m) { err = m; return code; }
     int cuda_fail(cudaError_t e, const char* what) {
@@ -257,8 +259,14 @@ int issue_one(rvc_ctx* ctx, const Op& op, const DeviceBases& B, cudaStream_t s, 
         case OP_SINEGEN: *n += launch_sinegen(op.sine, B, s); break;
         case OP_AVG3: *n += launch_avg3(op.avg3, B, s); break;
         case OP_CONVPOST: *n += launch_convpost(op.cpost, B, s); break;
-        case OP_KNN_SCAN: *n += launch_knn_scan(op.kd, B, s); break;
-        case OP_KNN_SELECT: *n += launch_knn_select(op.ks, B, s); break;
+        case OP_KNN_SCAN:
+            if (op.kd.umma) {
+                const int l = launch_knn_scan_umma(op.kd, B, s);
+                if (l < 0) return ctx->fail(RVC_ERR_CUDA, "kNN tensor maps could not be encoded");
+                *n += l;
+            } else *n += launch_knn_scan(op.kd, B, s);
+            break;
+        case OP_KNN_SELECT: *n += op.ks.rerank ? launch_knn_rerank(op.ks, B, s) : launch_knn_select(op.ks, B, s); break;
         case OP_KNN_BLEND: *n += launch_knn_blend(op.kb, B, s); break;
         case OP_GATHER_ROWS: *n += launch_gather_rows(op.gather, B, s); break;
         case OP_FILL: CK(cudaMemsetAsync(B.p<uint8_t>(op.fill.dst), 0, op.fill.bytes, s)); break;
@@ -395,6 +403,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
     opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
     opt.chain_side_max_m = ctx->chain_side_max_m;
     opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;
+    if (ctx->index.loaded && ctx->knn_umma) { opt.index_planes_off = ctx->index.d->planes_off; opt.index_ymax2 = ctx->index.d->ymax2; }
     {   // RVC_F0_UMMA: 0 never, 1 always, default = batched plans only
         const char* ev = getenv("RVC_F0_UMMA");
         const bool want = ev ? ev[0] == '1' : key.nb > 1;
@@ -670,6 +679,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_UMMA"); ctx->allow_umma = !(ev && ev[0] == '0'); }
     { const char* ev = getenv("RVC_SYNC_EACH"); g_sync_each = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
+    { const char* ev = getenv("RVC_KNN_UMMA"); ctx->knn_umma = !(ev && ev[0] == '0'); }
     {   // persistent chains: CTA budgets (0 = off).  RVC_CHAIN=0 disables both.
         const char* ev = getenv("RVC_CHAIN"); const bool on = !(ev && ev[0] == '0');
         ctx->chain_force = ev && ev[0] == '2';
@@ -803,9 +813,15 @@ static int upload_index(rvc_ctx* ctx, const float* rows, size_t n, size_t c, std
     if (c % 4 != 0 || c > 1024 || n > 0x7fffffffull || n < size_t(ctx->cfg.index_k))
         return ctx->fail(RVC_ERR_BAD_SHAPE, "index must be N x C with C % 4 == 0, C <= 1024, N >= k");
     out = std::make_shared<ModelData>();
-    CK(cudaMalloc(&out->dev.d, n * c * sizeof(float)));
-    out->dev.bytes = n * c * sizeof(float);
-    CK(cudaMemcpy(out->dev.d, rows, out->dev.bytes, cudaMemcpyHostToDevice));
+    const size_t row_bytes = (n * c * sizeof(float) + 1023) & ~size_t(1023);
+    const bool planes = knn_umma_ok(int(c), 1);   // widths the tensor-core candidate pass serves (C % 64 == 0, C <= 256)
+    CK(cudaMalloc(&out->dev.d, row_bytes + (planes ? size_t(knn_umma_planes_bytes(int(n), int(c))) : 0)));
+    out->dev.bytes = row_bytes;
+    CK(cudaMemcpy(out->dev.d, rows, n * c * sizeof(float), cudaMemcpyHostToDevice));
+    if (planes) {
+        out->planes_off = int64_t(row_bytes);
+        out->ymax2 = launch_knn_build_planes(reinterpret_cast<const float*>(out->dev.d), int(n), int(c), out->dev.d + row_bytes, ctx->streams[0]);
+    }
     CK(cudaDeviceSynchronize());
     out->rows = int(n); out->cols = int(c);
     return RVC_OK;
@@ -1001,6 +1017,19 @@ int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32
     CK(cudaMemcpyAsync(idx, e->work.d + e->plan.find("knn_idx")->ref.off, q * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(d2, e->work.d + e->plan.find("knn_d2")->ref.off, q * k * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return RVC_OK;
+}
+
+int rvc_knn_fallbacks(rvc_ctx* ctx, uint64_t* total) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!total) return ctx->fail(RVC_ERR_INVALID_ARG, "null argument");
+    *total = 0;
+    if (!ctx->index.loaded || ctx->index.d->planes_off == 0) return RVC_OK;
+    ctx->sync_all();
+    const int64_t off = ctx->index.d->planes_off + knn_umma_counters_off(ctx->index_rows, ctx->index_c);
+    unsigned int v = 0;
+    CK(cudaMemcpy(&v, ctx->index.d->dev.d + off, 4, cudaMemcpyDeviceToHost));
+    *total = v;
     return RVC_OK;
 }
 
@@ -1333,6 +1362,13 @@ int rvc_debug_chain_stamps(rvc_ctx* ctx, int chain, long long* out2048) {
     CK(cudaStreamSynchronize(ctx->streams[0]));
     chain_debug_read(out2048, 2048);
     chain_debug_read2(out2048 + 2048, 512);
+    return RVC_OK;
+}
+
+int rvc_debug_knn_stamps(rvc_ctx* ctx, long long* out256) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->sync_all();
+    rvc::knn_umma_debug_read(out256);
     return RVC_OK;
 }
 

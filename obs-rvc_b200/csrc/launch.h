@@ -48,6 +48,12 @@ int launch_convpost(const ConvPostOp& o, const DeviceBases& B, cudaStream_t stre
 int launch_knn_scan(const KnnScanOp& o, const DeviceBases& B, cudaStream_t stream);
 int launch_knn_select(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t stream);
 int launch_knn_blend(const KnnBlendOp& o, const DeviceBases& B, cudaStream_t stream);
+// tensor-core candidate pass + exact re-rank (kernels_knn_umma.cu); scan returns -1 when the tensor maps cannot be built
+int launch_knn_scan_umma(const KnnScanOp& o, const DeviceBases& B, cudaStream_t stream);
+int launch_knn_rerank(const KnnSelectOp& o, const DeviceBases& B, cudaStream_t stream);
+// builds [y_hi | y_lo' | |y|^2 | counters] at `planes` (knn_umma_planes_bytes) from N x C fp32 rows; returns max |y|^2 (synchronises)
+void knn_umma_debug_read(long long* out);   // [8 events][32 tiles] clock64 stamps of CTA 0 (build with -DRVC_KU_STAMPS)
+float launch_knn_build_planes(const float* index, int N, int C, uint8_t* planes, cudaStream_t stream);
 int launch_gather_rows(const GatherRowsOp& o, const DeviceBases& B, cudaStream_t stream);
 
 // streaming glue ("next" row #1): obs-rvc/src/rt_utils.rs + lib.rs:779-791 on the device

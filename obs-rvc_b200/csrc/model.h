@@ -75,6 +75,8 @@ struct PlanOptions {
     int32_t nb = 1;
     bool sequential = false;
     int32_t index_cols = 0;        // width of the loaded retrieval index (must equal the ContentVec width)
+    int64_t index_planes_off = 0;  // > 0: the index carries fp16 planes (tensor-core candidate pass, kernels_knn_umma.cu)
+    float index_ymax2 = 0.f;       // max |y|^2 over the index rows (error bound of the candidate pass)
     bool f0_umma = false;          // RMVPE's wide levels on the tcgen05 FP16-split kernel (batched plans; needs the f0 weight planes)
 };
 

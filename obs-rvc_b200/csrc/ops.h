@@ -141,9 +141,16 @@ struct ConvPostOp {  // tanh(conv1d(Cin->1, k)) on halo-padded channels-last inp
 struct KnnScanOp {  // per-part top-k of D[q,n] = sum_c (x[q,c]-index[n,c])^2; the parts partition the rows (how is up to the executor)
     Ref index; Ref queries; int64_t ldq = 0; Ref cand_d, cand_i;  // [Q][parts][k]
     int32_t N = 0, C = 0, Q = 0, k = 0, parts = 0;
+    // umma = 1: candidate pass on the tensor cores (kernels_knn_umma.cu): cand = [Q][parts][KNN_UMMA_KC] approximate
+    // scores |y|^2 - 2 x.y; the fp16 planes of the index sit planes_off bytes behind its fp32 rows
+    int32_t umma = 0; int64_t planes_off = 0;
 };
 struct KnnSelectOp {  // k smallest (d, idx) per query over parts*k candidates, ascending
     Ref cand_d, cand_i; Ref idx; Ref d2; int32_t Q = 0, k = 0, parts = 0;
+    // rerank = 1 (after a umma scan): the KNN_UMMA_KC best candidates by approximate score are re-evaluated exactly in
+    // fp32 (the scan's summation order), a guard proves the top-k, a failed guard falls back to the exact scan of all rows
+    int32_t rerank = 0; Ref index, queries; int64_t ldq = 0; int32_t N = 0, C = 0; float ymax2 = 0.f;
+    int64_t planes_off = 0, fallback_off = 0;
 };
 struct KnnBlendOp {  // out[Q,C] = rate * sum_i w_i index[idx_i] + (1-rate) x ; w = (1/d2)^2 normalised
     Ref index; Ref idx; Ref d2; Ref x; int64_t ldx = 0; Ref out; Ref params; int32_t C = 0, Q = 0, k = 0;
@@ -199,6 +206,18 @@ inline int knn_parts(int Q, int C, int k, int n_rows) {
     const int p = knn_two_ctas_per_sm(Q, C, k) ? 2 * KNN_PARTS : KNN_PARTS;
     return p < n_rows ? p : n_rows;
 }
+
+// tensor-core candidate pass of the retrieval (kernels_knn_umma.cu): tile of index rows, candidates per query and CTA
+constexpr int KNN_UMMA_BN = 32, KNN_UMMA_KC = 16;
+inline bool knn_umma_ok(int C, int k) { return C % 64 == 0 && C >= 64 && C <= 256 && k >= 1 && k <= 8; }
+inline int knn_umma_rows_padded(int n_rows) { return (n_rows + KNN_UMMA_BN - 1) / KNN_UMMA_BN * KNN_UMMA_BN; }
+inline int knn_umma_parts(int n_rows) { const int t = knn_umma_rows_padded(n_rows) / KNN_UMMA_BN; return t < 148 ? t : 148; }
+// The planes are stored tile by tile in exactly the shared-memory image the MMA reads (K-major SWIZZLE_128B, per 64-wide
+// k-block the y_hi rows then the y_lo' rows), followed by the tile's |y|^2: one contiguous cp.async.bulk per tile.
+inline int64_t knn_umma_tile_bytes(int C) { return int64_t(C / 64) * 2 * KNN_UMMA_BN * 128 + KNN_UMMA_BN * 4; }
+// [tiles x tile image | fallback counter, max |y|^2 bits]
+inline int64_t knn_umma_counters_off(int n_rows, int C) { return int64_t(knn_umma_rows_padded(n_rows) / KNN_UMMA_BN) * knn_umma_tile_bytes(C); }
+inline int64_t knn_umma_planes_bytes(int n_rows, int C) { return knn_umma_counters_off(n_rows, C) + 256; }
 
 // A run of consecutive same-lane ops executed by one persistent cooperative kernel (chain.h).
 // phase[i] is the barrier phase of op first+i: ops of one phase touch disjoint buffers.

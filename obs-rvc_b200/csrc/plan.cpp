@@ -496,6 +496,14 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
     return audio;
 }
 
+// second stage of a tensor-core retrieval: exact re-rank of the candidates (kernels_knn_umma.cu)
+void knn_rerank_setup(KnnSelectOp& ks, bool um, const KnnScanOp& kd, const PlanOptions& opt) {
+    if (!um) return;
+    ks.rerank = 1; ks.index = kd.index; ks.queries = kd.queries; ks.ldq = kd.ldq; ks.N = kd.N; ks.C = kd.C; ks.ymax2 = opt.index_ymax2;
+    ks.planes_off = opt.index_planes_off;
+    ks.fallback_off = opt.index_planes_off + knn_umma_counters_off(kd.N, kd.C);
+}
+
 // chooses the kernel variant / split-K factor of every GEMM and allocates its scratch
 void schedule_gemms(PB& b, int nb = 1) {
     for (Op& op : b.plan.ops) {
@@ -671,14 +679,16 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         // queries staged in the audio buffer region by the caller: [Q, C]; results -> work
         const int Q = g.n16k, C = g.sf16k, k = g.return_length, Nrows = opt.index_rows;
         if (Q <= 0 || C <= 0 || C % 4 != 0 || C > 1024 || k <= 0 || k > 16 || Nrows < k) { err = "bad kNN shape"; return false; }
-        const int parts = knn_parts(Q, C, k, Nrows);
-        Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
+        const bool um = opt.index_planes_off > 0 && knn_umma_ok(C, k);
+        const int parts = um ? knn_umma_parts(Nrows) : knn_parts(Q, C, k, Nrows), kc = um ? KNN_UMMA_KC : k;
+        Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * kc), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * kc, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
         Op& a = b.add(OP_KNN_SCAN, "knn_scan");
         a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = plan.audio; a.kd.ldq = C; a.kd.cand_d = cd; a.kd.cand_i = ci;
-        a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q; a.kd.k = k; a.kd.parts = parts;
+        a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q; a.kd.k = k; a.kd.parts = parts; a.kd.umma = um ? 1 : 0; a.kd.planes_off = opt.index_planes_off;
         Op& s = b.add(OP_KNN_SELECT, "knn_select");
         s.ks.cand_d = cd; s.ks.cand_i = ci; s.ks.idx = idx; s.ks.d2 = d2; s.ks.Q = Q; s.ks.k = k; s.ks.parts = parts;
+        knn_rerank_setup(s.ks, um, a.kd, opt);
         plan.knn_q = Q;
         schedule_gemms(b);
     form_chains(b, opt);
@@ -768,15 +778,17 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
             err = "retrieval index is " + std::to_string(opt.index_cols) + " wide, the ContentVec features are " + std::to_string(C);
             return false;
         }
-        const int parts = knn_parts(Q, C, k, Nrows);
-        Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * k), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * k, true);
+        const bool um = opt.index_planes_off > 0 && knn_umma_ok(C, k);
+        const int parts = um ? knn_umma_parts(Nrows) : knn_parts(Q, C, k, Nrows), kc = um ? KNN_UMMA_KC : k;
+        Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * kc), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * kc, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
         Ref xb = b.alloc("knn_blend", int64_t(Q) * C);
         Op& a = b.add(OP_KNN_SCAN, "knn_scan");
         a.kd.index = Ref{SP_IDX, 0}; a.kd.queries = x.plus(int64_t(first) * C); a.kd.ldq = C; a.kd.cand_d = cd;
-        a.kd.cand_i = ci; a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q; a.kd.k = k; a.kd.parts = parts;
+        a.kd.cand_i = ci; a.kd.N = Nrows; a.kd.C = C; a.kd.Q = Q; a.kd.k = k; a.kd.parts = parts; a.kd.umma = um ? 1 : 0; a.kd.planes_off = opt.index_planes_off;
         Op& s = b.add(OP_KNN_SELECT, "knn_select");
         s.ks.cand_d = cd; s.ks.cand_i = ci; s.ks.idx = idx; s.ks.d2 = d2; s.ks.Q = Q; s.ks.k = k; s.ks.parts = parts;
+        knn_rerank_setup(s.ks, um, a.kd, opt);
         Op& m = b.add(OP_KNN_BLEND, "knn_blend");
         m.kb.index = Ref{SP_IDX, 0}; m.kb.idx = idx; m.kb.d2 = d2; m.kb.x = x.plus(int64_t(first) * C); m.kb.ldx = C;
         m.kb.out = xb; m.kb.params = plan.params; m.kb.C = C; m.kb.Q = Q; m.kb.k = k;

@@ -272,6 +272,12 @@ class RvcInfer:
                                          idx.ctypes.data_as(c_void_p)))
         return d2, idx
 
+    def knn_fallbacks(self) -> int:
+        """Queries whose tensor-core candidate set failed its guard and were recomputed by the exact scan."""
+        n = c_uint64()
+        self._chk(self._L.rvc_knn_fallbacks(self._h, byref(n)))
+        return n.value
+
     # ------------------------------------------------------------------ streaming glue (next row #1)
     def envelop_mixing(self, inp, out, sample_rate: int, mix_rate: float, want_rms: bool = False):
         """rt_utils::envelop_mixing (obs-rvc/src/rt_utils.rs:119-132); returns the mixed output
