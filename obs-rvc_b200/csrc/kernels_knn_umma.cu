@@ -147,7 +147,7 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t t0, uint32_t t1, float* v, 
 __device__ long long g_ku_stamp[8 * 32];   // [event][tile < 32] clock64 of CTA 0: 0 producer empty-ok, 1 producer issued, 2 MMA acc-empty-ok, 3 MMA full-ok,
                                            // 4 MMA issued, 5 epilogue acc-full-ok, 6 epilogue ld done, 7 epilogue tile done
 #ifdef RVC_KU_STAMPS
-#define KU_STAMP(e, i) do { if (blockIdx.x == 0 && (i) < 32) g_ku_stamp[(e) * 32 + (i)] = clock64(); } while (0)
+#define KU_STAMP(e, i) do { if (blockIdx.x == 0 && (i) >= 180 && (i) < 212) g_ku_stamp[(e) * 32 + ((i) - 180)] = clock64(); } while (0)   // late tiles
 #else
 #define KU_STAMP(e, i) do { } while (0)
 #endif
@@ -157,9 +157,10 @@ struct KuCfg {
     // the queries (A operand) live in TENSOR memory for the whole scan: an MMA whose A comes from shared memory pays
     // ~100 cycles per instruction for the operand fetch whatever N (measured: t = 100 + N/2 cycles at M = 128, K = 16)
     static constexpr int STAGE_BYTES = KB * 2 * KU_BN * 128;         // y_hi | y_lo' per k-block
-    static constexpr int RING = (200 * 1024 - 1024 - KU_YN_SLOTS * KU_BN * 4) / STAGE_BYTES;
+    static constexpr int HIT_BYTES = 4 * 32 * 32 * 4;                 // per epilogue warp: the scores of one tile, [element][lane]
+    static constexpr int RING = (200 * 1024 - 1024 - KU_YN_SLOTS * KU_BN * 4 - HIT_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = RING > 8 ? 8 : RING;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + KU_YN_SLOTS * KU_BN * 4;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + KU_YN_SLOTS * KU_BN * 4 + HIT_BYTES;
     static_assert(STAGES + 3 <= KU_YN_SLOTS, "|y|^2 ring too short");
     static_assert(STAGES >= 2, "ring too small");
 };
@@ -178,6 +179,7 @@ knn_umma_scan_kernel(const uint8_t* __restrict__ planes, const float* __restrict
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sB = smem;
     float* sYn = reinterpret_cast<float*>(sB + STAGES * Cfg::STAGE_BYTES);
+    float* sHit = sYn + KU_YN_SLOTS * KU_BN;
 
     const int tiles_total = (N + KU_BN - 1) / KU_BN;
     const int per = (tiles_total + gridDim.x - 1) / gridDim.x;
@@ -306,13 +308,29 @@ knn_umma_scan_kernel(const uint8_t* __restrict__ planes, const float* __restrict
             const int row0 = (t_begin + i) * KU_BN;
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(-2.0f, fmaf(c[j], 1.0f / KU_LO_SCALE, v[j]), yn[j]);   // |y|^2 - 2 x.y
+            // hits of the whole tile against the threshold at tile start (a superset: thresholds only fall), OR-reduced
+            // over the warp in one redux: elements where no lane has a hit are skipped by a warp-uniform branch.  (One vote +
+            // branch per element serialised the 32 elements of a tile behind each other: ~100 cycles each, measured.)
+            unsigned hm = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const bool hit = v[j] < thr;
-                if (__any_sync(0xffffffffu, hit)) {
-                    if (hit) {
+            for (int j = 0; j < 32; ++j) hm |= (v[j] < thr) ? (1u << j) : 0u;
+            const unsigned am = __reduce_or_sync(0xffffffffu, hm);
+            if (am) {
+                // scores of the tile -> this warp's shared-memory strip, then a truly dynamic loop over the set bits only
+                // (an unrolled loop of uniform bit tests was predicated by the compiler: all 32 bodies ran whenever am != 0)
+                float* strip = sHit + warp * (32 * 32);
 #pragma unroll
-                        for (int u = 0; u < KC; ++u) { const bool w = u == maxpos; cs[u] = w ? v[j] : cs[u]; ci[u] = w ? row0 + j : ci[u]; }
+                for (int j = 0; j < 32; ++j) strip[j * 32 + lane] = v[j];
+                __syncwarp();
+                unsigned rem = am;
+#pragma unroll 1
+                while (rem) {
+                    const int j = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    const float sv = strip[j * 32 + lane];
+                    if (sv < thr) {
+#pragma unroll
+                        for (int u = 0; u < KC; ++u) { const bool w = u == maxpos; cs[u] = w ? sv : cs[u]; ci[u] = w ? row0 + j : ci[u]; }
                         float m[KC]; int mp[KC];
 #pragma unroll
                         for (int u = 0; u < KC; ++u) { m[u] = cs[u]; mp[u] = u; }
@@ -323,6 +341,7 @@ knn_umma_scan_kernel(const uint8_t* __restrict__ planes, const float* __restrict
                         thr = m[0]; maxpos = mp[0];
                     }
                 }
+                __syncwarp();
             }
             if (tid == 0) KU_STAMP(7, i);
         }

@@ -17,6 +17,6 @@ buf = (ctypes.c_longlong * 256)()
 rvc_b200.lib().rvc_debug_knn_stamps(eng.handle, buf)
 st = np.array(buf[:], np.int64).reshape(8, 32)
 t0 = st[st > 0].min()
-names = ["prod empty-ok", "prod issued", "mma acc-empty-ok", "mma full-ok", "mma issued", "epi acc-full-ok", "epi ld done", "epi tile done"]
-for i in range(8, 20):
-    print(f"tile {i:2d}: " + "  ".join(f"{names[e]}={st[e, i] - t0:7d}" for e in range(8)))
+names = ["Pe", "Pi", "Mae", "Mf", "Mi", "Eaf", "Eld", "Edone"]
+for i in range(4, 16):
+    print(f"tile {180+i:3d}: " + "  ".join(f"{names[e]}={st[e, i] - t0:7d}" for e in range(8)))
