@@ -2,6 +2,7 @@
 """bench.py - headline benchmark of the per-audio-window hot path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload stream1|offline32|streams8|knn1m]
 
 A "step" is one 160 ms @16 kHz window (2560 new samples; the call sees the last 35 840 samples)
 through `rvc_infer` of configs[1]: single stream, batch 1, ContentVec-768 + RMVPE + 40k x 768
@@ -11,6 +12,10 @@ index (k=8, index_rate 0.5) + NSF-HiFiGAN 40k, seeded synthetic weights, synthet
   e2e   : windows/s through the host-buffer C ABI call (rvc_infer): pinned H2D of the window and
           D2H of the audio inside the timed region, one window in flight (batch-1 latency bound);
   p50/p99_ms : per-window host-observed latency of that call.
+The default line (workload stream1 = BASELINE configs[1], the metric's configuration) also carries the other configs
+as sub-objects: `multi_stream` (configs[3] shape: 8 live streams per GPU through ONE batched plan, rvc_infer_batch),
+`offline32` (configs[2]: 32 consecutive windows of one stream per launch, rvc_infer_windows) and `knn1m` (configs[4]:
+1 M x 256 index, 128 queries, top-4 per GPU).  `--workload X` prints X's own line instead (value / e2e / roofline of X).
 N > 1 (torchrun): one process per GPU, each with its own independent stream (the path shards by
 stream, SURVEY 8e - no data-path collective), NCCL only for the barrier and the max-time reduce.
 `--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores.
@@ -139,6 +144,152 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def traffic_of(kernel_name):
+    """dram__bytes_read + write per launch from the committed `ncu --set full` summaries (profiles/ncu_traffic.json:
+    {kernel name prefix: {"bytes": ..., "source": "profiles/<file>"}}); None when no capture of that kernel is committed."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    for key, val in table.items():
+        if kernel_name.startswith(key):
+            return val
+    return None
+
+
+def bench_multi_stream(rvc_b200, torch, paths, eng, g, pcm_dev, pin_in, dev, local_rank, rank, world, dist, n_streams, ksteps, total):
+    """configs[3] shape: S independent live streams on this GPU, one window of each per call of rvc_infer_batch(_dev):
+    ONE batched plan (every kernel processes all S streams, weights read once per round), per-stream pitch cache /
+    call counter / noise seed.  Device-resident value (CUDA events on the plan's stream) and host-buffer e2e."""
+    n16k, sf, skip, R = g["n16k"], g["sf16k"], g["skip_head"], g["return_length"]
+    out_len = R * 400
+    engs = [eng]
+    for i in range(1, n_streams):
+        e2 = rvc_b200.RvcInfer(paths["data"], device=local_rank, noise_seed=rank * 1000 + i)
+        e2.load_contentvec(2); e2.load_f0(1); e2.load_model(paths["model"]); e2.load_index(paths["index"], 0.5)
+        engs.append(e2)
+    outs = [torch.empty(out_len, dtype=torch.float32, device=dev) for _ in engs]
+    pin_outs = [torch.empty(out_len, dtype=torch.float32).pin_memory() for _ in engs]
+
+    def ptrs(base, i):
+        return [base.data_ptr() + 4 * (((i + 7 * s_) % total) * sf) for s_ in range(n_streams)]
+
+    def step_dev(i):
+        rvc_b200.infer_batch_ptr(engs, ptrs(pcm_dev, i), n16k, sf, 12, skip, R, [o.data_ptr() for o in outs], out_len, True)
+
+    def step_host(i):
+        rvc_b200.infer_batch_ptr(engs, ptrs(pin_in, i), n16k, sf, 12, skip, R, [o.data_ptr() for o in pin_outs], out_len, False)
+
+    for i in range(4):
+        step_dev(i)
+    eng.sync()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    eng.event_record(2)
+    for i in range(ksteps):
+        step_dev(4 + i)
+    eng.event_record(3)
+    eng.sync()
+    ms_dev = eng.event_elapsed_ms(2, 3)
+    lat = []
+    for i in range(3):
+        step_host(i)
+    t0 = time.perf_counter()
+    for i in range(ksteps):
+        t1 = time.perf_counter()
+        step_host(3 + i)
+        lat.append((time.perf_counter() - t1) * 1e3)
+    s_host = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([ms_dev, s_host], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, s_host = float(t[0].item()), float(t[1].item())
+    info = eng.plan_info()
+    res = {"streams_per_gpu": n_streams, "value": world * n_streams * ksteps / (ms_dev * 1e-3), "unit": UNIT,
+           "ms_per_round": ms_dev / ksteps, "rounds": ksteps, "windows_per_launch": info.get("windows"),
+           "e2e": {"value": world * n_streams * ksteps / s_host, "unit": UNIT, "h2d_bytes_per_step": n_streams * n16k * 4,
+                   "d2h_bytes_per_step": n_streams * out_len * 4},
+           "round_latency_ms_p50": float(np.percentile(lat, 50)),
+           "timing": "value: CUDA events on the batched plan's stream, MAX over ranks; e2e: host clock around rvc_infer_batch with pinned host buffers",
+           "note": "one batched plan per GPU: every kernel processes all streams of the GPU, weights read once per round"}
+    for e_ in engs[1:]:
+        e_.close()
+    return res
+
+
+def bench_offline(torch, eng, g, pcm_dev, pin_in, dev, nb, groups, dist, world):
+    """configs[2]: offline conversion of one stream, `nb` consecutive windows per launch (rvc_infer_windows)."""
+    n16k, sf, skip, R = g["n16k"], g["sf16k"], g["skip_head"], g["return_length"]
+    out_len = R * 400
+    nwin = nb * groups
+    need = n16k + sf * nwin
+    if pcm_dev.numel() < need + sf * nb:
+        groups = max(1, (pcm_dev.numel() - n16k) // (sf * nb) - 1)
+        nwin = nb * groups
+    out = torch.empty(nwin * out_len, dtype=torch.float32, device=dev)
+    pin_out = torch.empty(nwin * out_len, dtype=torch.float32).pin_memory()
+    eng.reset_state()
+    eng.infer_windows_ptr(pcm_dev.data_ptr(), pcm_dev.numel(), n16k, sf, nb, 12, skip, R, out.data_ptr(), out.numel(), True, nb)   # warm: plan + graph
+    eng.infer_windows_ptr(pcm_dev.data_ptr(), pcm_dev.numel(), n16k, sf, nb, 12, skip, R, out.data_ptr(), out.numel(), True, nb)
+    eng.sync()
+    if dist is not None:
+        dist.barrier()
+    l0 = eng.kernel_launches()
+    eng.event_record(4)
+    eng.infer_windows_ptr(pcm_dev.data_ptr(), pcm_dev.numel(), n16k, sf, nwin, 12, skip, R, out.data_ptr(), out.numel(), True, nb)
+    eng.event_record(5)
+    eng.sync()
+    ms_dev = eng.event_elapsed_ms(4, 5)
+    launches = eng.kernel_launches() - l0
+    t0 = time.perf_counter()
+    eng.infer_windows_ptr(pin_in.data_ptr(), pin_in.numel(), n16k, sf, nwin, 12, skip, R, pin_out.data_ptr(), pin_out.numel(), False, nb)
+    s_host = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([ms_dev, s_host], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, s_host = float(t[0].item()), float(t[1].item())
+    return {"windows_per_launch": nb, "windows": nwin, "value": world * nwin / (ms_dev * 1e-3), "unit": UNIT, "ms_per_launch": ms_dev / groups,
+            "realtime_factor": nwin * 0.16 / (ms_dev * 1e-3), "gpu_launches": int(launches),
+            "e2e": {"value": world * nwin / s_host, "unit": UNIT, "h2d_bytes_per_step": (n16k + (nb - 1) * sf) * 4, "d2h_bytes_per_step": nb * out_len * 4},
+            "timing": "value: CUDA events around rvc_infer_windows_dev over all groups; e2e: host clock around rvc_infer_windows with pinned host buffers"}
+
+
+def bench_knn(rvc_b200, paths, local_rank, pk, n=1 << 20, c=256, q=128, k=4, reps=20):
+    """configs[4]: N x C index, Q queries per launch, top-k on one GPU.  Device time of the scan (+ re-rank) via the per-op
+    replay, host-observed time of rvc_knn_search (H2D of the queries + D2H of the result inside)."""
+    eng = rvc_b200.RvcInfer(paths["data"], device=local_rank, index_k=k)
+    rng = np.random.default_rng(2)
+    rows = rng.standard_normal((n, c), dtype=np.float32) * np.float32(0.34)
+    eng.set_index(rows, 0.5)
+    x = rng.standard_normal((q, c), dtype=np.float32) * np.float32(0.34)
+    d2, idx = eng.knn_search(x, k)
+    # spot-check 4 queries against a float64 brute force (the full literal-equality check is tests/test_gpu_parity.py)
+    for qi in range(0, q, q // 4):
+        d = ((rows.astype(np.float64) - x[qi].astype(np.float64)) ** 2).sum(1)
+        assert np.array_equal(np.asarray(idx[qi]), np.argsort(d, kind="stable")[:k]), "kNN spot check failed"
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); eng.knn_search(x, k); ts.append(time.perf_counter() - t0)
+    ops = {o["name"]: o["us"] for o in eng.profile_ops(10)}
+    scan_us, rerank_us = ops.get("knn_scan", 0.0), ops.get("knn_select", 0.0)
+    fallbacks = eng.knn_fallbacks()
+    eng.close()
+    bytes_alg = 4.0 * n * c          # the index is read once (as two fp16 planes = 4 B per element; fp32 rows only for the re-rank gather)
+    gbs = bytes_alg / (scan_us * 1e-6) / 1e9
+    host_s = float(np.median(ts))
+    tr = traffic_of("knn_umma_scan_kernel")
+    return {"workload": f"configs[4]: {n} x {c} f32 index, {q} queries per launch, top-{k}, one GPU", "value": q / ((scan_us + rerank_us) * 1e-6),
+            "unit": "queries/s", "scan_us": scan_us, "rerank_us": rerank_us, "guard_fallbacks": int(fallbacks),
+            "e2e": {"value": q / host_s, "unit": "queries/s", "search_us": host_s * 1e6, "h2d_bytes_per_step": q * c * 4, "d2h_bytes_per_step": q * k * 8},
+            "roofline": {"bound": "hbm", "kernel": "knn_umma_scan_kernel(tcgen05 candidate pass)", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": gbs / pk["hbm"], "peak_source": pk["src"], "algorithmic_bytes_per_launch": bytes_alg,
+                         "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,7 +299,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="also dump per-op device times to gpurun_out/")
     ap.add_argument("--streams", type=int, default=8,
-                    help="supplementary: independent live streams per GPU sharing one set of weights (configs[3]); 0 = skip")
+                    help="independent live streams per GPU through one batched plan (configs[3]); 0 = skip")
+    ap.add_argument("--workload", default="stream1", choices=["stream1", "offline32", "streams8", "knn1m"],
+                    help="stream1 = BASELINE configs[1] (the metric's configuration, default); the others print their own line")
+    ap.add_argument("--quick", action="store_true", help="stream1 only: skip the offline32 / knn1m sub-objects")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,7 +332,7 @@ def main():
     paths = data_dir()
     g = pipeline.BASELINE_GEOM
     n16k, sf, skip, R = g["n16k"], g["sf16k"], g["skip_head"], g["return_length"]
-    total = args.warmup + args.steps
+    total = max(args.warmup + args.steps, 32 * 7 + 8)
     pcm_all = pipeline.synthetic_pcm(n16k + sf * (total + 1), seed=rank)
 
     eng = rvc_b200.RvcInfer(paths["data"], device=local_rank, noise_seed=rank)
@@ -243,45 +397,16 @@ def main():
     sampler.join(timeout=2)
     e2e = aggregate_throughput(args.steps, world, e2e_s)
 
-    # ---- supplementary: S independent streams on this GPU (configs[3] shape: 8 per GPU), weights shared --
+    # ---- configs[3] shape: S independent live streams on this GPU through one batched plan --------
     multi = None
     if args.streams > 1:
-        engs = [eng]
-        for i in range(1, args.streams):
-            e2 = rvc_b200.RvcInfer(paths["data"], device=local_rank, noise_seed=rank * 1000 + i)
-            e2.load_contentvec(2); e2.load_f0(1); e2.load_model(paths["model"]); e2.load_index(paths["index"], 0.5)
-            engs.append(e2)
-        outs = [torch.empty(out_len, dtype=torch.float32, device=dev) for _ in engs]
-        ksteps = max(20, args.steps // 4)
-
-        def step_all(i):
-            for e_, o_ in zip(engs, outs):
-                e_.infer_ptr(pcm_dev.data_ptr() + 4 * (i % total) * sf, n16k, sf, 12, skip, R, o_.data_ptr(), out_len, True)
-
-        for i in range(5):
-            step_all(i)
-        for e_ in engs:
-            e_.sync()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for i in range(ksteps):
-            step_all(5 + i)
-        for e_ in engs:
-            e_.sync()
-        torch.cuda.synchronize(dev)
-        ms_t = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([ms_t], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_t = float(t.item())
-        multi = {"streams_per_gpu": args.streams, "value": world * args.streams * ksteps / ms_t, "unit": UNIT,
-                 "ms_per_round": ms_t / ksteps * 1e3,
-                 "timing": "host wall clock around K rounds of S async windows, device synchronised on both sides",
-                 "note": "plans built without persistent chains while several contexts share the device"}
-        for e_ in engs[1:]:
-            e_.close()
+        multi = bench_multi_stream(rvc_b200, torch, paths, eng, g, pcm_dev, pin_in, dev, local_rank, rank, world, dist, args.streams,
+                                   max(20, args.steps // 4), total)
+    # ---- configs[2]: offline, 32 consecutive windows of this stream per launch --------------------
+    offline = None
+    if not args.quick:
+        offline = bench_offline(torch, eng, g, pcm_dev, pin_in, dev, 32, max(2, min(6, total // 32 - 1)), dist, world)
+    eng.reset_state()
 
     # ---- roofline of the dominant kernel (rank 0): per-op device times via CUDA events ----------
     roof = None
@@ -326,21 +451,27 @@ def main():
 
         order = sorted(fam.items(), key=lambda kv: -kv[1]["us"])
         roof = roof_of(*order[0])
-        # dram__bytes_read+write of one launch of this kernel under `ncu --set full` (profiles/r01_e_prof_umma.md: grid
-        # (4,2,8) = a HiFiGAN stage-0 ResBlock conv, M=210 N=256 K=1792: fp16 hi + scaled-lo weight planes = 4 N K = 1.8 MB
-        # ... 2.9 MB for K=2816, + the fp32 A rows) - at the algorithmic figure, half of the 3xTF32 planes (6.26 MB, r01_d)
-        roof["traffic"] = 3.38e6 if order[0][0].startswith("umma") else None
+        # dram__bytes_read + write of one launch of this kernel: from the committed ncu summary of the capture (not measured
+        # by this run: a run under ncu is never a bench run), null when no capture of the kernel is committed
+        tr = traffic_of(order[0][0])
+        roof["traffic"] = tr["bytes"] if tr else None
+        roof["traffic_source"] = tr["source"] if tr else None
         roof["note"] = ("achieved = sum of algorithmic bytes (weights + activations) or flops (2MNK) of this kernel's launches in one "
                         "window / sum of their device times; each op timed as a 10-launch CUDA graph between events on the "
                         "engine stream (rvc_profile_ops); ncu captures: profiles/")
         for name, f in order[1:5]:
             roof_extra.append(roof_of(name, f))
         for r in roof_extra:
-            if r["kernel"] == "knn_scan":
-                r["traffic"] = 123.0e6  # dram__bytes_read of profiles/r01_d_prof_knn2.md (one-CTA-per-SM variant; algorithmic 122.9 MB)
+            tr = traffic_of(r["kernel"])
+            r["traffic"] = tr["bytes"] if tr else None
+            r["traffic_source"] = tr["source"] if tr else None
         if args.profile_ops:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             json.dump({"step_us": step_us, "ops": prof}, open(os.path.join(ROOT, "gpurun_out", "profile_ops.json"), "w"))
+
+    knn = None
+    if rank == 0 and not args.quick:
+        knn = bench_knn(rvc_b200, paths, local_rank, peaks())
 
     cpu_b = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -355,12 +486,31 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "parallelism": f"{world} independent stream(s), 1 per GPU",
                        "l2": "weights (850 MB fp32) + index (123 MB) exceed the 126 MB L2: every window re-streams them",
-                       "realtime_factor": value * 0.16 / world},
+                       "realtime_factor": value * 0.16 / world,
+                       "target": "north_star: >= 100x real time = 625 frames/s per stream at batch 1, p99 < 5 ms",
+                       "target_met": {"throughput_625": bool(value / world >= 625.0), "p99_lt_5ms": bool(np.percentile(lat, 99) < 5.0)},
+                       "reference_arm": "runs on rank 0 only: compare the two arms at N = 1"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n16k * 4, "d2h_bytes_per_step": out_len * 4},
-            "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)),
+            "p50_ms": float(np.percentile(lat, 50)),
+            # a 99th percentile needs >= 200 samples (with fewer it is the maximum): null below that
+            "p99_ms": float(np.percentile(lat, 99)) if len(lat) >= 200 else None, "max_ms": float(np.max(lat)), "latency_samples": len(lat),
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_b,
-            "multi_stream": multi, "roofline_other_kernels": roof_extra,
+            "multi_stream": multi, "offline32": offline, "knn1m": knn, "roofline_other_kernels": roof_extra,
         }
+        if args.workload == "streams8" and multi:
+            line = dict(line, metric="audio frames/sec (160 ms @16 kHz), %d live streams per GPU in one batched plan" % args.streams,
+                        value=multi["value"], ms_per_step=multi["ms_per_round"], e2e=multi["e2e"], steps=multi["rounds"],
+                        config=dict(line["config"], workload="configs[3] shape: %d independent live streams per GPU, one window of each per call "
+                                    "(rvc_infer_batch -> one batched plan)" % args.streams, streams_per_gpu=args.streams))
+        elif args.workload == "offline32" and offline:
+            line = dict(line, metric="audio frames/sec (160 ms @16 kHz), offline, 32 windows per launch", value=offline["value"],
+                        ms_per_step=offline["ms_per_launch"], e2e=offline["e2e"], steps=offline["windows"] // 32, gpu_launches=offline["gpu_launches"],
+                        config=dict(line["config"], workload="configs[2]: offline conversion of one stream, 32 consecutive windows per launch "
+                                    "(rvc_infer_windows)", windows_per_launch=32))
+        elif args.workload == "knn1m" and knn:
+            line = dict(line, metric="kNN queries/sec (1M x 256 index, top-4, 128 queries per launch)", unit="queries/s", value=knn["value"],
+                        ms_per_step=(knn["scan_us"] + knn["rerank_us"]) * 1e-3, e2e=knn["e2e"], roofline=knn["roofline"], steps=10,
+                        gpu_launches=2, config={"workload": knn["workload"]})
         print(json.dumps(line))
     eng.close()
     if dist is not None:

@@ -104,7 +104,64 @@ attn_kernel(const float* __restrict__ qkv, long long ld, float* __restrict__ out
     __syncthreads();
     // K / V of the head are staged once per CTA; a warp takes query rows qbase + warp, + 8, ... (batched plans give a
     // CTA many rows so the staging is amortised; a single window keeps 8 rows per CTA for the widest grid)
-    for (int qi = qbase + warp; qi < min(T, qbase + rows_per_cta); qi += ATT_WARPS) {
+    const int qend = min(T, qbase + rows_per_cta);
+    if (rows_per_cta > ATT_WARPS) {
+        // batched plans: a warp takes TWO query rows per pass (qi, qi + 8): every K / V element read from shared memory
+        // feeds both rows (the single-row loop is bound by one LDS per FMA).  Same per-row arithmetic and summation order.
+        float* Ps2 = Ps + (size_t)ATT_WARPS * Tp;
+        for (int qi = qbase + warp; qi < qend; qi += 2 * ATT_WARPS) {
+            const int qj = qi + ATT_WARPS;
+            const bool two = qj < qend;
+            float qa[D], qb[D];
+#pragma unroll
+            for (int d4 = 0; d4 < D / 4; ++d4) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(qkv + (long long)qi * ld + h * D) + d4);
+                qa[d4 * 4] = t4.x; qa[d4 * 4 + 1] = t4.y; qa[d4 * 4 + 2] = t4.z; qa[d4 * 4 + 3] = t4.w;
+                const float4 u4 = two ? __ldg(reinterpret_cast<const float4*>(qkv + (long long)qj * ld + h * D) + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                qb[d4 * 4] = u4.x; qb[d4 * 4 + 1] = u4.y; qb[d4 * 4 + 2] = u4.z; qb[d4 * 4 + 3] = u4.w;
+            }
+            float* pa = Ps + warp * Tp;
+            float* pb = Ps2 + warp * Tp;
+            float mxa = -FLT_MAX, mxb = -FLT_MAX;
+            for (int j = lane; j < T; j += 32) {
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; d += 2) {
+                    const float k0 = Kt[d * Tp + j], k1 = Kt[(d + 1) * Tp + j];
+                    a0 = fmaf(qa[d], k0, a0); a1 = fmaf(qa[d + 1], k1, a1);
+                    b0 = fmaf(qb[d], k0, b0); b1 = fmaf(qb[d + 1], k1, b1);
+                }
+                const float sa = a0 + a1, sb = b0 + b1;
+                pa[j] = sa; pb[j] = sb;
+                mxa = fmaxf(mxa, sa); mxb = fmaxf(mxb, sb);
+            }
+            mxa = warp_max(mxa); mxb = warp_max(mxb);
+            float suma = 0.f, sumb = 0.f;
+            for (int j = lane; j < T; j += 32) {
+                const float ea = expf(pa[j] - mxa), eb = expf(pb[j] - mxb);
+                pa[j] = ea; pb[j] = eb; suma += ea; sumb += eb;
+            }
+            suma = warp_sum(suma); sumb = warp_sum(sumb);
+            __syncwarp();
+            float oa0 = 0.f, oa1 = 0.f, ob0 = 0.f, ob1 = 0.f;
+            for (int j = 0; j < T; ++j) {
+                const float v0 = Vs[j * D + lane], v1 = Vs[j * D + lane + 32];
+                const float wa = pa[j], wb = pb[j];
+                oa0 = fmaf(wa, v0, oa0); oa1 = fmaf(wa, v1, oa1);
+                ob0 = fmaf(wb, v0, ob0); ob1 = fmaf(wb, v1, ob1);
+            }
+            const float inva = 1.0f / suma, invb = 1.0f / sumb;
+            out[(long long)qi * ldo + h * D + lane] = oa0 * inva;
+            out[(long long)qi * ldo + h * D + lane + 32] = oa1 * inva;
+            if (two) {
+                out[(long long)qj * ldo + h * D + lane] = ob0 * invb;
+                out[(long long)qj * ldo + h * D + lane + 32] = ob1 * invb;
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    for (int qi = qbase + warp; qi < qend; qi += ATT_WARPS) {
     float q[D];
 #pragma unroll
     for (int d4 = 0; d4 < D / 4; ++d4) {
@@ -471,7 +528,7 @@ inline int grid_for(long long n, int block, int cap = 148 * 8) {
     return int(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-size_t attn_smem(int T) { const int Tp = (T | 1) + 2; return sizeof(float) * (size_t(T) * ATT_D + size_t(ATT_D) * Tp + size_t(ATT_WARPS) * Tp); }
+size_t attn_smem(int T) { const int Tp = (T | 1) + 2; return sizeof(float) * (size_t(T) * ATT_D + size_t(ATT_D) * Tp + size_t(2 * ATT_WARPS) * Tp); }   // two score rows per warp (batched plans)
 size_t relattn_smem(int T, int dim) { return sizeof(float) * (size_t(dim) + size_t(T)); }
 
 }  // namespace
