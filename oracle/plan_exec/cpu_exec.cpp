@@ -509,7 +509,7 @@ void pe_set_params(void* h, uint64_t seed, int noise_mode, int index_k) {
 int pe_run(void* h, int kind, const float* pcm, int n, int sf16k, int pitch_shift, int skip_head, int return_length) {
     Exec* e = static_cast<Exec*>(h);
     Geometry g{n, sf16k, skip_head, return_length};
-    PlanOptions opt; opt.index_k = e->index_k; opt.allow_umma = e->allow_umma; opt.with_index = e->index_rows > 0; opt.index_rows = e->index_rows;
+    PlanOptions opt; opt.index_k = e->index_k; opt.allow_umma = e->allow_umma; opt.with_index = e->index_rows > 0; opt.index_rows = e->index_rows; opt.index_cols = e->index_c;
     opt.chain_grid_main = e->chain_main; opt.chain_grid_side = e->chain_side; opt.chain_side_max_m = e->chain_max_m;
     if (!build_plan(PlanKind(kind), g, opt, e->has_cv ? &e->cv : nullptr, &e->cvi, e->has_f0 ? &e->f0 : nullptr, &e->f0i,
                     e->has_syn ? &e->syn : nullptr, &e->syi, e->plan, e->err)) return 1;
