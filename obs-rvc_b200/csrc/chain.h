@@ -44,6 +44,7 @@ struct ChainDev {
     unsigned int* d_bar = nullptr;   // [0] arrivals, [1] exits (self-cleaning)
     unsigned long long* d_dbg = nullptr;  // optional: globaltimer at every phase start (+ end), CTA 0
     int n_ops = 0, n_phases = 0, grid = 0;
+    int cluster = 0;   // 1: the grid is ONE thread-block cluster (<= 16 CTAs), phases separated by the hardware cluster barrier
 };
 
 constexpr int CHAIN_THREADS = 256;
@@ -53,6 +54,7 @@ int launch_chain(const ChainDev& c, cudaStream_t stream);  // returns kernels la
 void init_chain_attributes();
 void chain_debug_read(long long* out, int n);  // [256 phases][8] clock64 stamps of the LAST chain launch, CTA 0
 void chain_debug_read2(long long* out, int n); // [256 phases][2]: barrier spin start / end of CTA 0
+int chain_max_cluster_ctas();     // largest single-cluster grid (16 with the non-portable size allowed), 0 = none
 int chain_max_coresident_ctas();  // occupancy-derived upper bound for a cooperative launch
 
 }  // namespace rvc

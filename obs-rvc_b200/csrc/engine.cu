@@ -26,6 +26,7 @@
 
 #include "../../include/rvc_b200.h"
 #include "chain.h"
+#include "cvstack.h"
 #include "launch.h"
 #include "model.h"
 #include "pdl.cuh"
@@ -107,6 +108,7 @@ struct PlanEntry {
     DevBuf work;
     DevBuf bstate;   // batched plans: nb state blocks (params | pitch cache | pcm | audio), plan.state_block bytes apart
     std::vector<ChainDev> chains;   // device tables of plan.chains (pointers resolved against this entry's arenas)
+    CvsDev cvs;                     // device tables of plan.cvstack (grid == 0: the stack runs as separate kernels)
     cudaGraphExec_t exec = nullptr;
     cudaGraph_t graph = nullptr;
     int runs = 0;
@@ -115,6 +117,7 @@ struct PlanEntry {
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
         for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); }
+        cudaFree(cvs.d_maps); cudaFree(cvs.d_phases); cudaFree(cvs.d_bar);
         work.release(); bstate.release();
     }
 };
@@ -189,6 +192,7 @@ struct rvc_ctx {
     int chain_grid_main = 0, chain_grid_side = 0, chain_side_max_m = 8;
     int f0_priority = 0;        // launch priority of the F0 lanes' kernels (highest stream priority of the device; RVC_F0_PRIO=0 disables)
     bool chain_force = false;   // RVC_CHAIN=2: keep chains even when several contexts share the device
+    int cvstack_grid = 64;      // CTAs of the persistent ContentVec stack kernel (RVC_CVSTACK=0 disables, RVC_CVSTACK_G sets the grid)
     bool knn_umma = true;       // RVC_KNN_UMMA=0: retrieval always on the fp32 scan (kernels_knn.cu)
 
     int fail(int code, const std::string& m) { err = m; return code; }
@@ -291,6 +295,11 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
             continue;
         }
         rvc::g_launch_priority = (ctx->f0_priority != 0 && (op.lane == 1 || op.lane == 3) && op.name.compare(0, 3, "sy.") != 0) ? ctx->f0_priority : 0;
+        if (op.stack && e.cvs.grid > 0) {
+            // ContentVec's transformer layers: one persistent tcgen05 kernel, launched where the first op stood
+            if (&op == &e.plan.ops[size_t(e.plan.cvstack.first)]) n += launch_cvstack(e.cvs, ctx->streams[op.lane]);
+            continue;
+        }
         if (op.chain >= 0 && size_t(op.chain) < e.chains.size()) {
             // the whole run executes in one persistent kernel, launched where its first op stood
             if (&op == &e.plan.ops[size_t(e.plan.chains[size_t(op.chain)].first)]) n += launch_chain(e.chains[size_t(op.chain)], ctx->streams[op.lane]);
@@ -376,6 +385,11 @@ int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
         ChainDev cd;
         cd.n_ops = ci.count; cd.n_phases = ci.n_phases;
         cd.grid = std::max(1, std::min(ci.grid, chain_max_coresident_ctas()));
+        {   // small grids run as ONE thread-block cluster: hardware cluster barrier instead of the L2 grid barrier
+            static const int max_cluster = chain_max_cluster_ctas();
+            const char* ce = getenv("RVC_CHAIN_CLUSTER");
+            cd.cluster = (!(ce && ce[0] == '0') && cd.grid >= 2 && cd.grid <= max_cluster) ? 1 : 0;
+        }
         CK(cudaMalloc(&cd.d_ops, ops.size() * sizeof(ChainOpDev)));
         CK(cudaMalloc(&cd.d_phases, phases.size() * sizeof(ChainPhaseDev)));
         CK(cudaMalloc(&cd.d_bar, 256));
@@ -387,6 +401,97 @@ int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
         CK(cudaStreamSynchronize(ctx->streams[0]));  // the host vectors go out of scope
         e.chains.push_back(cd);
     }
+    return RVC_OK;
+}
+
+// Phase table + tensor maps of the persistent ContentVec stack kernel (cvstack.h) from the plan's own ops.
+int build_cvstack_tables(rvc_ctx* ctx, PlanEntry& e) {
+    const CvStackInfo& cs = e.plan.cvstack;
+    if (cs.first < 0 || cs.count <= 0 || ctx->cvstack_grid <= 0) return RVC_OK;
+    const DeviceBases B = ctx->bases(e);
+    const int64_t h16 = B.hilo16_off[SP_CV], plane = B.hilo16_plane[SP_CV];
+    if (h16 <= 0) return RVC_OK;   // no fp16 weight planes: the ops run as separate kernels
+    const int W = cs.width, F = cs.ffn;
+    auto unfuse = [&]() { for (int k = 0; k < cs.count; ++k) e.plan.ops[size_t(cs.first + k)].stack = 0; return RVC_OK; };
+    if (W % 128 != 0 || W > 1024 || W % CVS_BN != 0 || F % CVS_BN != 0 || (3 * W) % CVS_BN != 0 || (W / 64) % CVS_SPLITK != 0 || (F / 64) % CVS_SPLITK != 0) return unfuse();
+    std::vector<CvsPhase> phases;
+    std::vector<uint8_t> maps;   // 128 bytes per CUtensorMap
+    auto add_map = [&](const void* base, int K, int rows, int box_rows) -> int {
+        const int idx = int(maps.size() / 128);
+        maps.resize(maps.size() + 128);
+        if (!cvstack_encode_map(maps.data() + size_t(idx) * 128, base, K, rows, box_rows)) return -1;
+        return idx;
+    };
+    struct Planes { unsigned short* hi; unsigned short* lo; int K; int map; };
+    auto mk_planes = [&](const Ref& r, int K) { Planes p; p.hi = B.p<unsigned short>(r); p.lo = p.hi + size_t(128) * K; p.K = K; p.map = -1; return p; };
+    Planes px = mk_planes(cs.planes_x, W), px1 = mk_planes(cs.planes_x1, W), pa = mk_planes(cs.planes_a, W), phh = mk_planes(cs.planes_h, F);
+    for (Planes* p : {&px, &px1, &pa, &phh}) {
+        p->map = add_map(p->hi, p->K, 128, 128);
+        if (p->map < 0 || add_map(p->lo, p->K, 128, 128) < 0) return unfuse();
+    }
+    float* partial = B.p<float>(cs.partial);
+    const GemmOp* pending = nullptr;   // split-K GEMM whose partial tiles the next LayerNorm sums
+    int n_ln = 0, n_gemm = 0;
+    for (int k = 0; k < cs.count; ++k) {
+        const Op& op = e.plan.ops[size_t(cs.first + k)];
+        CvsPhase P;
+        std::memset(&P, 0, sizeof(P));
+        if (op.kind == OP_LAYERNORM) {
+            const LayerNormOp& ln = op.ln;
+            if (ln.cols != W || ln.rows != cs.T) return unfuse();
+            P.kind = CVS_LN; P.items = (cs.T + 7) / 8; P.cols = W; P.eps = ln.eps;
+            P.gamma = B.p<float>(ln.gamma); P.beta = B.p<float>(ln.beta); P.Y = B.p<float>(ln.Y); P.ldy = ln.ldy;
+            if (pending) {
+                P.X = partial; P.ldx = pending->N; P.slab = int64_t(128) * pending->N; P.S = CVS_SPLITK;
+                P.bias = B.p<float>(pending->bias); P.R = B.p<float>(pending->R); P.ldr = pending->ldr;
+                pending = nullptr;
+            } else {
+                P.X = B.p<float>(ln.X); P.ldx = ln.ldx; P.slab = 0; P.S = 1;
+            }
+            const Planes& out = (n_ln % 2 == 0) ? px : px1;   // enc_in / ln2 feed the next QKV, ln1 feeds FC1
+            P.p_hi = out.hi; P.p_lo = out.lo; P.ldp = W;
+            ++n_ln;
+        } else if (op.kind == OP_ATTN) {
+            const AttnOp& a = op.attn;
+            if (a.dim != 64 || a.T != cs.T || a.heads * 64 != W) return unfuse();
+            P.kind = CVS_ATTN; P.items = a.heads * ((cs.T + CVS_ATT_ROWS - 1) / CVS_ATT_ROWS);
+            P.qkv = B.p<float>(a.qkv); P.ldqkv = a.ldqkv; P.heads = a.heads;
+            P.p_hi = pa.hi; P.p_lo = pa.lo; P.ldp = W;
+        } else if (op.kind == OP_GEMM) {
+            const GemmOp& g = op.gemm;
+            const int role = n_gemm % 4;   // qkv, o, fc1, fc2
+            ++n_gemm;
+            const Planes& in = role == 0 ? px : (role == 1 ? pa : (role == 2 ? px1 : phh));
+            const bool split = !g.R.null();
+            if (g.K != in.K || g.N % CVS_BN != 0 || g.M != cs.T || g.batch != 1 || g.seg_len < g.K || g.ldw != g.K || g.alpha != 1.0f ||
+                (split != (role == 1 || role == 3)) || (role == 2) != (g.act == ACT_GELU) || (role != 2 && g.act != ACT_NONE) || g.bias.null() ||
+                g.W.space != SP_CV || g.W.off % 32 != 0)
+                return unfuse();
+            const uint8_t* w_hi = B.b[SP_CV] + h16 + g.W.off / 2;
+            P.kind = CVS_GEMM; P.a_map = in.map;
+            P.w_map = add_map(w_hi, g.K, g.N, CVS_BN);
+            if (P.w_map < 0 || add_map(w_hi + plane, g.K, g.N, CVS_BN) < 0) return unfuse();
+            P.splitk = split ? CVS_SPLITK : 1; P.nkb = g.K / 64 / P.splitk; P.items = (g.N / CVS_BN) * P.splitk;
+            P.bias = B.p<float>(g.bias);
+            if (split) { P.epi = CVS_EPI_PARTIAL; P.C = partial; P.ldc = g.N; pending = &g; }
+            else if (role == 2) { P.epi = CVS_EPI_GELU_PLANES; P.p_hi = phh.hi; P.p_lo = phh.lo; P.ldp = F; }
+            else { P.epi = CVS_EPI_BIAS; P.C = B.p<float>(g.C); P.ldc = g.ldc; }
+        } else {
+            return unfuse();
+        }
+        phases.push_back(P);
+    }
+    if (pending || int(phases.size()) > CVS_MAX_PHASES) return unfuse();
+    CvsDev& d = e.cvs;
+    d.n_phases = int(phases.size()); d.T = cs.T;
+    d.grid = std::max(1, std::min(ctx->cvstack_grid, cvstack_max_ctas()));
+    CK(cudaMalloc(&d.d_maps, maps.size()));
+    CK(cudaMalloc(&d.d_phases, phases.size() * sizeof(CvsPhase)));
+    CK(cudaMalloc(&d.d_bar, 256));
+    CK(cudaMemcpyAsync(d.d_maps, maps.data(), maps.size(), cudaMemcpyHostToDevice, ctx->streams[0]));
+    CK(cudaMemcpyAsync(d.d_phases, phases.data(), phases.size() * sizeof(CvsPhase), cudaMemcpyHostToDevice, ctx->streams[0]));
+    CK(cudaMemsetAsync(d.d_bar, 0, 256, ctx->streams[0]));
+    CK(cudaStreamSynchronize(ctx->streams[0]));
     return RVC_OK;
 }
 
@@ -402,6 +507,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
     opt.allow_umma = ctx->allow_umma;
     opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
     opt.chain_side_max_m = ctx->chain_side_max_m;
+    opt.cv_stack = key.chains && ctx->cvstack_grid > 0 && ctx->allow_umma;
     opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;
     if (ctx->index.loaded && ctx->knn_umma) { opt.index_planes_off = ctx->index.d->planes_off; opt.index_ymax2 = ctx->index.d->ymax2; }
     {   // RVC_F0_UMMA: 0 never, 1 always, default = batched plans only
@@ -424,6 +530,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
         CK(cudaMemsetAsync(e->bstate.d, 0, e->bstate.bytes, ctx->streams[0]));
     }
     { int rc = build_chain_tables(ctx, *e); if (rc != RVC_OK) return rc; }
+    { int rc = build_cvstack_tables(ctx, *e); if (rc != RVC_OK) return rc; }
     *out = e.get();
     ctx->plans[key] = std::move(e);
     return RVC_OK;
@@ -680,6 +787,10 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_SYNC_EACH"); g_sync_each = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_KNN_UMMA"); ctx->knn_umma = !(ev && ev[0] == '0'); }
+    {
+        const char* ev = getenv("RVC_CVSTACK"); const char* eg = getenv("RVC_CVSTACK_G");
+        ctx->cvstack_grid = (ev && ev[0] == '0') ? 0 : (eg ? atoi(eg) : 64);
+    }
     {   // persistent chains: CTA budgets (0 = off).  RVC_CHAIN=0 disables both.
         const char* ev = getenv("RVC_CHAIN"); const bool on = !(ev && ev[0] == '0');
         ctx->chain_force = ev && ev[0] == '2';
@@ -1352,6 +1463,15 @@ int rvc_profile_chains(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_by
         std::memcpy(out, js.data(), js.size()); out[js.size()] = 0;
     }
     return RVC_OK;
+}
+
+// [phase][4] clock64 stamps (worker start, work done, arrived) of CTA 0 of the last persistent ContentVec stack launch
+int rvc_debug_cvstack_stamps(rvc_ctx* ctx, long long* out, int n) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->sync_all();
+    if (!ctx->last || ctx->last->cvs.grid <= 0) return RVC_ERR_INVALID_ARG;
+    cvstack_debug_read(out, n);
+    return ctx->last->cvs.n_phases;
 }
 
 int rvc_debug_chain_stamps(rvc_ctx* ctx, int chain, long long* out2048) {

@@ -580,7 +580,7 @@ constexpr int CHAIN_MAX_OPS = 256;   // table entries kept in shared memory (pla
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 1)
 chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict__ phases, int n_ops, int n_phases, unsigned int* bar,
-             unsigned long long* dbg) {
+             unsigned long long* dbg, int cluster_mode) {
     extern __shared__ __align__(16) float smem[];
     __shared__ ChainOpDev s_op;
     __shared__ ChainPhaseDev s_phase[CHAIN_MAX_OPS];
@@ -644,6 +644,12 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
         pre = false;
         if (ph + 1 < n_phases) {
             // arrive first, then use the wait: descriptor + first weight stages of this CTA's next item
+            if (cluster_mode) {
+                // the whole grid is ONE thread-block cluster: the hardware cluster barrier (release / acquire at cluster
+                // scope, a few hundred cycles) stands where the L2 atomic + polling round trip of the grid barrier stood
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                if (blockIdx.x == 0 && tid == 0 && ph < 256) g_chain_stamp[ph * 8 + 7] = clock64();
+            } else {
             __syncthreads();
             if (tid == 0) {
                 // arrivals are counted on bar[0]; the last one publishes the phase on bar[32] (its own 128-byte
@@ -653,7 +659,9 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 if (ticket == (unsigned int)(ph + 1) * G - 1) { __threadfence(); asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 32), "r"((unsigned int)(ph + 1)) : "memory"); }
                 if (blockIdx.x == 0 && ph < 256) g_chain_stamp[ph * 8 + 7] = clock64();
             }
+            }
             if (nxt_o >= 0) {
+                if (cluster_mode) __syncthreads();   // every thread is done with s_op of this phase (the cluster arrive does not wait)
                 if (tid < OP_WORDS) reinterpret_cast<int*>(&s_op)[tid] = nxt_word;
                 cur = nxt_o;
                 __syncthreads();
@@ -668,6 +676,11 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 }
                 pre = true;
             }
+            if (cluster_mode) {
+                if (blockIdx.x == 0 && tid == 0 && ph < 256) g_chain_stamp2[ph * 2] = clock64();
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                if (blockIdx.x == 0 && tid == 0 && ph < 256) g_chain_stamp2[ph * 2 + 1] = clock64();
+            } else {
             if (tid == 0) {
                 const unsigned int target = (unsigned int)(ph + 1);
                 const long long t0 = clock64();
@@ -683,12 +696,13 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 if (blockIdx.x == 0 && ph < 256) g_chain_stamp2[ph * 2 + 1] = clock64();
             }
             __syncthreads();
+            }
         }
     }
     if (dbg && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[n_phases] = t; }
     // exit ticket: the last CTA out re-arms the barrier words for the next launch / graph replay
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !cluster_mode) {
         __threadfence();
         if (atomicAdd(bar + 1, 1u) == G - 1) { bar[0] = 0; bar[1] = 0; bar[32] = 0; __threadfence(); }
     }
@@ -700,6 +714,7 @@ int g_chain_max_ctas = 0;
 
 void init_chain_attributes() {
     cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES);
+    cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // single-cluster chains of 16 CTAs
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -716,15 +731,39 @@ int launch_chain(const ChainDev& c, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = CHAIN_SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident or none: the grid barrier cannot deadlock
-    attr[0].val.cooperative = 1;
+    if (c.cluster) {
+        // the grid is one thread-block cluster (co-scheduled by the hardware): cluster barriers between phases
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = unsigned(c.grid); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident or none: the grid barrier cannot deadlock
+        attr[0].val.cooperative = 1;
+    }
     attr[1].id = cudaLaunchAttributePriority;
     attr[1].val.priority = g_launch_priority;
     cfg.attrs = attr; cfg.numAttrs = g_launch_priority != 0 ? 2 : 1;
     const ChainOpDev* ops = c.d_ops; const ChainPhaseDev* phases = c.d_phases; int no = c.n_ops, n = c.n_phases; unsigned int* bar = c.d_bar;
     unsigned long long* dbg = c.d_dbg;
-    cudaLaunchKernelEx(&cfg, chain_kernel, ops, phases, no, n, bar, dbg);
+    int cm = c.cluster ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, chain_kernel, ops, phases, no, n, bar, dbg, cm);
     return 1;
+}
+
+// largest single-cluster grid the chain kernel can be launched with on this device (0 = clusters unavailable)
+int chain_max_cluster_ctas() {
+    int best = 0;
+    for (int g = 16; g >= 2; g >>= 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(unsigned(g)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = CHAIN_SMEM_BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = unsigned(g); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, chain_kernel, &cfg) == cudaSuccess && n >= 1) { best = g; break; }
+        cudaGetLastError();
+    }
+    return best;
 }
 
 }  // namespace rvc

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 
 #include "chain.h"
+#include "cvstack.h"
 #include "launch.h"
 #include "pdl.cuh"
 #include "noise.h"
@@ -541,6 +542,7 @@ void init_kernel_attributes() {
     init_gemm_v2_attributes();
     init_umma_attributes();
     init_chain_attributes();
+    init_cvstack_attributes();
 }
 
 void launch_split_hilo16(const float* src, unsigned short* dst_hi, unsigned short* dst_lo, size_t n, cudaStream_t stream) {

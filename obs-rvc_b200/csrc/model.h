@@ -77,6 +77,7 @@ struct PlanOptions {
     int32_t index_cols = 0;        // width of the loaded retrieval index (must equal the ContentVec width)
     int64_t index_planes_off = 0;  // > 0: the index carries fp16 planes (tensor-core candidate pass, kernels_knn_umma.cu)
     float index_ymax2 = 0.f;       // max |y|^2 over the index rows (error bound of the candidate pass)
+    bool cv_stack = false;         // ContentVec transformer layers as one persistent tcgen05 kernel (single-window plans, T <= 128)
     bool f0_umma = false;          // RMVPE's wide levels on the tcgen05 FP16-split kernel (batched plans; needs the f0 weight planes)
 };
 
@@ -84,6 +85,7 @@ struct Plan {
     std::vector<Op> ops;
     std::vector<NamedBuf> bufs;
     std::vector<ChainInfo> chains;
+    CvStackInfo cvstack;
     int64_t work_bytes = 0;
     int32_t n_lanes = 1;
     // well-known buffers

@@ -173,6 +173,7 @@ struct Op {
     int32_t kind = OP_FILL;
     int32_t lane = 0;
     int32_t chain = -1;  // index into Plan::chains when the op executes inside a persistent chain kernel
+    int32_t stack = 0;   // 1: the op is executed by the persistent ContentVec stack kernel (Plan::cvstack, kernels_cvstack.cu)
     std::string name;  // plan-unique; debug lookups + parity tests
     // exactly one of these is meaningful, selected by `kind`
     GemmOp gemm; LayerNormOp ln; AttnOp attn; RelAttnOp relattn; Conv0StatsOp c0s; Conv0ApplyOp c0a;
@@ -222,6 +223,14 @@ inline int64_t knn_umma_planes_bytes(int n_rows, int C) { return knn_umma_counte
 // A run of consecutive same-lane ops executed by one persistent cooperative kernel (chain.h).
 // phase[i] is the barrier phase of op first+i: ops of one phase touch disjoint buffers.
 struct ChainInfo { int32_t first = 0, count = 0, lane = 0, grid = 0, n_phases = 0; std::vector<int32_t> phase; };
+
+// The ContentVec transformer layers as one persistent tcgen05 kernel (cvstack.h): ops [first, first + count) of the
+// plan (enc_in LayerNorm, then per layer qkv / attn / o / ln1 / fc1 / fc2 / ln2) plus the buffers only that kernel
+// uses: fp16 operand planes [hi | lo'] of the four GEMM inputs and the split-K partial tiles.
+struct CvStackInfo {
+    int32_t first = -1, count = 0, T = 0, width = 0, ffn = 0;
+    Ref planes_x, planes_x1, planes_a, planes_h, partial;
+};
 
 // A named buffer of the plan (debug / result lookups).
 struct NamedBuf { std::string name; Ref ref; int64_t elems = 0; int32_t is_int = 0; };

@@ -26,6 +26,7 @@ struct PB {
     int sc_lane = -1;   // >= 0: the 1x1 shortcut convs of RMVPE's residual blocks run on this lane, beside c1
     bool allow_umma = true;
     bool f0_umma = false;
+    bool cv_stack = false;
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
 
@@ -128,6 +129,7 @@ Ref build_contentvec(PB& b, const Packed* P, const CvInfo& info, Ref pcm, int N,
         g.sR = 48; g.cta_budget = 128;   // 16 groups x split-K 8: 6144-deep contraction, 24 k-blocks per CTA
     }
     Ref cur = b.alloc("cv.enc_in", int64_t(T) * 768);
+    const int stack_first = int(b.plan.ops.size());
     b.layernorm("cv.enc_in", pc, 768, cur, 768, W("eln.g"), W("eln.b"), T, 768);
     for (int i = 0; i < info.n_layers; ++i) {
         std::string d = "L" + S(i) + ".", n = "cv.L" + S(i) + ".";
@@ -152,6 +154,18 @@ Ref build_contentvec(PB& b, const Packed* P, const CvInfo& info, Ref pcm, int N,
         Ref x2 = b.alloc("cv.layer" + S(i), int64_t(T) * 768);
         b.layernorm("cv.layer" + S(i), t2, 768, x2, 768, W(d + "ln2.g"), W(d + "ln2.b"), T, 768);
         cur = x2;
+    }
+    if (b.cv_stack && b.allow_umma && T <= 128 && info.n_layers * 7 + 1 <= 128) {
+        // the layers run as one persistent tcgen05 kernel (kernels_cvstack.cu); the ops stay in the list for the CPU
+        // plan interpreter and the per-op tools, the CUDA launcher replaces them by one launch
+        CvStackInfo& cs = b.plan.cvstack;
+        cs.first = stack_first; cs.count = int(b.plan.ops.size()) - stack_first; cs.T = T; cs.width = 768; cs.ffn = 3072;
+        for (int k = 0; k < cs.count; ++k) b.plan.ops[size_t(stack_first + k)].stack = 1;
+        cs.planes_x = b.alloc("cv.dbg_planes_x", int64_t(2) * 128 * 768 / 2);     // [hi | lo'][128][768] halves
+        cs.planes_x1 = b.alloc("", int64_t(2) * 128 * 768 / 2);
+        cs.planes_a = b.alloc("", int64_t(2) * 128 * 768 / 2);
+        cs.planes_h = b.alloc("", int64_t(2) * 128 * 3072 / 2);
+        cs.partial = b.alloc("cv.dbg_partial", int64_t(4) * 128 * 768);          // [z][128][768] fp32
     }
     if (info.final_proj) {
         Ref o = b.alloc("cv.out", int64_t(T) * 256);
@@ -540,6 +554,7 @@ bool gemm_aligned(const GemmOp& g) {
 }
 
 bool chain_eligible(const Op& op, int side_max_m) {
+    if (op.stack) return false;   // runs inside the persistent ContentVec stack kernel
     switch (op.kind) {
         case OP_GEMM: {
             const GemmOp& g = op.gemm;
@@ -655,6 +670,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     PB b{plan, err};
     b.allow_umma = opt.allow_umma;
     b.f0_umma = opt.f0_umma;
+    b.cv_stack = opt.cv_stack && opt.nb <= 1;
     plan.params = Ref{SP_STATE, StateLayout::off_params};
     plan.cache = Ref{SP_STATE, StateLayout::off_cache};
     plan.pcm = Ref{SP_STATE, StateLayout::off_pcm};
@@ -749,7 +765,8 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     F0Out fo{};
     static const bool f0_first = sched_env("RVC_F0_FIRST", 1) != 0;
     auto emit_f0 = [&]() {
-        if (ml) { b.lane = 1; b.sc_lane = 3; }
+        static const bool sc_side = sched_env("RVC_SC_LANE", 1) != 0;   // 0: shortcut convs stay on the F0 lane (same chain phase as c1)
+        if (ml) { b.lane = 1; b.sc_lane = sc_side ? 3 : -1; }
         fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
         b.lane = 0; b.sc_lane = -1;
     };
