@@ -134,6 +134,10 @@ int rvc_infer_windows_dev(rvc_ctx* ctx, const float* pcm_dev, size_t n_pcm, size
 /* MelSpectrogram::mel_extract - rmvpe.rs:159-205. out: (128, T) row-major, T = 1 + n/160. */
 int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap,
                     size_t* out_frames);
+/* Rmvpe::decode + to_local_average_cents (rmvpe.rs:118-133, 243-248) on caller-supplied salience rows (t_frames, 360):
+ * the decode stage of `pitch` without the network (argmax per frame, 9-tap cents window in the configured convention,
+ * 0.03 threshold, f0 = 10 * 2^(cents / 1200), unvoiced -> 0).  f0_out / argmax_out: t_frames entries. */
+int rvc_decode_salience(rvc_ctx* ctx, const float* salience, size_t t_frames, float* f0_out, int32_t* argmax_out);
 /* Exact brute-force L2 top-k on the loaded index (stress config 5). d2/idx: (q, k). */
 int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32_t k,
                    float* d2, int32_t* idx);

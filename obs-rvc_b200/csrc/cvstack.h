@@ -7,7 +7,15 @@
 namespace rvc {
 
 constexpr int CVS_BN = 48;          // output columns per GEMM tile (N of every stack GEMM is a multiple of 48)
-constexpr int CVS_ATT_ROWS = 24;    // query rows per attention item
+constexpr int CVS_ATT_ROWS = 24;    // most query rows per attention item
+constexpr int CVS_SCRATCH_BYTES = 46 * 1024;   // worker scratch of a CTA: K^T / V staging, scores, q rows
+// query rows per attention item that fit the scratch at T rows: K^T [64][Tp] + per row (scores [Tp], 1 / sum, q [64])
+inline int cvs_att_rows(int T) {
+    const int Tp = (T | 1) + 2;
+    for (int r = CVS_ATT_ROWS; r >= 8; r -= 8)
+        if (64 * Tp * 4 + r * (Tp * 4 + 4 + 256) <= CVS_SCRATCH_BYTES) return r;
+    return 0;
+}
 constexpr int CVS_MAX_PHASES = 128;
 constexpr int CVS_SPLITK = 4;       // out-proj / FC2: K split in four, partial tiles summed by the following LayerNorm phase
 
@@ -25,8 +33,8 @@ struct CvsPhase {
     float* C; long long ldc;
     // fp16 planes written by this phase (GELU epilogue, attention, LayerNorm): element [m * ldp + n]
     unsigned short* p_hi; unsigned short* p_lo; long long ldp;
-    // CVS_ATTN: qkv = [T][3 * heads * 64] fp32, q pre-scaled; items = heads * ceil(T / CVS_ATT_ROWS)
-    const float* qkv; long long ldqkv; int heads, pad1;
+    // CVS_ATTN: qkv = [T][3 * heads * 64] fp32, q pre-scaled; items = heads * ceil(T / att_rows), att_rows <= CVS_ATT_ROWS
+    const float* qkv; long long ldqkv; int heads, att_rows;
     // CVS_LN: t = sum_{z < S} X[z * slab + m * ldx + c] (+ bias[c]) (+ R[m * ldr + c]); Y = LayerNorm(t) * gamma + beta; items = ceil(T / 8)
     const float* X; long long ldx, slab; int S, cols;
     const float* R; long long ldr;
@@ -46,6 +54,7 @@ bool cvstack_encode_map(void* out128, const void* base, int K, int rows, int box
 int launch_cvstack(const CvsDev& c, cudaStream_t stream);   // returns kernels launched (1)
 void init_cvstack_attributes();
 int cvstack_max_ctas();
+void cvstack_debug_read2(long long* out, int n);  // [phase][8] GEMM pipeline stamps of CTA 0
 void cvstack_debug_read(long long* out, int n);   // [phase][4] clock64 stamps of CTA 0 of the last launch
 
 }  // namespace rvc

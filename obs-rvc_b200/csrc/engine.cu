@@ -454,7 +454,9 @@ int build_cvstack_tables(rvc_ctx* ctx, PlanEntry& e) {
         } else if (op.kind == OP_ATTN) {
             const AttnOp& a = op.attn;
             if (a.dim != 64 || a.T != cs.T || a.heads * 64 != W) return unfuse();
-            P.kind = CVS_ATTN; P.items = a.heads * ((cs.T + CVS_ATT_ROWS - 1) / CVS_ATT_ROWS);
+            P.att_rows = cvs_att_rows(cs.T);
+            if (P.att_rows <= 0) return unfuse();
+            P.kind = CVS_ATTN; P.items = a.heads * ((cs.T + P.att_rows - 1) / P.att_rows);
             P.qkv = B.p<float>(a.qkv); P.ldqkv = a.ldqkv; P.heads = a.heads;
             P.p_hi = pa.hi; P.p_lo = pa.lo; P.ldp = W;
         } else if (op.kind == OP_GEMM) {
@@ -789,7 +791,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_KNN_UMMA"); ctx->knn_umma = !(ev && ev[0] == '0'); }
     {
         const char* ev = getenv("RVC_CVSTACK"); const char* eg = getenv("RVC_CVSTACK_G");
-        ctx->cvstack_grid = (ev && ev[0] == '0') ? 0 : (eg ? atoi(eg) : 64);
+        ctx->cvstack_grid = (ev && ev[0] == '1') ? (eg ? atoi(eg) : 64) : 0;   // opt-in: measured on par with the separate kernels (profiles/README.md)
     }
     {   // persistent chains: CTA budgets (0 = off).  RVC_CHAIN=0 disables both.
         const char* ev = getenv("RVC_CHAIN"); const bool on = !(ev && ev[0] == '0');
@@ -1094,6 +1096,34 @@ int rvc_pitch(rvc_ctx* ctx, const float* pcm, size_t n, int32_t pitch_shift, siz
     return RVC_OK;
 }
 
+// Rmvpe::decode (rmvpe.rs:243-248) + to_local_average_cents (rmvpe.rs:118-133) on caller-supplied salience rows
+// [T][360]: the decode stage of `pitch` without the network in front of it, so that tests can drive every argmax bin,
+// the exact-threshold case and both cents-window conventions.  f0 is returned unshifted (pitch factor 1).
+int rvc_decode_salience(rvc_ctx* ctx, const float* salience, size_t t_frames, float* f0_out, int32_t* argmax_out) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!salience || !f0_out || !argmax_out || t_frames == 0 || t_frames * 362 > size_t(StateLayout::AUDIO_CAP))
+        return ctx->fail(RVC_ERR_INVALID_ARG, "bad salience / outputs");
+    cudaStream_t s = ctx->streams[0];
+    const int T = int(t_frames);
+    float* d_sal = state_audio(ctx);
+    CK(cudaMemcpyAsync(d_sal, salience, size_t(T) * 360 * sizeof(float), cudaMemcpyHostToDevice, s));
+    set_params(ctx, 0);
+    DeviceBases B;
+    B.b[SP_STATE] = ctx->state.d;
+    F0DecodeOp o;
+    o.salience = Ref{SP_STATE, StateLayout::off_audio};
+    o.f0 = Ref{SP_STATE, StateLayout::off_audio + int64_t(T) * 360 * 4};
+    o.argmax = Ref{SP_STATE, StateLayout::off_audio + int64_t(T) * 361 * 4};
+    o.params = Ref{SP_STATE, StateLayout::off_params};
+    o.T = T; o.bins = 360; o.threshold = 0.03f; o.upstream_window = ctx->cfg.upstream_cents_window;
+    ctx->total_launches += uint64_t(launch_f0decode(o, B, s));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(f0_out, d_sal + size_t(T) * 360, size_t(T) * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(argmax_out, d_sal + size_t(T) * 361, size_t(T) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return RVC_OK;
+}
+
 int rvc_mel_extract(rvc_ctx* ctx, const float* pcm, size_t n, float* out, size_t cap, size_t* out_frames) {
     int rc = enter(ctx); if (rc) return rc;
     if (!ctx->f0.loaded) return ctx->fail(RVC_ERR_F0_NOT_LOADED, "F0NotLoaded");
@@ -1209,9 +1239,9 @@ int rvc_plan_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) 
     char buf[512];
     int n = std::snprintf(buf, sizeof(buf),
                           "{\"ops\": %zu, \"kernels_per_run\": %d, \"lanes\": %d, \"work_bytes\": %lld, \"hubert_T\": %d, \"hubert_C\": %d, "
-                          "\"f0_T\": %d, \"audio_len\": %d, \"knn_q\": %d, \"graph\": %d, \"windows\": %d, \"chains\": %zu}",
+                          "\"f0_T\": %d, \"audio_len\": %d, \"knn_q\": %d, \"graph\": %d, \"windows\": %d, \"chains\": %zu, \"cvstack\": %d}",
                           p.ops.size(), ctx->last->launches, p.n_lanes, (long long)p.work_bytes, p.hubert_T, p.hubert_C, p.f0_T,
-                          p.audio_len, p.knn_q, ctx->last->exec ? 1 : 0, p.nb, p.chains.size());
+                          p.audio_len, p.knn_q, ctx->last->exec ? 1 : 0, p.nb, p.chains.size(), ctx->last->cvs.grid > 0 ? 1 : 0);
     if (out_bytes) *out_bytes = size_t(n);
     if (out && cap_bytes > 0) { size_t m = size_t(n) < cap_bytes - 1 ? size_t(n) : cap_bytes - 1; std::memcpy(out, buf, m); out[m] = 0; }
     return RVC_OK;
@@ -1383,6 +1413,9 @@ int rvc_profile_timeline(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_
     const DeviceBases B = ctx->bases(e);
     std::vector<cudaEvent_t> evs;
     std::vector<const Op*> which;
+    std::string marks_s;
+    { const char* m = getenv("RVC_TL_MARKS"); if (m && *m) marks_s = std::string(",") + m + ","; }
+    const char* marks = marks_s.empty() ? nullptr : marks_s.c_str();
     cudaEvent_t t0; CK(cudaEventCreate(&t0));
     cudaStream_t s0 = ctx->streams[0];
     CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
@@ -1395,12 +1428,18 @@ int rvc_profile_timeline(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_
             CK(cudaStreamWaitEvent(ctx->streams[op.wait.dst_lane], ctx->events[ev], 0));
             ++ev; continue;
         }
-        if (op.chain >= 0 && size_t(op.chain) < e.chains.size()) {
+        if (op.stack && e.cvs.grid > 0) {
+            if (&op != &e.plan.ops[size_t(e.plan.cvstack.first + e.plan.cvstack.count - 1)]) continue;
+            n += launch_cvstack(e.cvs, ctx->streams[op.lane]);   // reported under the stack's LAST op
+        } else if (op.chain >= 0 && size_t(op.chain) < e.chains.size()) {
             if (&op != &e.plan.ops[size_t(e.plan.chains[size_t(op.chain)].first + e.plan.chains[size_t(op.chain)].count - 1)]) continue;
             n += launch_chain(e.chains[size_t(op.chain)], ctx->streams[op.lane]);  // reported under the chain's LAST op
         } else {
             issue_one(ctx, op, B, ctx->streams[op.lane], &n);
         }
+        // RVC_TL_MARKS=name,name,...: events only after these ops (a sparse timeline barely perturbs the window; an event
+        // after every op serialises the lanes' launches and inflates it by a third)
+        if (marks && std::strstr(marks, ("," + op.name + ",").c_str()) == nullptr) continue;
         cudaEvent_t x; CK(cudaEventCreate(&x));
         CK(cudaEventRecordWithFlags(x, ctx->streams[op.lane], cudaEventRecordExternal));
         evs.push_back(x); which.push_back(&op);
@@ -1470,7 +1509,8 @@ int rvc_debug_cvstack_stamps(rvc_ctx* ctx, long long* out, int n) {
     int rc = enter(ctx); if (rc) return rc;
     ctx->sync_all();
     if (!ctx->last || ctx->last->cvs.grid <= 0) return RVC_ERR_INVALID_ARG;
-    cvstack_debug_read(out, n);
+    cvstack_debug_read(out, n < 512 ? n : 512);
+    if (n >= 512 + 1024) cvstack_debug_read2(out + 512, 1024);
     return ctx->last->cvs.n_phases;
 }
 

@@ -79,6 +79,10 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma, int nb = 1, boo
     else { s.variant = 3; s.bm = 32; s.bn = 64; }
     // tall, narrow outputs (RMVPE's top levels: thousands of pixels x 16 / 32 channels): half the tile width, half the k loop
     if (g.N <= 32 && g.M >= 256) { s.variant = 4; s.bm = 32; s.bn = 32; }
+    // weight-streaming convs with a single row tile (RMVPE's deep levels: <= 32 pixels x 256..512 channels x K in the
+    // thousands): 32-wide column tiles double the CTAs that pull the weights (RVC_V2_NARROW=0 restores 64-wide tiles)
+    static const int kNarrow = sched_env("RVC_V2_NARROW", 1);
+    if (kNarrow && g.M <= 32 && g.N >= 128 && g.K >= 1024 && s.variant == 3) { s.variant = 4; s.bm = 32; s.bn = 32; }
     // narrow outputs: do not waste a 256/128-wide tile on a 32..64-column problem
     if (s.variant == 1 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
     if (s.variant == 2 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }

@@ -39,7 +39,7 @@ constexpr int CS_STAGES = 4;
 constexpr int CS_A_BYTES = 128 * 128;         // one fp16 plane of an A k-block: 128 rows x 64 halves
 constexpr int CS_W_BYTES = CS_BN * 128;       // one fp16 plane of a W k-block: 48 rows x 64 halves
 constexpr int CS_STAGE_BYTES = 2 * CS_A_BYTES + 2 * CS_W_BYTES;   // 45056
-constexpr int CS_SCRATCH_BYTES = 44 * 1024;   // worker scratch (attention staging)
+constexpr int CS_SCRATCH_BYTES = CVS_SCRATCH_BYTES;   // worker scratch (attention staging: K^T / V 28.9 KB, scores 10.8 KB, q rows 6 KB at T = 111)
 constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES + CS_SCRATCH_BYTES + 1024;
 constexpr int CS_THREADS = 320;
 constexpr int CS_WORKERS = 256;
@@ -144,7 +144,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
-__device__ long long g_cvs_stamp[CVS_MAX_PHASES * 4];   // CTA 0: [phase][worker start, work done, arrived, -]
+__device__ long long g_cvs_stamp[CVS_MAX_PHASES * 4];   // CTA 0: [phase][worker start, work done, arrived, grid wait over]
+__device__ long long g_cvs_stamp2[CVS_MAX_PHASES * 8];  // CTA 0, GEMM phases: producer [wait over, last issue], MMA [first full, last full, last commit], worker [acc full]
+#define CVS_ST2(e) do { if (blockIdx.x == 0 && ph < CVS_MAX_PHASES) g_cvs_stamp2[ph * 8 + (e)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(CS_THREADS, 1)
 cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict__ phases, int n_phases, unsigned int* bar, int T) {
@@ -172,51 +174,61 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
     const uint32_t tmem_base = s_tmem;
 
     if (warp == 0) {
-        // ===== TMA producer (one thread).  Runs ahead of the grid barrier with the WEIGHT halves of a phase's first
-        // stages; the activation halves follow once every CTA has finished the previous phase =====
-        if (lane == 0) {
+        // ===== TMA producer: lanes 0-3 of warp 0 issue one of the four loads of a k-block each (A_hi, A_lo', W_hi, W_lo':
+        // an issuing thread is busy for a few hundred cycles per TMA instruction, four in a row paced the whole k loop).
+        // The warp runs ahead of the grid barrier with the WEIGHT halves of a phase's first stages; the activation
+        // halves follow once every CTA has finished the previous phase =====
+        {
             unsigned int it = 0;   // k-blocks issued so far (ring position)
             for (int ph = 0; ph < n_phases; ++ph) {
                 const CvsPhase& P = phases[ph];
                 if (P.kind != CVS_GEMM) continue;
-                const CUtensorMap* mAh = maps + P.a_map; const CUtensorMap* mAl = mAh + 1;
-                const CUtensorMap* mWh = maps + P.w_map; const CUtensorMap* mWl = mWh + 1;
+                const CUtensorMap* mymap = maps + ((lane < 2) ? P.a_map + lane : P.w_map + (lane - 2));   // lanes 0-3 only
+                const int my_off = lane == 0 ? 0 : (lane == 1 ? CS_A_BYTES : (lane == 2 ? 2 * CS_A_BYTES : 2 * CS_A_BYTES + CS_W_BYTES));
                 bool passed = false;
                 for (int item = blockIdx.x; item < P.items; item += G) {
                     const int tn = item / P.splitk, z = item - tn * P.splitk;
                     const int n0 = tn * CS_BN, kb0 = z * P.nkb;
+                    // every CTA walks the same A planes: each starts at its own k-block (the sum over k is commutative up
+                    // to fp32 rounding, fixed per tile) so that the CTAs do not hit the same L2 lines in lockstep
+                    const int rot = tn % P.nkb;
+                    auto kx = [&](int kb_) { int k = kb_ + rot; if (k >= P.nkb) k -= P.nkb; return (kb0 + k) * 64; };
+                    const int my_row = lane < 2 ? 0 : n0;
                     int kb = 0;
                     if (!passed) {
                         const int pre = min(P.nkb, CS_STAGES);
                         const unsigned int it0 = it;
                         for (; kb < pre; ++kb, ++it) {
                             const int s = it % CS_STAGES;
-                            mbar_wait(&bar_empty[s], ((it / CS_STAGES) & 1) ^ 1);
-                            mbar_expect_tx(&bar_full[s], CS_STAGE_BYTES);
-                            uint8_t* st = smem + s * CS_STAGE_BYTES;
-                            tma_load_2d(mWh, st + 2 * CS_A_BYTES, &bar_full[s], (kb0 + kb) * 64, n0);
-                            tma_load_2d(mWl, st + 2 * CS_A_BYTES + CS_W_BYTES, &bar_full[s], (kb0 + kb) * 64, n0);
+                            if (lane == 0) {
+                                mbar_wait(&bar_empty[s], ((it / CS_STAGES) & 1) ^ 1);
+                                mbar_expect_tx(&bar_full[s], CS_STAGE_BYTES);
+                            }
+                            __syncwarp();
+                            if (lane == 2 || lane == 3) tma_load_2d(mymap, smem + s * CS_STAGE_BYTES + my_off, &bar_full[s], kx(kb), my_row);
                         }
-                        if (ph > 0) wait_grid(bar, (unsigned int)ph * G);
+                        if (ph > 0 && lane == 0) wait_grid(bar, (unsigned int)ph * G);
+                        if (lane == 0) CVS_ST2(0);
+                        __syncwarp();
                         asm volatile("fence.proxy.async;" ::: "memory");   // peers' generic-proxy stores -> this thread's TMA reads
                         passed = true;
-                        for (int j = 0; j < pre; ++j) {
-                            const int s = (it0 + j) % CS_STAGES;
-                            uint8_t* st = smem + s * CS_STAGE_BYTES;
-                            tma_load_2d(mAh, st, &bar_full[s], (kb0 + j) * 64, 0);
-                            tma_load_2d(mAl, st + CS_A_BYTES, &bar_full[s], (kb0 + j) * 64, 0);
+                        if (lane < 2) {
+                            for (int j = 0; j < pre; ++j) {
+                                const int s = (it0 + j) % CS_STAGES;
+                                tma_load_2d(mymap, smem + s * CS_STAGE_BYTES + my_off, &bar_full[s], kx(j), 0);
+                            }
                         }
                     }
                     for (; kb < P.nkb; ++kb, ++it) {
                         const int s = it % CS_STAGES;
-                        mbar_wait(&bar_empty[s], ((it / CS_STAGES) & 1) ^ 1);
-                        mbar_expect_tx(&bar_full[s], CS_STAGE_BYTES);
-                        uint8_t* st = smem + s * CS_STAGE_BYTES;
-                        tma_load_2d(mWh, st + 2 * CS_A_BYTES, &bar_full[s], (kb0 + kb) * 64, n0);
-                        tma_load_2d(mWl, st + 2 * CS_A_BYTES + CS_W_BYTES, &bar_full[s], (kb0 + kb) * 64, n0);
-                        tma_load_2d(mAh, st, &bar_full[s], (kb0 + kb) * 64, 0);
-                        tma_load_2d(mAl, st + CS_A_BYTES, &bar_full[s], (kb0 + kb) * 64, 0);
+                        if (lane == 0) {
+                            mbar_wait(&bar_empty[s], ((it / CS_STAGES) & 1) ^ 1);
+                            mbar_expect_tx(&bar_full[s], CS_STAGE_BYTES);
+                        }
+                        __syncwarp();
+                        if (lane < 4) tma_load_2d(mymap, smem + s * CS_STAGE_BYTES + my_off, &bar_full[s], kx(kb), my_row);
                     }
+                    if (lane == 0) CVS_ST2(1);
                 }
             }
         }
@@ -237,6 +249,8 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
                     for (int kb = 0; kb < P.nkb; ++kb, ++it) {
                         const int s = it % CS_STAGES;
                         mbar_wait(&bar_full[s], (it / CS_STAGES) & 1);
+                        if (kb == 0) CVS_ST2(2);
+                        if (kb == P.nkb - 1) CVS_ST2(3);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t a_hi = smem_u32(smem + s * CS_STAGE_BYTES), a_lo = a_hi + CS_A_BYTES, w_hi = a_hi + 2 * CS_A_BYTES;
 #pragma unroll
@@ -248,6 +262,7 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
                         umma_commit(&bar_empty[s]);   // stage reusable once these MMAs have read it
                     }
                     umma_commit(&bar_acc_full);
+                    CVS_ST2(4);
                 }
             }
         }
@@ -264,6 +279,16 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
             // Every CTA must have finished phase ph - 1 before this one starts phase ph: attention / LayerNorm read what
             // the previous phase wrote, and the arrival count is only meaningful when nobody arrives for phase ph early
             // (a CTA without items in a GEMM phase would otherwise arrive twice before a slow CTA has arrived once).
+            // parameter vectors are cold in L2 every window (850 MB of weights stream through it): requested before the wait
+            if (P.kind == CVS_LN) {
+                for (int l = wt * 32; l < P.cols; l += CS_WORKERS * 32) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.gamma + l));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.beta + l));
+                    if (P.bias) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.bias + l));
+                }
+            } else if (P.kind == CVS_GEMM && P.epi != CVS_EPI_PARTIAL && int(blockIdx.x) < P.items) {
+                if (wt < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.bias + (blockIdx.x / P.splitk) * CS_BN + wt * 32));
+            }
             if (ph > 0) {
                 if (wt == 0) wait_grid(bar, (unsigned int)ph * G);
                 worker_sync();
@@ -273,7 +298,14 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
                 for (int item = blockIdx.x; item < P.items; item += G, ++tiles) {
                     const int tn = item / P.splitk, z = item - tn * P.splitk;
                     const int n0 = tn * CS_BN + half * (CS_BN / 2);
+                    // bias of this thread's 24 columns: requested before the accumulator is ready (cold parameter vectors)
+                    float4 bq[CS_BN / 8];
+                    if (P.epi != CVS_EPI_PARTIAL) {
+#pragma unroll
+                        for (int j = 0; j < CS_BN / 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(P.bias + n0) + j);
+                    }
                     mbar_wait(&bar_acc_full, tiles & 1);
+                    if (wt == 0) CVS_ST2(5);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int c0 = 0; c0 < CS_BN / 2; c0 += 8) {
@@ -288,8 +320,7 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
                                 __stcg(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
                                 __stcg(reinterpret_cast<float4*>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
                             } else {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(P.bias + n));
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(P.bias + n) + 1);
+                                const float4 b0 = bq[c0 / 4], b1 = bq[c0 / 4 + 1];
                                 v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
                                 if (P.epi == CVS_EPI_BIAS) {
                                     float* dst = P.C + (long long)row * P.ldc + n;
@@ -316,70 +347,172 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
                     const int Tp = (T | 1) + 2;
                     float* KV = reinterpret_cast<float*>(scratch);              // [64][Tp] (K^T) then [T][64] (V)
                     float* Ps = KV + CS_D * Tp;                                  // [CS_ATT_ROWS][Tp]
-                    float* inv_s = Ps + CS_ATT_ROWS * Tp;                        // [CS_ATT_ROWS]
+                    float* inv_s = Ps + P.att_rows * Tp;                         // [att_rows]
                     const int HD = P.heads * CS_D;
-                    const int nblk = (T + CS_ATT_ROWS - 1) / CS_ATT_ROWS;
+                    const int AR = P.att_rows;   // query rows per item (8, 16 or 24: what the scratch holds at this T)
+                    const int nblk = (T + AR - 1) / AR;
                     for (int item = blockIdx.x; item < P.items; item += G) {
-                        const int h = item / nblk, qbase = (item - h * nblk) * CS_ATT_ROWS;
-                        const int qend = min(T, qbase + CS_ATT_ROWS);
+                        const int h = item / nblk, qbase = (item - h * nblk) * AR;
+                        const int qend = min(T, qbase + AR);
                         const float* qkv = P.qkv;
-                        for (int i = wt; i < T * (CS_D / 4); i += CS_WORKERS) {
+                        if (wt == 0 && item == int(blockIdx.x)) CVS_ST2(0);
+                        constexpr int NLD = 8;   // float4 per thread: T * 16 <= 256 * 8  (T <= 128)
+                        float4 kreg[NLD], vreg[NLD];
+#pragma unroll
+                        for (int u = 0; u < NLD; ++u) {
+                            const int i = wt + u * CS_WORKERS;
                             const int t = i / (CS_D / 4), d4 = i - t * (CS_D / 4);
-                            const float4 k = __ldcg(reinterpret_cast<const float4*>(qkv + (long long)t * P.ldqkv + HD + h * CS_D) + d4);
-                            KV[(d4 * 4 + 0) * Tp + t] = k.x; KV[(d4 * 4 + 1) * Tp + t] = k.y;
-                            KV[(d4 * 4 + 2) * Tp + t] = k.z; KV[(d4 * 4 + 3) * Tp + t] = k.w;
+                            kreg[u] = t < T ? __ldcg(reinterpret_cast<const float4*>(qkv + (long long)t * P.ldqkv + HD + h * CS_D) + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        // the block's query rows of this warp (up to CS_ATT_ROWS / 8 = 3), requested together with K
+                        float4 qreg[CS_ATT_ROWS / 8][2];
+#pragma unroll
+                        for (int rr_ = 0; rr_ < CS_ATT_ROWS / 8; ++rr_) {
+                            const int qi = qbase + ww + rr_ * 8;
+                            // lane l holds q[2l], q[2l+1] ... as one float2 would need shuffles: keep two float4 = dims [8 (l%8) .. +8) of the row
+                            const int d8 = (lane & 7) * 8;
+                            qreg[rr_][0] = qi < qend ? __ldcg(reinterpret_cast<const float4*>(qkv + (long long)qi * P.ldqkv + h * CS_D + d8)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            qreg[rr_][1] = qi < qend ? __ldcg(reinterpret_cast<const float4*>(qkv + (long long)qi * P.ldqkv + h * CS_D + d8 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < NLD; ++u) {
+                            const int i = wt + u * CS_WORKERS;
+                            const int t = i / (CS_D / 4), d4 = i - t * (CS_D / 4);
+                            vreg[u] = t < T ? __ldcg(reinterpret_cast<const float4*>(qkv + (long long)t * P.ldqkv + 2 * HD + h * CS_D) + d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < NLD; ++u) {
+                            const int i = wt + u * CS_WORKERS;
+                            const int t = i / (CS_D / 4), d4 = i - t * (CS_D / 4);
+                            if (t < T) {
+                                KV[(d4 * 4 + 0) * Tp + t] = kreg[u].x; KV[(d4 * 4 + 1) * Tp + t] = kreg[u].y;
+                                KV[(d4 * 4 + 2) * Tp + t] = kreg[u].z; KV[(d4 * 4 + 3) * Tp + t] = kreg[u].w;
+                            }
+                        }
+                        if (wt == 0 && item == int(blockIdx.x)) CVS_ST2(1);
+                        // q rows -> shared memory (row-major [rows][64]) so every lane can read the whole row as broadcasts
+                        float* Qs = inv_s + AR;   // [att_rows][64]
+#pragma unroll
+                        for (int rr_ = 0; rr_ < CS_ATT_ROWS / 8; ++rr_) {
+                            if (lane < 8 && ww + rr_ * 8 < AR) {
+                                float* qd = Qs + (ww + rr_ * 8) * CS_D + lane * 8;
+                                *reinterpret_cast<float4*>(qd) = qreg[rr_][0];
+                                *reinterpret_cast<float4*>(qd + 4) = qreg[rr_][1];
+                            }
                         }
                         worker_sync();
-                        for (int qi = qbase + ww; qi < qend; qi += 8) {
-                            float qr[CS_D];
+                        if (wt == 0 && item == int(blockIdx.x)) CVS_ST2(2);
+                        {
+                            // scores of this warp's (up to three) rows qbase + ww + {0, 8, 16} together: a lane owns keys lane, lane + 32,
+                            // lane + 64, lane + 96; every K element read from shared memory feeds three rows, every q element (broadcast)
+                            // four keys - 12 independent FMA chains per lane instead of one load -> one FMA at a time.  Per (row, key)
+                            // the sum runs over d ascending in two interleaved partial sums (even / odd d), as in attn_kernel.
+                            constexpr int NR = CS_ATT_ROWS / 8, NK = 4;
+                            float a0[NR][NK], a1[NR][NK];
 #pragma unroll
-                            for (int d4 = 0; d4 < CS_D / 4; ++d4) {
-                                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(qkv + (long long)qi * P.ldqkv + h * CS_D) + d4);
-                                qr[d4 * 4] = t4.x; qr[d4 * 4 + 1] = t4.y; qr[d4 * 4 + 2] = t4.z; qr[d4 * 4 + 3] = t4.w;
-                            }
-                            float* ps = Ps + (qi - qbase) * Tp;
-                            float mx = -FLT_MAX;
-                            for (int j = lane; j < T; j += 32) {
-                                float a0 = 0.f, a1 = 0.f;
+                            for (int r_ = 0; r_ < NR; ++r_)
 #pragma unroll
-                                for (int d = 0; d < CS_D; d += 2) {
-                                    a0 = fmaf(qr[d], KV[d * Tp + j], a0);
-                                    a1 = fmaf(qr[d + 1], KV[(d + 1) * Tp + j], a1);
+                                for (int k_ = 0; k_ < NK; ++k_) { a0[r_][k_] = 0.f; a1[r_][k_] = 0.f; }
+                            int jk[NK];
+#pragma unroll
+                            for (int k_ = 0; k_ < NK; ++k_) jk[k_] = min(lane + 32 * k_, T - 1);   // clamped: the extra keys are never stored
+                            const float* qrow[NR];
+#pragma unroll
+                            for (int r_ = 0; r_ < NR; ++r_) qrow[r_] = Qs + min(ww + r_ * 8, AR - 1) * CS_D;   // clamped: rows past the block are never stored
+#pragma unroll 4
+                            for (int d = 0; d < CS_D; d += 4) {
+                                float4 qv[NR];
+#pragma unroll
+                                for (int r_ = 0; r_ < NR; ++r_) qv[r_] = *reinterpret_cast<const float4*>(qrow[r_] + d);
+                                float kx0[NK], kx1[NK], kx2[NK], kx3[NK];
+#pragma unroll
+                                for (int k_ = 0; k_ < NK; ++k_) {
+                                    kx0[k_] = KV[d * Tp + jk[k_]]; kx1[k_] = KV[(d + 1) * Tp + jk[k_]];
+                                    kx2[k_] = KV[(d + 2) * Tp + jk[k_]]; kx3[k_] = KV[(d + 3) * Tp + jk[k_]];
                                 }
-                                const float a = a0 + a1;
-                                ps[j] = a;
-                                mx = fmaxf(mx, a);
+#pragma unroll
+                                for (int r_ = 0; r_ < NR; ++r_)
+#pragma unroll
+                                    for (int k_ = 0; k_ < NK; ++k_) {
+                                        a0[r_][k_] = fmaf(qv[r_].x, kx0[k_], a0[r_][k_]);
+                                        a1[r_][k_] = fmaf(qv[r_].y, kx1[k_], a1[r_][k_]);
+                                        a0[r_][k_] = fmaf(qv[r_].z, kx2[k_], a0[r_][k_]);
+                                        a1[r_][k_] = fmaf(qv[r_].w, kx3[k_], a1[r_][k_]);
+                                    }
                             }
-                            mx = warp_max(mx);
-                            float sum = 0.f;
-                            for (int j = lane; j < T; j += 32) { const float e = expf(ps[j] - mx); ps[j] = e; sum += e; }
-                            sum = warp_sum(sum);
-                            if (lane == 0) inv_s[qi - qbase] = 1.0f / sum;
+#pragma unroll
+                            for (int r_ = 0; r_ < NR; ++r_) {
+                                const int qi = qbase + ww + r_ * 8;
+                                if (qi >= qend || ww + r_ * 8 >= AR) continue;
+                                float* ps = Ps + (qi - qbase) * Tp;
+                                float sc[NK];
+                                float mx = -FLT_MAX;
+#pragma unroll
+                                for (int k_ = 0; k_ < NK; ++k_) {
+                                    sc[k_] = a0[r_][k_] + a1[r_][k_];
+                                    if (lane + 32 * k_ < T) mx = fmaxf(mx, sc[k_]);
+                                }
+                                mx = warp_max(mx);
+                                float sum = 0.f;
+#pragma unroll
+                                for (int k_ = 0; k_ < NK; ++k_) {
+                                    if (lane + 32 * k_ < T) { const float e = expf(sc[k_] - mx); ps[lane + 32 * k_] = e; sum += e; }
+                                }
+                                sum = warp_sum(sum);
+                                if (lane == 0) inv_s[qi - qbase] = 1.0f / sum;
+                            }
                         }
-                        worker_sync();   // scores done: K^T may be overwritten
-                        for (int i = wt; i < T * (CS_D / 4); i += CS_WORKERS) {
+                        if (wt == 0 && item == int(blockIdx.x)) CVS_ST2(3);
+                        worker_sync();   // scores done: K^T may be overwritten by V (already in registers)
+                        if (wt == 0 && item == int(blockIdx.x)) CVS_ST2(4);
+#pragma unroll
+                        for (int u = 0; u < NLD; ++u) {
+                            const int i = wt + u * CS_WORKERS;
                             const int t = i / (CS_D / 4), d4 = i - t * (CS_D / 4);
-                            reinterpret_cast<float4*>(KV + (size_t)t * CS_D)[d4] =
-                                __ldcg(reinterpret_cast<const float4*>(qkv + (long long)t * P.ldqkv + 2 * HD + h * CS_D) + d4);
+                            if (t < T) reinterpret_cast<float4*>(KV + (size_t)t * CS_D)[d4] = vreg[u];
                         }
                         worker_sync();
-                        for (int qi = qbase + ww; qi < qend; qi += 8) {
-                            const float* ps = Ps + (qi - qbase) * Tp;
-                            float o0 = 0.f, o1 = 0.f;
-                            for (int j = 0; j < T; ++j) {
-                                const float pj = ps[j];
-                                o0 = fmaf(pj, KV[j * CS_D + lane], o0);
-                                o1 = fmaf(pj, KV[j * CS_D + lane + 32], o1);
+                        {
+                            // o = sum_j p_j v_j, j ascending, for the warp's three rows together (every V element feeds three rows)
+                            constexpr int NR = CS_ATT_ROWS / 8;
+                            float o0[NR], o1[NR];
+                            const float* psr[NR];
+#pragma unroll
+                            for (int r_ = 0; r_ < NR; ++r_) { o0[r_] = 0.f; o1[r_] = 0.f; psr[r_] = Ps + min(ww + r_ * 8, AR - 1) * Tp; }
+                            int j = 0;
+                            for (; j + 4 <= T; j += 4) {
+                                float va[4], vb[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) { va[u] = KV[(j + u) * CS_D + lane]; vb[u] = KV[(j + u) * CS_D + lane + 32]; }
+#pragma unroll
+                                for (int r_ = 0; r_ < NR; ++r_) {
+                                    const float p0 = psr[r_][j], p1 = psr[r_][j + 1], p2 = psr[r_][j + 2], p3 = psr[r_][j + 3];
+                                    o0[r_] = fmaf(p0, va[0], o0[r_]); o1[r_] = fmaf(p0, vb[0], o1[r_]);
+                                    o0[r_] = fmaf(p1, va[1], o0[r_]); o1[r_] = fmaf(p1, vb[1], o1[r_]);
+                                    o0[r_] = fmaf(p2, va[2], o0[r_]); o1[r_] = fmaf(p2, vb[2], o1[r_]);
+                                    o0[r_] = fmaf(p3, va[3], o0[r_]); o1[r_] = fmaf(p3, vb[3], o1[r_]);
+                                }
                             }
-                            const float inv = inv_s[qi - qbase];
-                            o0 *= inv; o1 *= inv;
-                            // planes of the attention output (the A operand of the out-projection)
-                            const __half h0 = __float2half_rn(o0), h1 = __float2half_rn(o1);
-                            const __half l0 = __float2half_rn((o0 - __half2float(h0)) * CS_LO_SCALE), l1 = __float2half_rn((o1 - __half2float(h1)) * CS_LO_SCALE);
-                            __half* ph_ = reinterpret_cast<__half*>(P.p_hi) + (long long)qi * P.ldp + h * CS_D;
-                            __half* pl_ = reinterpret_cast<__half*>(P.p_lo) + (long long)qi * P.ldp + h * CS_D;
-                            ph_[lane] = h0; ph_[lane + 32] = h1; pl_[lane] = l0; pl_[lane + 32] = l1;
+                            for (; j < T; ++j) {
+                                const float v0 = KV[j * CS_D + lane], v1 = KV[j * CS_D + lane + 32];
+#pragma unroll
+                                for (int r_ = 0; r_ < NR; ++r_) { const float pj = psr[r_][j]; o0[r_] = fmaf(pj, v0, o0[r_]); o1[r_] = fmaf(pj, v1, o1[r_]); }
+                            }
+#pragma unroll
+                            for (int r_ = 0; r_ < NR; ++r_) {
+                                const int qi = qbase + ww + r_ * 8;
+                                if (qi >= qend || ww + r_ * 8 >= AR) continue;
+                                const float inv = inv_s[qi - qbase];
+                                const float x0 = o0[r_] * inv, x1 = o1[r_] * inv;
+                                // planes of the attention output (the A operand of the out-projection)
+                                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                                const __half l0 = __float2half_rn((x0 - __half2float(h0)) * CS_LO_SCALE), l1 = __float2half_rn((x1 - __half2float(h1)) * CS_LO_SCALE);
+                                __half* ph_ = reinterpret_cast<__half*>(P.p_hi) + (long long)qi * P.ldp + h * CS_D;
+                                __half* pl_ = reinterpret_cast<__half*>(P.p_lo) + (long long)qi * P.ldp + h * CS_D;
+                                ph_[lane] = h0; ph_[lane + 32] = h1; pl_[lane] = l0; pl_[lane + 32] = l1;
+                            }
                         }
+                        if (wt == 0 && item == int(blockIdx.x)) CVS_ST2(5);
                         worker_sync();   // the next item restages K^T
                     }
                 } else if (P.kind == CVS_LN) {
@@ -388,19 +521,37 @@ cvstack_kernel(const CUtensorMap* __restrict__ maps, const CvsPhase* __restrict_
                     for (int item = blockIdx.x; item < P.items; item += G) {
                         const int r = item * 8 + ww;
                         if (r >= T) continue;
+                        // the loads of three float4 columns (partials, residual, bias) in flight at once - a dependent chain of L2
+                        // round trips otherwise - then summed in the fixed order  ((p0 + p1 + p2 + p3) + bias) + residual
                         float4 v[8];
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (i >= nv) break;
-                            const int c = i * 128 + lane * 4;
-                            float4 a = __ldcg(reinterpret_cast<const float4*>(P.X + (long long)r * P.ldx + c));
-                            for (int zz = 1; zz < P.S; ++zz) {
-                                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(P.X + (long long)zz * P.slab + (long long)r * P.ldx + c));
-                                a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w;
+                        for (int i0 = 0; i0 < 8; i0 += 3) {
+                            float4 pz[3][CVS_SPLITK], rr[3], bb[3];
+#pragma unroll
+                            for (int u = 0; u < 3; ++u) {
+                                const int i = i0 + u;
+                                if (i >= 8 || i >= nv) break;
+                                const int c = i * 128 + lane * 4;
+#pragma unroll
+                                for (int zz = 0; zz < CVS_SPLITK; ++zz)
+                                    pz[u][zz] = zz < P.S ? __ldcg(reinterpret_cast<const float4*>(P.X + (long long)zz * P.slab + (long long)r * P.ldx + c)) : zero4;
+                                rr[u] = P.R ? __ldcg(reinterpret_cast<const float4*>(P.R + (long long)r * P.ldr + c)) : zero4;
+                                bb[u] = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + c)) : zero4;
                             }
-                            if (P.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + c)); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-                            if (P.R) { const float4 t4 = __ldcg(reinterpret_cast<const float4*>(P.R + (long long)r * P.ldr + c)); a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w; }
-                            v[i] = a;
+#pragma unroll
+                            for (int u = 0; u < 3; ++u) {
+                                const int i = i0 + u;
+                                if (i >= 8 || i >= nv) break;
+                                float4 a = pz[u][0];
+#pragma unroll
+                                for (int zz = 1; zz < CVS_SPLITK; ++zz) {
+                                    if (zz < P.S) { a.x += pz[u][zz].x; a.y += pz[u][zz].y; a.z += pz[u][zz].z; a.w += pz[u][zz].w; }
+                                }
+                                if (P.bias) { a.x += bb[u].x; a.y += bb[u].y; a.z += bb[u].z; a.w += bb[u].w; }
+                                if (P.R) { a.x += rr[u].x; a.y += rr[u].y; a.z += rr[u].z; a.w += rr[u].w; }
+                                v[i] = a;
+                            }
                         }
                         float s = 0.f;
 #pragma unroll
@@ -512,5 +663,6 @@ int launch_cvstack(const CvsDev& c, cudaStream_t stream) {
 }
 
 void cvstack_debug_read(long long* out, int n) { cudaMemcpyFromSymbol(out, g_cvs_stamp, sizeof(long long) * size_t(n)); }
+void cvstack_debug_read2(long long* out, int n) { cudaMemcpyFromSymbol(out, g_cvs_stamp2, sizeof(long long) * size_t(n)); }
 
 }  // namespace rvc

@@ -609,11 +609,13 @@ void chain_schedule_gemm(PB& b, GemmOp& g, int G) {
         const int ct = v.bn / (32 / v.lk);
         // cycles per unit of K for one CTA: FMA issue (~60% of 128 lanes), shared-memory wavefronts (one 16-byte
         // broadcast per row + 4 per W column, 8 * LK quads in flight), L2 -> SM bytes at ~64 B/clk; + per-k-tile sync
-        const double per_k = std::max(std::max(v.bm * v.bn / 77.0, 1.5 * (v.bm + 4.0 * ct) / (4.0 * v.lk)), (v.bm + v.bn) * 4 / 64.0) + 150.0 / v.bk;
+        // (RVC_CHAIN_BW = assumed L2 -> SM bytes per clock of the cp.async ring, RVC_CHAIN_SK = cycles charged for a split-K round trip)
+        static const double kBw = double(sched_env("RVC_CHAIN_BW", 64)), kSk = double(sched_env("RVC_CHAIN_SK", 4000));
+        const double per_k = std::max(std::max(v.bm * v.bn / 77.0, 1.5 * (v.bm + 4.0 * ct) / (4.0 * v.lk)), (v.bm + v.bn) * 4 / kBw) + 150.0 / v.bk;
         for (int sk = 1; sk <= 8; sk *= 2) {
             if (sk > 1 && (tiles * sk > G || nkt / sk < 2)) break;
             const int waves = (tiles * sk + G - 1) / G;
-            const double cost = waves * (double(nkt / sk + (nkt % sk ? 1 : 0)) * v.bk * per_k + 2500.0) + (sk > 1 ? 4000.0 : 0.0);
+            const double cost = waves * (double(nkt / sk + (nkt % sk ? 1 : 0)) * v.bk * per_k + 2500.0) + (sk > 1 ? kSk : 0.0);
             if (cost < best - 1e-9) {
                 best = cost; g.ch_variant = v.id; g.ch_tiles_m = tm; g.ch_tiles_n = tn; g.ch_splitk = sk;
             }
@@ -773,8 +775,17 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     // The lane whose ops are emitted (= whose graph nodes are created) first gets the SMs first when both lanes have
     // work ready.  Since the tcgen05 GEMMs got faster the F0 chain is the longer branch: it goes first.
     if (f0_first) emit_f0();
+    const size_t cv_first_op = b.plan.ops.size();
     x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
     if (!b.ok) return false;
+    {
+        // ContentVec finishes ~0.3 ms before the F0 lane (profiles/README.md, sparse timeline): a CTA budget below the
+        // tcgen05 default (96) leaves the F0 lane - the critical path of the front end - more SMs (RVC_CV_WANT; 0 = scheduler default)
+        static const int cv_want = sched_env("RVC_CV_WANT", 80);
+        if (cv_want > 0 && ml && opt.nb <= 1)
+            for (size_t i = cv_first_op; i < b.plan.ops.size(); ++i)
+                if (b.plan.ops[i].kind == OP_GEMM && b.plan.ops[i].gemm.cta_budget == 0) b.plan.ops[i].gemm.cta_budget = cv_want;
+    }
     if (!f0_first) emit_f0();
     plan.f0_T = fo.T;
     const int C = cvi->out_dim;

@@ -263,6 +263,16 @@ class RvcInfer:
                                           out.ctypes.data_as(c_void_p), c_size_t(cap), byref(t)))
         return out[:128 * t.value].reshape(128, t.value).copy()
 
+    def decode_salience(self, salience):
+        """rmvpe.rs:118-133, 243-248 on given salience rows (T, 360) -> (f0[T] f32, argmax[T] i32)."""
+        sal = _f32(salience)
+        assert sal.ndim == 2 and sal.shape[1] == 360
+        f0 = np.empty(sal.shape[0], np.float32)
+        am = np.empty(sal.shape[0], np.int32)
+        self._chk(self._L.rvc_decode_salience(self._h, sal.ctypes.data_as(c_void_p), c_size_t(sal.shape[0]),
+                                              f0.ctypes.data_as(c_void_p), am.ctypes.data_as(c_void_p)))
+        return f0, am
+
     def knn_search(self, queries, k: int):
         q = _f32(queries)
         d2 = np.empty((q.shape[0], k), np.float32)
