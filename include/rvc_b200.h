@@ -146,6 +146,33 @@ int rvc_knn_search(rvc_ctx* ctx, const float* queries, size_t q, size_t c, int32
  * Counts those recomputations since the index was set (0 on every test and bench input). */
 int rvc_knn_fallbacks(rvc_ctx* ctx, uint64_t* total);
 
+/* ---- the streaming loop around the call, device-resident (obs-rvc/src/lib.rs:186-300 state, :659-795 process_one_frame) ----
+ * rvc_stream_open derives RvcInferenceState's sizes from the OBS settings (lib.rs:200-226), builds the two rubato
+ * FftFixedInOut resamplers (lib.rs:236-242; OBS rate -> 16 kHz, model rate -> OBS rate) and the ring buffers on the
+ * device.  rvc_process_frame is process_one_frame: append the new block, down-sample, RvcInfer::infer, up-sample,
+ * envelope mixing (rms_mix_rate < 1), SOLA offset + sin^2 cross-fade - ONE host-to-device copy of sample_frame_size
+ * samples in, ONE device-to-host copy of sample_frame_size samples out.  One open stream per context. */
+typedef struct rvc_stream_config {
+    uint32_t sample_rate;            /* OBS audio rate (lib.rs:186) */
+    int32_t pitch_shift;             /* lib.rs:262 */
+    double sample_length;            /* seconds, lib.rs:188 (default 0.30) */
+    double crossfade_length;         /* lib.rs:189 (0.07) */
+    double extra_inference_time;     /* lib.rs:190 (2.00) */
+    double rms_mix_rate;             /* lib.rs:265 (0.00): envelope mixing runs while < 1 */
+    int32_t skip_inference;          /* lib.rs:198: the 16 kHz tail is passed through instead of the model */
+    int32_t reserved[7];
+} rvc_stream_config;
+void rvc_stream_config_default(rvc_stream_config* cfg);
+int rvc_stream_open(rvc_ctx* ctx, const rvc_stream_config* cfg, uint32_t* sample_frame_size);
+int rvc_stream_close(rvc_ctx* ctx);
+int rvc_stream_set(rvc_ctx* ctx, int32_t pitch_shift, double rms_mix_rate);      /* settings that change without a rebuild */
+int rvc_stream_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes); /* JSON of the derived sizes */
+int rvc_process_frame(rvc_ctx* ctx, const float* input, float* output, uint32_t* sola_offset);
+/* One chunk through the rubato 0.15.0 FftFixedInOut equivalent (n_in must be a multiple of fs_in / gcd): out = n_in * fs_out /
+ * fs_in samples; overlap_inout ([n_out]) carries the overlap-add state between calls (zeros at the start). */
+int rvc_resample_chunk(rvc_ctx* ctx, uint32_t fs_in, uint32_t fs_out, const float* in, size_t n_in, float* overlap_inout,
+                       float* out, size_t cap, size_t* n_out);
+
 /* ---- streaming glue around the call ("next" row) ---------------------------------
  * rt_utils::envelop_mixing(input, output, sample_rate, mix_rate) - obs-rvc/src/rt_utils.rs:119-132.
  * `output` (n_out samples) is modified in place; `input` must hold at least n_out samples.

@@ -30,6 +30,7 @@
 #include "launch.h"
 #include "model.h"
 #include "pdl.cuh"
+#include "resample.h"
 
 using namespace rvc;
 
@@ -175,7 +176,38 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 }  // namespace
 
+// Device-resident state of the streaming loop around the call (obs-rvc/src/lib.rs RvcInferenceState, :88-130, sizes
+// :200-245): ring buffers at the OBS rate and at 16 kHz, the two rubato resamplers as polyphase tables + overlaps, the
+// SOLA buffer.  One per context (one OBS filter instance drives one engine).
+struct ResamplerDev {
+    rvc::ResampleTable t;          // host copy of the geometry (table moved to the device)
+    float* kappa = nullptr;
+    float* overlap[2] = {nullptr, nullptr};
+    int cur = 0;
+    void release() { cudaFree(kappa); cudaFree(overlap[0]); cudaFree(overlap[1]); kappa = nullptr; overlap[0] = overlap[1] = nullptr; }
+};
+struct StreamState {
+    bool open = false;
+    rvc_stream_config cfg{};
+    int zc = 0, sample_frame_time = 0, sample_frame_size = 0, sample_frame_16k = 0, crossfade = 0, sola_buf = 0, sola_search = 0,
+        extra = 0, in_size = 0, in16k_size = 0, ret_len = 0, ret_size = 0, model_sr = 0, skip_head = 0, up_out = 0;
+    ResamplerDev down, up;
+    float* inbuf[2] = {nullptr, nullptr};
+    float* in16k[2] = {nullptr, nullptr};
+    int cur = 0;
+    float* scratch = nullptr;      // frame in | down out | model out | up out | rms1 | rms2 | cor | offset | sola | block
+    size_t scratch_floats = 0;
+    uint64_t frames = 0;
+    void release() {
+        down.release(); up.release();
+        for (int i = 0; i < 2; ++i) { cudaFree(inbuf[i]); cudaFree(in16k[i]); inbuf[i] = in16k[i] = nullptr; }
+        cudaFree(scratch); scratch = nullptr; open = false;
+    }
+};
+
 struct rvc_ctx {
+    StreamState stream;
+    std::map<std::string, ResamplerDev> resamplers;   // rvc_resample_chunk: tables by (fs_in, fs_out, chunk)
     std::string data_path, err;
     rvc_config cfg{};
     cudaStream_t streams[MAX_LANES] = {nullptr};
@@ -841,6 +873,8 @@ void rvc_destroy(rvc_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     ctx->sync_all();
     ctx->plans.clear();
+    ctx->stream.release();
+    for (auto& kv : ctx->resamplers) kv.second.release();
     ctx->cv.unload(); ctx->f0.unload(); ctx->syn.unload(); ctx->index.unload(); ctx->state.release();
     for (auto ev : ctx->events) cudaEventDestroy(ev);
     for (auto ev : ctx->timers) if (ev) cudaEventDestroy(ev);
@@ -1278,7 +1312,7 @@ int rvc_envelop_mixing(rvc_ctx* ctx, const float* input, size_t n_in, float* out
 
 static int sola_common(rvc_ctx* ctx, const float* x, size_t n, const float* sola, uint32_t buf, uint32_t search, float** d_x_out,
                        float** d_sola_out, int** d_off_out) {
-    if (!x || !sola || buf == 0 || size_t(buf) + search > n || n + buf + search + 64 > size_t(StateLayout::AUDIO_CAP))
+    if (!x || !sola || buf == 0 || size_t(buf) + search > n || 2 * n + buf + search + 96 > size_t(StateLayout::AUDIO_CAP))   // x | sola | cor | offset | block (<= n)
         return ctx->fail(RVC_ERR_BAD_SHAPE, "bad SOLA shape");
     cudaStream_t s = ctx->streams[0];
     float* base = state_audio(ctx);
@@ -1321,6 +1355,201 @@ int rvc_sola_crossfade(rvc_ctx* ctx, const float* infer_out, size_t n, float* so
     CK(cudaMemcpyAsync(&h, doff, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (offset) *offset = uint32_t(h);
+    return RVC_OK;
+}
+
+// ---- streaming loop around the call: obs-rvc/src/lib.rs:186-300 (state), :659-795 (process_one_frame) ----
+static int upload_resampler(rvc_ctx* ctx, int fs_in, int fs_out, int chunk, ResamplerDev& r) {
+    r.release();
+    if (!build_resample_table(fs_in, fs_out, chunk, r.t)) return ctx->fail(RVC_ERR_BAD_SHAPE, "bad resampler arguments");
+    if (size_t(2 * r.t.n_in + 31 * r.t.a + 1) * 4 > size_t(220 * 1024))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "resampler chunk too long for the polyphase kernel (" + std::to_string(r.t.n_in) + " samples)");
+    CK(cudaMalloc(&r.kappa, r.t.kappa.size() * sizeof(float)));
+    CK(cudaMemcpy(r.kappa, r.t.kappa.data(), r.t.kappa.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&r.overlap[i], size_t(r.t.n_out) * sizeof(float)));
+        CK(cudaMemset(r.overlap[i], 0, size_t(r.t.n_out) * sizeof(float)));
+    }
+    r.cur = 0;
+    std::vector<float>().swap(r.t.kappa);
+    return RVC_OK;
+}
+
+static void run_resampler(rvc_ctx* ctx, ResamplerDev& r, const float* x, float* out, cudaStream_t s) {
+    launch_resample(x, r.kappa, r.overlap[r.cur], r.overlap[r.cur ^ 1], out, r.t.a, r.t.b, r.t.period, r.t.n_in, r.t.n_out, s);
+    r.cur ^= 1;
+    ctx->total_launches++;
+}
+
+void rvc_stream_config_default(rvc_stream_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    // defaults of the OBS filter's settings (lib.rs:179,188-190,262-265)
+    c->sample_rate = 48000; c->sample_length = 0.30; c->crossfade_length = 0.07; c->extra_inference_time = 2.00;
+    c->rms_mix_rate = 0.0; c->pitch_shift = 12; c->skip_inference = 0;
+}
+
+static long long rust_round(double x) { return (long long)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
+
+int rvc_stream_open(rvc_ctx* ctx, const rvc_stream_config* cfg, uint32_t* sample_frame_size) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!cfg || cfg->sample_rate < 8000 || cfg->sample_rate % 100 != 0) return ctx->fail(RVC_ERR_INVALID_ARG, "bad stream config");
+    if (!cfg->skip_inference && !ctx->syn.loaded) return ctx->fail(RVC_ERR_MODEL_NOT_LOADED, "ModelNotLoaded");
+    StreamState& st = ctx->stream;
+    ctx->sync_all();
+    st.release();
+    st.cfg = *cfg;
+    const int sr = int(cfg->sample_rate), zc = sr / 100;
+    st.zc = zc;
+    st.sample_frame_time = int(rust_round(cfg->sample_length * sr / zc));
+    st.sample_frame_size = st.sample_frame_time * zc;
+    st.sample_frame_16k = st.sample_frame_time * 160;
+    st.crossfade = int(rust_round(cfg->crossfade_length * sr / zc)) * zc;
+    st.sola_buf = std::min(st.crossfade, 4 * zc);
+    st.sola_search = zc;
+    st.extra = int(rust_round(cfg->extra_inference_time * sr / zc)) * zc;
+    st.in_size = st.extra + st.crossfade + st.sola_search + st.sample_frame_size;
+    st.in16k_size = 160 * st.in_size / zc;
+    st.ret_len = (st.sample_frame_size + st.sola_buf + st.sola_search) / zc;
+    st.model_sr = cfg->skip_inference ? 16000 : ctx->syi.sr;
+    st.ret_size = st.ret_len * (st.model_sr / 100);
+    st.skip_head = st.extra / zc;
+    if (st.sample_frame_time <= 0 || st.sola_buf <= 0 || st.in16k_size > int(StateLayout::PCM_CAP))
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "stream geometry out of range");
+    rc = upload_resampler(ctx, sr, 16000, st.sample_frame_size + 2 * zc, st.down); if (rc) return rc;
+    rc = upload_resampler(ctx, st.model_sr, sr, st.ret_size, st.up); if (rc) return rc;
+    // the loop only works when the resamplers consume exactly the chunk they are given (rubato would return an error otherwise)
+    if (st.down.t.n_in != st.sample_frame_size + 2 * zc || st.down.t.n_out != (st.sample_frame_time + 2) * 160 || st.up.t.n_in != st.ret_size)
+        return ctx->fail(RVC_ERR_BAD_SHAPE, "resampler chunk sizes do not tile the frame");
+    st.up_out = st.up.t.n_out;
+    if (st.up_out < st.sola_search + st.sample_frame_size + st.sola_buf) return ctx->fail(RVC_ERR_BAD_SHAPE, "upsampled block shorter than search + frame + fade");
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMalloc(&st.inbuf[i], size_t(st.in_size) * 4)); CK(cudaMemset(st.inbuf[i], 0, size_t(st.in_size) * 4));
+        CK(cudaMalloc(&st.in16k[i], size_t(st.in16k_size) * 4)); CK(cudaMemset(st.in16k[i], 0, size_t(st.in16k_size) * 4));
+    }
+    st.scratch_floats = size_t(st.sample_frame_size) * 2 + size_t(st.down.t.n_out) + size_t(st.ret_size) + size_t(st.up_out) + 2 * 2048 +
+                        size_t(st.sola_search) + 64 + size_t(st.sola_buf) + 1024;
+    CK(cudaMalloc(&st.scratch, st.scratch_floats * 4));
+    CK(cudaMemset(st.scratch, 0, st.scratch_floats * 4));
+    st.cur = 0; st.frames = 0; st.open = true;
+    if (sample_frame_size) *sample_frame_size = uint32_t(st.sample_frame_size);
+    return RVC_OK;
+}
+
+int rvc_stream_close(rvc_ctx* ctx) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->sync_all();
+    ctx->stream.release();
+    return RVC_OK;
+}
+
+int rvc_stream_set(rvc_ctx* ctx, int32_t pitch_shift, double rms_mix_rate) {
+    if (!ctx || !ctx->stream.open) return RVC_ERR_INVALID_ARG;
+    ctx->stream.cfg.pitch_shift = pitch_shift; ctx->stream.cfg.rms_mix_rate = rms_mix_rate;
+    return RVC_OK;
+}
+
+int rvc_stream_info(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_bytes) {
+    if (!ctx || !ctx->stream.open) return RVC_ERR_INVALID_ARG;
+    const StreamState& st = ctx->stream;
+    char buf[640];
+    int n = std::snprintf(buf, sizeof(buf),
+        "{\"sample_rate\": %u, \"sample_frame_size\": %d, \"sample_frame_16k\": %d, \"crossfade_frame_size\": %d, \"sola_buffer_frame_size\": %d, "
+        "\"sola_search_frame_size\": %d, \"extra_frame_size\": %d, \"input_buffer_size\": %d, \"input_buffer_16k_size\": %d, "
+        "\"model_return_length\": %d, \"model_return_size\": %d, \"model_sample_rate\": %d, \"skip_head\": %d, \"down\": [%d, %d], \"up\": [%d, %d], \"frames\": %llu}",
+        st.cfg.sample_rate, st.sample_frame_size, st.sample_frame_16k, st.crossfade, st.sola_buf, st.sola_search, st.extra, st.in_size, st.in16k_size,
+        st.ret_len, st.ret_size, st.model_sr, st.skip_head, st.down.t.n_in, st.down.t.n_out, st.up.t.n_in, st.up.t.n_out, (unsigned long long)st.frames);
+    if (out_bytes) *out_bytes = size_t(n);
+    if (out && cap_bytes > 0) { size_t m = size_t(n) < cap_bytes - 1 ? size_t(n) : cap_bytes - 1; std::memcpy(out, buf, m); out[m] = 0; }
+    return RVC_OK;
+}
+
+// process_one_frame (lib.rs:659-795): one H2D of the new block, everything else device-resident, one D2H of the result
+int rvc_process_frame(rvc_ctx* ctx, const float* input, float* output, uint32_t* sola_offset) {
+    int rc = enter(ctx); if (rc) return rc;
+    StreamState& st = ctx->stream;
+    if (!st.open) return ctx->fail(RVC_ERR_INVALID_ARG, "no open stream (rvc_stream_open)");
+    if (!input || !output) return ctx->fail(RVC_ERR_INVALID_ARG, "null input / output");
+    cudaStream_t s = ctx->streams[0];
+    float* d_frame = st.scratch;
+    float* d_down = d_frame + st.sample_frame_size;
+    float* d_model = d_down + st.down.t.n_out;
+    float* d_up = d_model + st.ret_size;
+    float* d_r1 = d_up + st.up_out; float* d_r2 = d_r1 + 2048;
+    float* d_cor = d_r2 + 2048;
+    int* d_off = reinterpret_cast<int*>(d_cor + st.sola_search + 32);
+    float* d_sola = d_cor + st.sola_search + 64;
+    float* d_block = d_sola + st.sola_buf + 512;
+    const int p = st.cur, q = p ^ 1;
+    CK(cudaMemcpyAsync(d_frame, input, size_t(st.sample_frame_size) * 4, cudaMemcpyHostToDevice, s));
+    // lib.rs:661-669: both ring buffers move left by one frame; the new block lands at the end of the OBS-rate one
+    launch_shift_append(st.inbuf[q], st.inbuf[p], st.in_size, st.sample_frame_size, d_frame, st.sample_frame_size, s);
+    launch_shift_append(st.in16k[q], st.in16k[p], st.in16k_size, st.sample_frame_16k, nullptr, 0, s);
+    ctx->total_launches += 2;
+    // lib.rs:671-683: the last frame + 2 zc samples -> 16 kHz; the first 160 samples of the result are dropped
+    run_resampler(ctx, st.down, st.inbuf[q] + (st.in_size - st.sample_frame_size - 2 * st.zc), d_down, s);
+    const int copy_n = (st.sample_frame_time + 1) * 160;
+    CK(cudaMemcpyAsync(st.in16k[q] + (st.in16k_size - copy_n), d_down + 160, size_t(copy_n) * 4, cudaMemcpyDeviceToDevice, s));
+    st.cur = q;
+    if (st.cfg.skip_inference) {
+        CK(cudaMemcpyAsync(d_model, st.in16k[q] + (st.in16k_size - st.ret_size), size_t(st.ret_size) * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+        size_t got = 0;
+        rc = enqueue_infer(ctx, st.in16k[q], size_t(st.in16k_size), true, uint32_t(st.sample_frame_16k), st.cfg.pitch_shift, uint32_t(st.skip_head),
+                           uint32_t(st.ret_len), d_model, true, size_t(st.ret_size), &got);
+        if (rc) return rc;
+        if (int(got) != st.ret_size) return ctx->fail(RVC_ERR_BAD_SHAPE, "model output size mismatch (lib.rs:728)");
+    }
+    run_resampler(ctx, st.up, d_model, d_up, s);
+    if (st.cfg.rms_mix_rate < 1.0) {   // lib.rs:758-765
+        const int n_out = st.up_out, zc = st.zc;
+        const int nfr = (n_out + (4 * zc) / 2 * 2 - 4 * zc) / zc + 1;
+        if (nfr > 2048 || nfr < 2) return ctx->fail(RVC_ERR_BAD_SHAPE, "too many rms frames");
+        launch_rms(st.inbuf[q] + st.extra, n_out, 4 * zc, zc, d_r1, nfr, s);
+        launch_rms(d_up, n_out, 4 * zc, zc, d_r2, nfr, s);
+        launch_envelop_mix(d_up, n_out, d_r1, d_r2, nfr, float(1.0 - st.cfg.rms_mix_rate), nullptr, nullptr, s);
+        ctx->total_launches += 3;
+    }
+    // lib.rs:767-794: SOLA offset, sin^2 cross-fade with the previous tail, new tail, the emitted block
+    launch_sola(d_up, d_sola, st.sola_buf, st.sola_search, d_cor, d_off, s);
+    launch_sola_crossfade(d_up, d_off, d_sola, st.sola_buf, st.sample_frame_size, d_block, s);
+    ctx->total_launches += 4;
+    CK(cudaGetLastError());
+    int h = 0;
+    CK(cudaMemcpyAsync(output, d_block, size_t(st.sample_frame_size) * 4, cudaMemcpyDeviceToHost, s));
+    if (sola_offset) CK(cudaMemcpyAsync(&h, d_off, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (sola_offset) *sola_offset = uint32_t(h);
+    st.frames++;
+    return RVC_OK;
+}
+
+// one chunk through a rubato-equivalent resampler (unit entry for the parity tests): overlap_inout carries the
+// overlap-add state between calls ([n_out] floats, zeros at the start of a stream)
+int rvc_resample_chunk(rvc_ctx* ctx, uint32_t fs_in, uint32_t fs_out, const float* in, size_t n_in, float* overlap_inout, float* out,
+                       size_t cap, size_t* n_out) {
+    int rc = enter(ctx); if (rc) return rc;
+    if (!in || !out || !overlap_inout || n_in == 0) return ctx->fail(RVC_ERR_INVALID_ARG, "null buffers");
+    const std::string key = std::to_string(fs_in) + ">" + std::to_string(fs_out) + ":" + std::to_string(n_in);
+    auto it = ctx->resamplers.find(key);
+    if (it == ctx->resamplers.end()) {
+        ResamplerDev r;
+        rc = upload_resampler(ctx, int(fs_in), int(fs_out), int(n_in), r); if (rc) { r.release(); return rc; }
+        it = ctx->resamplers.emplace(key, r).first;
+    }
+    ResamplerDev& r = it->second;
+    if (size_t(r.t.n_in) != n_in) return ctx->fail(RVC_ERR_BAD_SHAPE, "chunk must be a multiple of fs_in / gcd(fs_in, fs_out) (FftFixedInOut::input_frames_next)");
+    if (size_t(r.t.n_out) > cap || size_t(r.t.n_in + r.t.n_out) + 64 > size_t(StateLayout::AUDIO_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "output buffer too small");
+    cudaStream_t s = ctx->streams[0];
+    float* d_in = state_audio(ctx); float* d_out = d_in + r.t.n_in;
+    CK(cudaMemcpyAsync(d_in, in, n_in * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(r.overlap[r.cur], overlap_inout, size_t(r.t.n_out) * 4, cudaMemcpyHostToDevice, s));
+    run_resampler(ctx, r, d_in, d_out, s);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, size_t(r.t.n_out) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(overlap_inout, r.overlap[r.cur], size_t(r.t.n_out) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n_out) *n_out = size_t(r.t.n_out);
     return RVC_OK;
 }
 

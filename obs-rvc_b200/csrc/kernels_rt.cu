@@ -122,7 +122,79 @@ __global__ void sola_finish_kernel(const float* __restrict__ out, const int* __r
     if (i < frame) block_out[i] = o[i];
 }
 
+
+// rubato FftFixedInOut as a direct-form polyphase filter (resample.h): output m = b i + c of a chunk is
+//   y[m] = sum_n x[n] kappa_ph[r][(a i + qc - n) mod P],   r = (a c) mod b, qc = (a c) div b.
+// A CTA takes 32 consecutive i of one residue c: their kappa windows overlap (shifted by a), so the window and the
+// chunk are staged in shared memory once; a warp produces four outputs per pass (every x element feeds four sums),
+// lanes stride over n; fixed summation order (lane partial sums, then a butterfly).  First half + previous overlap
+// -> out, second half -> the new overlap (rubato's overlap-add, synchro.rs resample_unit).
+constexpr int RS_OUT = 32;
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ x, const float* __restrict__ kappa, const float* __restrict__ ov_old, float* __restrict__ ov_new,
+                float* __restrict__ out, int a, int b, int P, int nin, int nout) {
+    pdl_enter();
+    extern __shared__ __align__(16) float rs_sm[];
+    float* xs = rs_sm;                 // [nin]
+    float* W = rs_sm + nin;            // [nin + (RS_OUT - 1) a + 1]
+    const int c = blockIdx.y, i0 = blockIdx.x * RS_OUT;
+    const int r = (a * c) % b, qc = (a * c) / b;
+    const int wlen = nin + (RS_OUT - 1) * a + 1;
+    const long long qbase = (long long)a * i0 + qc - (nin - 1);
+    const float* kp = kappa + (long long)r * P;
+    for (int t = threadIdx.x; t < nin; t += 256) xs[t] = x[t];
+    for (int t = threadIdx.x; t < wlen; t += 256) {
+        long long q = (qbase + t) % P;
+        if (q < 0) q += P;
+        W[t] = kp[q];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_c = (2 * nout) / b;   // outputs of one residue
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int li0 = warp * 4;
+    const float* w0 = W + (nin - 1) + a * li0;
+    for (int n = lane; n < nin; n += 32) {
+        const float xv = xs[n];
+        acc[0] = fmaf(xv, w0[-n], acc[0]);
+        acc[1] = fmaf(xv, w0[a - n], acc[1]);
+        acc[2] = fmaf(xv, w0[2 * a - n], acc[2]);
+        acc[3] = fmaf(xv, w0[3 * a - n], acc[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float y = warp_sum_f(acc[j]);
+        const int i = i0 + li0 + j;
+        if (lane == 0 && i < per_c) {
+            const int m = b * i + c;
+            if (m < nout) out[m] = y + ov_old[m];
+            else ov_new[m - nout] = y;
+        }
+    }
+}
+
+// dst = [src[shift:], tail]: the left-rotating ring buffers of the streaming loop (lib.rs:661-669) as a ping-pong copy
+__global__ void shift_append_kernel(float* __restrict__ dst, const float* __restrict__ src, int len, int shift, const float* __restrict__ tail, int n_tail) {
+    pdl_enter();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    if (i < len - shift) dst[i] = src[i + shift];
+    else if (tail && i - (len - shift) < n_tail) dst[i] = tail[i - (len - shift)];
+}
+
 }  // namespace
+
+void launch_resample(const float* x, const float* kappa, const float* ov_old, float* ov_new, float* out, int a, int b, int period, int nin,
+                     int nout, cudaStream_t s) {
+    const size_t smem = sizeof(float) * size_t(2 * nin + (RS_OUT - 1) * a + 1);
+    static unsigned long long attr = 0;
+    if (first_time_on_device(attr)) cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    const int per_c = (2 * nout) / b;
+    launch_k(resample_kernel, dim3((per_c + RS_OUT - 1) / RS_OUT, b), dim3(256), smem, s, x, kappa, ov_old, ov_new, out, a, b, period, nin, nout);
+}
+void launch_shift_append(float* dst, const float* src, int len, int shift, const float* tail, int n_tail, cudaStream_t s) {
+    launch_k(shift_append_kernel, dim3((len + 255) / 256), dim3(256), size_t(0), s, dst, src, len, shift, tail, n_tail);
+}
 
 void launch_rms(const float* y, int n, int frame_length, int hop, float* out, int n_frames, cudaStream_t s) {
     launch_k(rms_kernel, dim3((n_frames * 32 + 255) / 256), dim3(256), size_t(0), s, y, n, frame_length, hop, out, n_frames);

@@ -62,6 +62,10 @@ void launch_envelop_mix(float* out, int n_out, const float* r1, const float* r2,
                         cudaStream_t s);
 void launch_sola(const float* x, const float* sola, int buf, int search, float* cor, int* offset, cudaStream_t s);
 void launch_sola_crossfade(float* out, const int* offset, float* sola_buffer, int buf, int frame, float* block_out, cudaStream_t s);
+// rubato FftFixedInOut in direct polyphase form (resample.h): one chunk x[nin] -> out[nout] (+ previous overlap), new overlap[nout]
+void launch_resample(const float* x, const float* kappa, const float* ov_old, float* ov_new, float* out, int a, int b, int period, int nin,
+                     int nout, cudaStream_t s);
+void launch_shift_append(float* dst, const float* src, int len, int shift, const float* tail, int n_tail, cudaStream_t s);
 
 // Function attributes (dynamic shared memory opt-in) belong to a device: `mask` remembers the devices a call site has
 // already configured; returns true the first time it is reached with the calling thread's current device.

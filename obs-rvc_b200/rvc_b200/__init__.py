@@ -59,6 +59,13 @@ _ERRORS = {c.code: c for c in (ModelNotLoaded, ContentvecNotLoaded, F0NotLoaded,
                                BadShape, IoError, InvalidArg)}
 
 
+class StreamConfig(ctypes.Structure):
+    """`rvc_stream_config` (include/rvc_b200.h): the OBS filter settings that size the streaming loop (lib.rs:186-226)."""
+    _fields_ = [("sample_rate", ctypes.c_uint32), ("pitch_shift", c_int32), ("sample_length", ctypes.c_double),
+                ("crossfade_length", ctypes.c_double), ("extra_inference_time", ctypes.c_double),
+                ("rms_mix_rate", ctypes.c_double), ("skip_inference", c_int32), ("reserved", c_int32 * 7)]
+
+
 class Config(ctypes.Structure):
     """`rvc_config` (include/rvc_b200.h)."""
     _fields_ = [("device", c_int32), ("noise_mode", c_int32), ("noise_seed", c_uint64),
@@ -262,6 +269,52 @@ class RvcInfer:
         self._chk(self._L.rvc_mel_extract(self._h, pcm.ctypes.data_as(c_void_p), c_size_t(pcm.shape[0]),
                                           out.ctypes.data_as(c_void_p), c_size_t(cap), byref(t)))
         return out[:128 * t.value].reshape(128, t.value).copy()
+
+    # ------------------------------------------------------------------ streaming loop (obs-rvc/src/lib.rs:186-300, 659-795)
+    def stream_open(self, sample_rate=48000, sample_length=0.30, crossfade_length=0.07, extra_inference_time=2.0,
+                    pitch_shift=12, rms_mix_rate=0.0, skip_inference=False) -> int:
+        """Builds RvcInferenceState on the device; returns sample_frame_size (samples per process_frame call)."""
+        cfg = StreamConfig()
+        self._L.rvc_stream_config_default(byref(cfg))
+        cfg.sample_rate, cfg.pitch_shift, cfg.sample_length = sample_rate, pitch_shift, sample_length
+        cfg.crossfade_length, cfg.extra_inference_time = crossfade_length, extra_inference_time
+        cfg.rms_mix_rate, cfg.skip_inference = rms_mix_rate, int(skip_inference)
+        n = ctypes.c_uint32()
+        self._chk(self._L.rvc_stream_open(self._h, byref(cfg), byref(n)))
+        self._frame = int(n.value)
+        return self._frame
+
+    def stream_info(self) -> dict:
+        import json
+        buf = ctypes.create_string_buffer(1024)
+        n = c_size_t()
+        self._chk(self._L.rvc_stream_info(self._h, buf, c_size_t(1024), byref(n)))
+        return json.loads(buf.value.decode())
+
+    def stream_close(self):
+        self._chk(self._L.rvc_stream_close(self._h))
+
+    def process_frame(self, block):
+        """process_one_frame (lib.rs:659-795): sample_frame_size samples in, sample_frame_size samples out."""
+        x = _f32(block)
+        assert x.shape[0] == self._frame
+        out = np.empty(self._frame, np.float32)
+        off = ctypes.c_uint32()
+        self._chk(self._L.rvc_process_frame(self._h, x.ctypes.data_as(c_void_p), out.ctypes.data_as(c_void_p), byref(off)))
+        self.last_sola_offset = int(off.value)
+        return out
+
+    def resample_chunk(self, fs_in: int, fs_out: int, chunk, overlap):
+        """rubato FftFixedInOut::process on one chunk; `overlap` ([n_out] f32) is updated in place."""
+        x = _f32(chunk)
+        cap = int(x.shape[0] * fs_out // fs_in + 16)
+        out = np.empty(cap, np.float32)
+        n = c_size_t()
+        assert overlap.dtype == np.float32 and overlap.flags["C_CONTIGUOUS"]
+        self._chk(self._L.rvc_resample_chunk(self._h, ctypes.c_uint32(fs_in), ctypes.c_uint32(fs_out), x.ctypes.data_as(c_void_p),
+                                             c_size_t(x.shape[0]), overlap.ctypes.data_as(c_void_p), out.ctypes.data_as(c_void_p),
+                                             c_size_t(cap), byref(n)))
+        return out[:n.value].copy()
 
     def decode_salience(self, salience):
         """rmvpe.rs:118-133, 243-248 on given salience rows (T, 360) -> (f0[T] f32, argmax[T] i32)."""

@@ -215,3 +215,63 @@ def test_two_chained_contexts_share_one_device(env, monkeypatch):
             np.testing.assert_allclose(a, solo[s][w][0], rtol=0, atol=1e-4)
     for e in es:
         e.close()
+
+
+# ---- the streaming loop around the call ("next" row 1): resamplers + process_one_frame on the device ----------------
+
+@pytest.mark.parametrize("fs_in,fs_out,chunk", [(48000, 16000, 15360), (40000, 48000, 14000), (44100, 16000, 441 * 32),
+                                                  (32000, 48000, 3200), (48000, 48000, 4800)])
+def test_resampler_matches_rubato_restatement(env, fs_in, fs_out, chunk):
+    """rubato 0.15.0 FftFixedInOut (obs-rvc/src/lib.rs:236-242) on the device as a polyphase filter against the numpy
+    FFT restatement (oracle/resample.py; parity unpinned - no golden exists): four consecutive chunks incl. the
+    overlap-add state, 1e-5 of full scale."""
+    from oracle.resample import FftFixedInOut
+    rng = np.random.default_rng(5)
+    e = env["rvc_b200"].RvcInfer(env["paths"]["data"])
+    ora = FftFixedInOut(fs_in, fs_out, chunk)
+    assert ora.fft_size_in == chunk
+    t = np.arange(4 * chunk) / fs_in
+    x = (0.4 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3100 * t) + 0.05 * rng.standard_normal(4 * chunk)).astype(np.float32)
+    ov = np.zeros(ora.fft_size_out, np.float32)
+    for i in range(4):
+        got = e.resample_chunk(fs_in, fs_out, x[i * chunk:(i + 1) * chunk], ov)
+        want = ora.process(x[i * chunk:(i + 1) * chunk])
+        assert got.shape == want.shape == (ora.fft_size_out,)
+        assert np.abs(got - want).max() < 1e-5, (i, float(np.abs(got - want).max()))
+        assert np.abs(ov - ora.overlap.astype(np.float32)).max() < 1e-5
+    assert _rms(want) > 0.1
+    e.close()
+
+
+@pytest.mark.parametrize("skip_inference,mix", [(True, 0.0), (False, 0.0), (False, 1.0)])
+def test_process_frame_matches_streaming_loop(env, skip_inference, mix):
+    """process_one_frame (obs-rvc/src/lib.rs:659-795) device-resident behind rvc_process_frame - ring buffers, down-sample,
+    infer, up-sample, envelope mixing, SOLA, cross-fade - against the same loop restated on the oracle (oracle/stream.py)
+    for consecutive frames: same SOLA offsets, block within the waveform tolerance."""
+    from oracle.stream import Stream, StreamGeometry
+    pl = env["pipeline"]
+    e = _engine(env, noise_seed=12)
+    kw = dict(sample_rate=48000, sample_length=0.16, crossfade_length=0.04, extra_inference_time=2.0)
+    frame = e.stream_open(pitch_shift=12, rms_mix_rate=mix, skip_inference=skip_inference, **kw)
+    g = StreamGeometry(model_sample_rate=40000, skip_inference=skip_inference, **kw)
+    info = e.stream_info()
+    assert frame == g.sample_frame_size and info["input_buffer_16k_size"] == g.input_buffer_16k_size
+    assert info["model_return_length"] == g.model_return_length and info["skip_head"] == g.skip_head
+    ora_eng = None
+    if not skip_inference:
+        ora_eng = pl.RvcInfer(env["paths"]["data"], noise_seed=12)
+        ora_eng.load_contentvec(2); ora_eng.load_f0(1); ora_eng.load_model(env["paths"]["model"])
+    ora = Stream(ora_eng, g, pitch_shift=12, rms_mix_rate=mix)
+    nfr = 4 if skip_inference else 3
+    x48 = pl.synthetic_pcm(frame * nfr, seed=61)          # any band-limited test signal; used at the OBS rate here
+    for i in range(nfr):
+        blk = x48[i * frame:(i + 1) * frame]
+        got = e.process_frame(blk)
+        want = ora.process_one_frame(blk)
+        assert got.shape == want.shape == (frame,)
+        if _rms(want) > 1e-3:
+            assert e.last_sola_offset == ora.last["sola_offset"], (i, e.last_sola_offset, ora.last["sola_offset"])
+        assert _rms(got - want) < WAVE_RMS_TOL, (i, _rms(got - want), _rms(want))
+    assert _rms(want) > 0.01
+    e.stream_close()
+    e.close()

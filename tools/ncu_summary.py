@@ -59,13 +59,15 @@ def full(tag, rep):
                     i = hdr.index(k)
                     f.write(f"- {k}: {r[i]} {units[i]}\n")
             f.write("\n")
-    with open(os.path.join(OUT, f"{tag}_{rep}_raw.csv"), "w") as f:
-        f.write(out)
+    if os.environ.get("RAW_CSV"):   # the full raw page (200+ KB per capture) only on request
+        with open(os.path.join(OUT, f"{tag}_{rep}_raw.csv"), "w") as f:
+            f.write(out)
 
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-    for rep in ("prof_umma", "prof_knn", "prof_gemm2", "prof_chain", "prof_knn2"):
-        full(tag, rep)
+    import glob
+    for path in sorted(glob.glob(os.path.join(GO, "prof_*.ncu-rep"))):
+        full(tag, os.path.basename(path)[:-len(".ncu-rep")])
