@@ -63,4 +63,5 @@ def test_stream_loop_passthrough_level_and_block_structure():
     assert 0.3 < np.sqrt(np.mean(tail ** 2)) < 0.4                              # 0.5 / sqrt(2)
     slope = 0.5 * 2 * np.pi * 220.0 / 48000.0
     jumps = np.nonzero(np.abs(np.diff(tail)) > 3 * slope)[0]
-    assert 1 <= len(jumps) <= 2 * 4                                             # at most the seam (and its fade) per block
+    seams = 1 + int(np.count_nonzero(np.diff(jumps) > 100))                     # clusters of steep samples
+    assert 1 <= seams <= 4                                                      # one seam per emitted block, nothing else
