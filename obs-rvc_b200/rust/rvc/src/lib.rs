@@ -93,4 +93,29 @@ impl RvcInfer {
     }
 }
 
+impl RvcInfer {
+    /// Retrieval (the reference keeps `index_path` / `index_rate` in its settings but never uses them: lib.rs:78,81,264,
+    /// TODO at rvc.rs:159): exact top-k over the index rows blended into the features at `index_rate`.
+    pub fn load_index(&mut self, index_path: PathBuf, index_rate: f32) -> Result<(), RvcInferError> {
+        let p = CString::new(index_path.to_string_lossy().as_bytes()).unwrap();
+        self.chk(unsafe { sys::rvc_load_index(self.ctx, p.as_ptr(), index_rate) })
+    }
+    pub fn set_index_rate(&mut self, index_rate: f32) -> Result<(), RvcInferError> {
+        self.chk(unsafe { sys::rvc_set_index_rate(self.ctx, index_rate) })
+    }
+    /// Offline conversion: `n_windows` consecutive windows of this stream, up to 32 per launch (BASELINE configs[2]).
+    pub fn infer_windows(&mut self, pcm: ArrayView1<f32>, n: usize, sample_frame_16k_size: usize, n_windows: usize, pitch_shift: i32,
+                         skip_head: u32, return_length: u32) -> Result<Array1<f32>, RvcInferError> {
+        let x = pcm.to_owned();
+        let mut out = vec![0f32; n_windows * (return_length as usize * 480 + 16)];
+        let mut audio_len = 0usize;
+        self.chk(unsafe {
+            sys::rvc_infer_windows(self.ctx, x.as_ptr(), x.len(), n, sample_frame_16k_size as u32, n_windows, pitch_shift, skip_head,
+                                   return_length, out.as_mut_ptr(), out.len(), &mut audio_len, 0)
+        })?;
+        out.truncate(n_windows * audio_len);
+        Ok(Array1::from_vec(out))
+    }
+}
+
 impl Drop for RvcInfer { fn drop(&mut self) { unsafe { sys::rvc_destroy(self.ctx) } } }

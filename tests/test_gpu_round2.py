@@ -275,3 +275,14 @@ def test_process_frame_matches_streaming_loop(env, skip_inference, mix):
     assert _rms(want) > 0.01
     e.stream_close()
     e.close()
+
+
+def test_c_smoke_program_links_and_runs(env):
+    """A plain-C caller of the boundary (obs-rvc_b200/examples/smoke.c: rvc_create ... rvc_infer, rvc_process_frame),
+    built against include/rvc_b200.h and librvc_b200.so only."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "obs-rvc_b200", "smoke")
+    assert os.path.exists(exe), "make -C obs-rvc_b200 smoke"
+    r = subprocess.run([exe, env["paths"]["data"], env["paths"]["model"]], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SMOKE_C ok" in r.stdout and "rvc_infer: 8400 samples" in r.stdout

@@ -205,3 +205,26 @@ def test_hubert_matches_torchaudio_structure():
     got = nets.hubert_forward(tw, x)
     assert got.shape == want.shape == (111, 768)
     assert float((got - want).abs().max()) < 2e-4
+
+
+def test_rust_sys_mirror_is_complete():
+    """Seam 1/2 boundary artefacts: the raw Rust FFI crate is generated from include/rvc_b200.h (tools/gen_rust_sys.py)
+    and mirrors EVERY declared entry point; the Seam-2 adapter keeps the reference adapter's public surface
+    (obs-rvc/src/rvcadapter.rs:33-67,122-126)."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"]).returncode == 0, \
+        "rvc-cuda-sys/src/lib.rs is stale: run python tools/gen_rust_sys.py"
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "rvc_b200.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(rvc_[a-z0-9_]+)\s*\(", hdr))
+    rust = open(os.path.join(root, "obs-rvc_b200", "rust", "rvc-cuda-sys", "src", "lib.rs")).read()
+    mirrored = set(re.findall(r"pub fn (rvc_[a-z0-9_]+)\(", rust))
+    assert declared and declared == mirrored, sorted(declared ^ mirrored)
+    adapter = open(os.path.join(root, "obs-rvc_b200", "rust", "obs-rvc-adapter", "src", "rvcadapter.rs")).read()
+    for item in ("pub struct RvcInfer", "pub enum RvcAdapterError", "RvcInferError(RvcInferError)", "IoError(std::io::Error)",
+                 "pub fn new(_binary_path: PathBuf, model_version: RvcModelVersion, pitch_algorithm: PitchAlgorithm, model_path: PathBuf",
+                 "pub fn infer(&mut self, input: ndarray::ArrayView1<f32>, sample_frame_16k_size: usize, pitch_shift: i32, skip_head: u32",
+                 "impl Drop for RvcInfer"):
+        assert item in adapter, item
