@@ -290,6 +290,47 @@ def bench_knn(rvc_b200, paths, local_rank, pk, n=1 << 20, c=256, q=128, k=4, rep
                          "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None}}
 
 
+def bench_knn_sharded(rvc_b200, torch, dist, paths, local_rank, rank, world, pk, n=1 << 20, c=256, q=128, k=4, reps=20):
+    """Index-sharded retrieval (SURVEY 8e optional, rvc_b200/sharded.py): the N x C index split by rows over the ranks,
+    every rank brings its own batch of Q queries; per search: all-gather queries (NCCL) -> exact local top-k of all
+    W x Q queries on N / W rows (rvc_knn_search) -> all-gather candidates -> merge by (d2, row).  Host-observed time
+    between barriers, MAX over ranks (the searcher's result crosses the host, so this IS the end-to-end number)."""
+    from rvc_b200.sharded import ShardedIndex, shard_rows
+    lo, hi = shard_rows(n, rank, world)
+    rng = np.random.default_rng(2)
+    rows = rng.standard_normal((n, c), dtype=np.float32) * np.float32(0.34)      # same table on every rank; each keeps its shard
+    eng = rvc_b200.RvcInfer(paths["data"], device=local_rank, index_k=k)
+    eng.set_index(np.ascontiguousarray(rows[lo:hi]), 0.5)
+    dev = torch.device("cuda", local_rank)
+    sh = ShardedIndex(eng.knn_search, lo, k, device=dev if world > 1 else torch.device("cpu"))
+    x = np.random.default_rng(100 + rank).standard_normal((q, c), dtype=np.float32) * np.float32(0.34)
+    if world == 1 and not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+    d2, idx = sh.search(x)
+    for qi in range(0, q, q // 4):      # spot check against a float64 brute force over the WHOLE index
+        d = ((rows.astype(np.float64) - x[qi].astype(np.float64)) ** 2).sum(1)
+        assert np.array_equal(idx[qi], np.argsort(d, kind="stable")[:k]), "sharded kNN spot check failed"
+    del rows
+    for _ in range(3):
+        sh.search(x)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sh.search(x)
+    s = time.perf_counter() - t0
+    t = torch.tensor([s], device=dev if world > 1 else None)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t.item())
+    eng.close()
+    scan_bytes = 4.0 * (hi - lo) * c
+    return {"workload": f"index-sharded kNN: {n} x {c} f32 index split over {world} GPU(s) ({hi - lo} rows each), {q} queries per GPU per search, top-{k}",
+            "value": world * q * reps / s, "unit": "queries/s", "ms_per_search": s / reps * 1e3, "searches": reps,
+            "queries_per_search_per_gpu": q, "queries_scanned_per_gpu": world * q,
+            "collectives_per_search": {"all_gather_queries_bytes": world * q * c * 4, "all_gather_candidates_bytes": world * world * q * k * 8},
+            "shard_bytes": scan_bytes, "timing": "host clock between barriers around ShardedIndex.search, MAX over ranks (H2D of the gathered queries, "
+            "D2H of the local candidates and both NCCL all-gathers inside)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,7 +341,7 @@ def main():
     ap.add_argument("--profile-ops", action="store_true", help="also dump per-op device times to gpurun_out/")
     ap.add_argument("--streams", type=int, default=8,
                     help="independent live streams per GPU through one batched plan (configs[3]); 0 = skip")
-    ap.add_argument("--workload", default="stream1", choices=["stream1", "offline32", "streams8", "knn1m"],
+    ap.add_argument("--workload", default="stream1", choices=["stream1", "offline32", "streams8", "knn1m", "knn_sharded"],
                     help="stream1 = BASELINE configs[1] (the metric's configuration, default); the others print their own line")
     ap.add_argument("--quick", action="store_true", help="stream1 only: skip the offline32 / knn1m sub-objects")
     args = ap.parse_args()
@@ -325,6 +366,26 @@ def main():
     import rvc_b200
     from oracle import pipeline  # synthetic input generator + geometry constants only
     from oracle.weights import read_rvcw
+    if args.workload == "knn_sharded":
+        # its own line: the one workload of the path with a real exchange step (NCCL all-gathers); scaling = strong
+        # (the 1 M-row index is fixed, each GPU scans 1 / N of it) for the scan, weak for the queries (128 per GPU)
+        import torch.distributed as tdist
+        if rank == 0:
+            paths = data_dir()
+        if dist is not None:
+            dist.barrier()
+        paths = data_dir()
+        res = bench_knn_sharded(rvc_b200, torch, tdist, paths, local_rank, rank, world, peaks(), reps=max(5, min(args.steps, 50)))
+        if rank == 0:
+            print(json.dumps({"metric": "kNN queries/sec, index sharded by rows across the GPUs (1M x 256, top-4, 128 queries per GPU)",
+                              "value": res["value"], "unit": "queries/s", "n_gpus": world, "steps": res["searches"], "warmup": 3,
+                              "ms_per_step": res["ms_per_search"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic", "config": {"workload": res["workload"]},
+                              "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": world * 128 * 256 * 4,
+                                      "d2h_bytes_per_step": world * 128 * 4 * 8}, "gpu_launches": 2 * res["searches"], "knn_sharded": res}))
+        if tdist.is_initialized():
+            tdist.destroy_process_group()
+        return
     if rank == 0:
         paths = data_dir()
     if dist is not None:
