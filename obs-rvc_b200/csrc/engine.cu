@@ -895,6 +895,11 @@ int rvc_load_contentvec(rvc_ctx* ctx, int32_t model_version) {
         if (!f.load(path, err)) return ctx->fail(RVC_ERR_IO, err);
         d = std::make_shared<ModelData>();
         if (!pack_contentvec(f, d->packed, d->cvi, err)) return ctx->fail(RVC_ERR_IO, err);
+        // the file must BE the requested version (enums.rs:9-23): a 12-layer file under the v1 name (e.g. a converted
+        // checkpoint without meta tensors) would silently run the wrong network
+        if (d->cvi.n_layers != l || d->cvi.out_dim != c)
+            return ctx->fail(RVC_ERR_BAD_SHAPE, path + " holds " + std::to_string(d->cvi.n_layers) + " layers / " + std::to_string(d->cvi.out_dim) +
+                                                    " output channels, the requested model version needs " + std::to_string(l) + " / " + std::to_string(c));
         rc = upload(ctx, *d, ctx->allow_umma); if (rc) return rc;
         cache_store(key, d);
     }

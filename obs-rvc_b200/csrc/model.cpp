@@ -107,7 +107,11 @@ void pack_conv1d(Packed& out, const std::string& name, const float* w, int cout,
 
 bool pack_contentvec(const RvcwFile& f, Packed& out, CvInfo& info, std::string& err) {
     Loader L{f, err};
-    info.n_layers = L.meta("meta.n_layers", 12);
+    // layer count: the meta tensor when the file has one, otherwise the encoder layers actually present (a converted
+    // ONNX / state_dict checkpoint carries no meta tensors; the engine checks the count against the requested version)
+    int present = 0;
+    while (f.find("encoder.layers." + std::to_string(present) + ".self_attn.q_proj.weight") != nullptr) ++present;
+    info.n_layers = L.meta("meta.n_layers", present > 0 ? present : 12);
     info.final_proj = f.find("final_proj.weight") != nullptr;
     info.out_dim = info.final_proj ? 256 : 768;
     static const int K[7] = {10, 3, 3, 3, 3, 2, 2};

@@ -39,8 +39,12 @@ int main(int argc, char** argv) {
         for (;;) {
             uint32_t nbytes, sf16k, skip_head, return_length; int32_t shift;
             if (!read_exact(&nbytes, 4)) return 1;           // EOF = parent gone
+            // exactly nbytes payload bytes are consumed, as main.rs:66-70 does (read_exact of the whole buffer, then
+            // chunks_exact(4) drops a ragged tail): a length that is not a multiple of 4 must not desynchronise the stream
+            std::vector<unsigned char> raw(nbytes);
+            if (nbytes && !read_exact(raw.data(), nbytes)) return 1;
             pcm.resize(nbytes / 4);
-            if (!read_exact(pcm.data(), size_t(nbytes / 4) * 4)) return 1;
+            if (!pcm.empty()) std::memcpy(pcm.data(), raw.data(), size_t(nbytes / 4) * 4);
             if (!read_exact(&sf16k, 4) || !read_exact(&shift, 4) || !read_exact(&skip_head, 4) || !read_exact(&return_length, 4)) return 1;
             std::vector<float> out = eng.infer(pcm.data(), pcm.size(), sf16k, shift, skip_head, return_length);
             const uint32_t obytes = uint32_t(out.size() * 4);
@@ -51,5 +55,8 @@ int main(int argc, char** argv) {
     } catch (const rvc::RvcInferError& e) {
         std::fprintf(stderr, "rvc-rpc: %s (status %d)\n", e.what(), e.code);
         return 101;  // Rust panic exit code
+    } catch (const std::exception& e) {   // e.g. bad_alloc from an absurd length field of an untrusted peer
+        std::fprintf(stderr, "rvc-rpc: %s\n", e.what());
+        return 101;
     }
 }

@@ -14,7 +14,8 @@ converted once:
   caller supplies a `rename` map for them) - there is no real checkpoint in this environment to test a graph
   tracer against, so none is pretended.
 * `index_to_rvcw` - the retrieval matrix (`big_npy`) from a `.npy` file or a FAISS `IndexFlat` file
-  (fourcc `IxF2` / `IxFI`: d, ntotal, two dummies, is_trained, metric, then the float vector).  IVF indices are
+  (fourcc `IxF2` / `IxFI`: d, ntotal, two dummies, is_trained, metric, then the float vector) or a FAISS `IndexIVFFlat`
+  file (`IwFl`, what upstream RVC ships: vectors recovered from the inverted lists in id order).  PQ / other IVF codecs are
   not decoded; upstream RVC saves `total_fea.npy` next to them.
 
 Only the container layout is shared with `oracle/weights.py` (test infrastructure); nothing here imports it.
@@ -209,9 +210,96 @@ def read_faiss_flat(path: str) -> np.ndarray:
     return np.frombuffer(buf, "<f4", count=n_floats, offset=p).reshape(ntotal, d).copy()
 
 
+def _index_header(buf, p):
+    """faiss/impl/index_write.cpp write_index_header: d, ntotal, two dummies, is_trained, metric_type (+ metric_arg)."""
+    d, ntotal = struct.unpack_from("<iq", buf, p)
+    p += 4 + 8 + 8 + 8
+    p += 1                                   # is_trained
+    (metric,) = struct.unpack_from("<i", buf, p)
+    p += 4
+    if metric > 1:
+        p += 4                               # metric_arg
+    return d, ntotal, p
+
+
+def read_faiss_ivf_flat(path: str) -> np.ndarray:
+    """Vectors of a FAISS IndexIVFFlat file - what upstream RVC ships as `added_IVF{n}_Flat_nprobe_1_*.index` - in their
+    ORIGINAL row order (the ids of the inverted lists), i.e. the `big_npy` the exact search needs.  Layout
+    (faiss/impl/index_write.cpp): fourcc `IwFl`, index header, nlist, nprobe, the coarse quantizer as a nested index
+    (IndexFlat: header + centroid vector), the direct map (type byte + id array [+ hashtable pairs]), then the
+    ArrayInvertedLists: fourcc `ilar`, nlist, code_size, list-size table (`full`: one size per list, `sprs`: (list, size)
+    pairs), and per non-empty list its codes (size x code_size bytes) followed by its ids (size x int64).
+    No real .index file exists offline: the reader is tested on files written to the same published layout."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    if buf[:4] != b"IwFl":
+        raise ValueError(f"{path}: fourcc {buf[:4]!r} is not an IndexIVFFlat file")
+    d, ntotal, p = _index_header(buf, 4)
+    nlist, _nprobe = struct.unpack_from("<QQ", buf, p)
+    p += 16
+    q4 = buf[p:p + 4]
+    if q4 not in (b"IxF2", b"IxFI", b"IxFl"):
+        raise ValueError(f"{path}: coarse quantizer {q4!r} is not a flat index")
+    qd, _qn, p = _index_header(buf, p + 4)
+    (qfloats,) = struct.unpack_from("<Q", buf, p)
+    p += 8 + 4 * qfloats                     # centroids: not needed for the exact search
+    dm_type = buf[p]
+    p += 1
+    (dm_n,) = struct.unpack_from("<Q", buf, p)
+    p += 8 + 8 * dm_n
+    if dm_type == 2:                         # DirectMap::Hashtable: vector of (id, lo) pairs
+        (hn,) = struct.unpack_from("<Q", buf, p)
+        p += 8 + 16 * hn
+    if buf[p:p + 4] != b"ilar":
+        raise ValueError(f"{path}: inverted lists {buf[p:p + 4]!r} are not ArrayInvertedLists")
+    il_nlist, code_size = struct.unpack_from("<QQ", buf, p + 4)
+    p += 4 + 16
+    if il_nlist != nlist or code_size != 4 * d or qd != d:
+        raise ValueError(f"{path}: inconsistent IVF header (nlist {nlist}/{il_nlist}, code_size {code_size}, d {d}/{qd})")
+    kind = buf[p:p + 4]
+    p += 4
+    sizes = np.zeros(nlist, np.int64)
+    (n,) = struct.unpack_from("<Q", buf, p)
+    p += 8
+    if kind == b"full":
+        sizes[:] = np.frombuffer(buf, "<u8", count=n, offset=p)
+        p += 8 * n
+    elif kind == b"sprs":
+        pairs = np.frombuffer(buf, "<u8", count=n, offset=p).reshape(-1, 2)
+        sizes[pairs[:, 0].astype(np.int64)] = pairs[:, 1].astype(np.int64)
+        p += 8 * n
+    else:
+        raise ValueError(f"{path}: unknown list-size table {kind!r}")
+    if int(sizes.sum()) != ntotal:
+        raise ValueError(f"{path}: list sizes sum to {int(sizes.sum())}, ntotal is {ntotal}")
+    rows = np.zeros((ntotal, d), np.float32)
+    seen = np.zeros(ntotal, bool)
+    for sz in sizes:
+        sz = int(sz)
+        if sz == 0:
+            continue
+        codes = np.frombuffer(buf, "<f4", count=sz * d, offset=p).reshape(sz, d)
+        p += sz * code_size
+        ids = np.frombuffer(buf, "<i8", count=sz, offset=p)
+        p += 8 * sz
+        if ids.min() < 0 or ids.max() >= ntotal:
+            raise ValueError(f"{path}: vector id out of range")
+        rows[ids] = codes
+        seen[ids] = True
+    if not seen.all():
+        raise ValueError(f"{path}: {int((~seen).sum())} vector ids missing from the inverted lists")
+    return rows
+
+
 def index_to_rvcw(src_path: str, out_path: str) -> tuple:
-    """`big_npy` for `rvc_load_index` from total_fea.npy / big_npy.npy or a FAISS flat index.  Returns its shape."""
-    rows = np.load(src_path) if src_path.endswith(".npy") else read_faiss_flat(src_path)
+    """`big_npy` for `rvc_load_index` from total_fea.npy / big_npy.npy, a FAISS flat index or a FAISS IVF-Flat index.
+    Returns its shape."""
+    if src_path.endswith(".npy"):
+        rows = np.load(src_path)
+    else:
+        with open(src_path, "rb") as f:
+            fourcc = f.read(4)
+        rows = read_faiss_ivf_flat(src_path) if fourcc == b"IwFl" else read_faiss_flat(src_path)
     rows = np.ascontiguousarray(rows, np.float32)
     if rows.ndim != 2 or rows.shape[1] % 4 != 0:
         raise ValueError(f"index rows must be [N, C] with C a multiple of 4, got {rows.shape}")

@@ -108,9 +108,52 @@ def test_index_conversion(tmp_path):
     (tmp_path / "flat.index").write_bytes(blob)
     assert convert.index_to_rvcw(str(tmp_path / "flat.index"), str(tmp_path / "b.rvcw")) == (37, 8)
     np.testing.assert_array_equal(read_rvcw(str(tmp_path / "b.rvcw"))["big_npy"], rows)
-    (tmp_path / "ivf.index").write_bytes(b"IwFl" + blob[4:])
+    (tmp_path / "bad_ivf.index").write_bytes(b"IwFl" + blob[4:])          # IVF fourcc on a flat body: must be refused
+    with pytest.raises((ValueError, struct.error)):
+        convert.index_to_rvcw(str(tmp_path / "bad_ivf.index"), str(tmp_path / "c.rvcw"))
+
+
+def _ivf_flat_file(rows, nlist, sparse, seed=0):
+    """An IndexIVFFlat file written to FAISS's published layout (faiss/impl/index_write.cpp): what upstream RVC's
+    `added_IVF{nlist}_Flat_nprobe_1_*.index` holds.  Vectors are dealt to lists at random; ids keep the original order."""
+    n, d = rows.shape
+    rng = np.random.default_rng(seed)
+    assign = rng.integers(0, nlist, n)
+    if sparse:
+        assign[assign == 1] = 0                                            # an empty list -> FAISS picks the sparse size table
+    hdr = struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 1)
+    cent = rng.standard_normal((nlist, d)).astype(np.float32)
+    quant = b"IxF2" + struct.pack("<iqqqBi", d, nlist, 1 << 20, 1 << 20, 1, 1) + struct.pack("<Q", cent.size) + cent.tobytes()
+    direct_map = struct.pack("<B", 0) + struct.pack("<Q", 0)               # DirectMap::NoMap, empty array
+    sizes = np.bincount(assign, minlength=nlist).astype(np.uint64)
+    if sparse:
+        nz = np.nonzero(sizes)[0]
+        table = b"sprs" + struct.pack("<Q", 2 * len(nz)) + np.stack([nz.astype(np.uint64), sizes[nz]], 1).tobytes()
+    else:
+        table = b"full" + struct.pack("<Q", nlist) + sizes.tobytes()
+    lists = b""
+    for l in range(nlist):
+        ids = np.nonzero(assign == l)[0].astype(np.int64)
+        ids = ids[rng.permutation(len(ids))]
+        if len(ids):
+            lists += rows[ids].tobytes() + ids.tobytes()
+    return b"IwFl" + hdr + struct.pack("<QQ", nlist, 1) + quant + direct_map + b"ilar" + struct.pack("<QQ", nlist, 4 * d) + table + lists
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_faiss_ivf_flat_index_is_decoded_in_id_order(tmp_path, sparse):
+    from oracle.weights import read_rvcw
+    rows = np.random.default_rng(4).standard_normal((203, 16)).astype(np.float32)
+    path = tmp_path / "added_IVF8_Flat_nprobe_1.index"
+    path.write_bytes(_ivf_flat_file(rows, 8, sparse))
+    np.testing.assert_array_equal(convert.read_faiss_ivf_flat(str(path)), rows)
+    assert convert.index_to_rvcw(str(path), str(tmp_path / "ivf.rvcw")) == (203, 16)
+    np.testing.assert_array_equal(read_rvcw(str(tmp_path / "ivf.rvcw"))["big_npy"], rows)
+    blob = bytearray(path.read_bytes())
+    blob[-8:] = struct.pack("<q", 10 ** 6)                                  # an id outside [0, ntotal)
+    (tmp_path / "corrupt.index").write_bytes(bytes(blob))
     with pytest.raises(ValueError):
-        convert.index_to_rvcw(str(tmp_path / "ivf.index"), str(tmp_path / "c.rvcw"))
+        convert.read_faiss_ivf_flat(str(tmp_path / "corrupt.index"))
 
 
 def test_converted_model_runs_through_the_engine_packer(tmp_path):
