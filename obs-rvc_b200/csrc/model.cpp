@@ -351,7 +351,7 @@ bool pack_rmvpe(const RvcwFile& f, Packed& out, F0Info& info, std::string& err) 
 }
 
 // ------------------------------------------------------------------------------------------
-// SynthesizerTrnMs768NSFsid (40k)
+// SynthesizerTrnMs768NSFsid (32k / 40k / 48k generator configs)
 // ------------------------------------------------------------------------------------------
 
 bool pack_synth(const RvcwFile& f, Packed& out, SynInfo& info, std::string& err) {
@@ -360,7 +360,7 @@ bool pack_synth(const RvcwFile& f, Packed& out, SynInfo& info, std::string& err)
     info.sr = L.meta("meta.sr", 40000);
     info.phone_dim = L.meta("meta.phone_dim", 768);
     int sid = L.meta("meta.sid", 0);
-    if (info.sr != 40000) { err = "only the 40k synthesizer config is supported"; return false; }
+    if (!syn_config_for_rate(info)) { err = "synthesizer output rate " + std::to_string(info.sr) + " is not one of the generator configs (32k / 40k / 48k)"; return false; }
     const int PD = info.phone_dim;
     copy_vec(out, "emb.wp", L.get("enc_p.emb_phone.weight", {H, PD}), int64_t(H) * PD);
     copy_vec(out, "emb.bp", L.get("enc_p.emb_phone.bias", {H}), H);
@@ -464,9 +464,11 @@ bool pack_synth(const RvcwFile& f, Packed& out, SynInfo& info, std::string& err)
                 out.p(ob)[n] = float(a);
             }
     }
-    static const int RATES[4] = {10, 10, 2, 2}, UK[4] = {16, 16, 4, 4}, RK[3] = {3, 7, 11};
+    const int* RATES = info.rates; const int* UK = info.up_kernels;
+    static const int RK[3] = {3, 7, 11};
     for (int i = 0; i < 4 && L.ok; ++i) {
         int cin = 512 >> i, cout = 512 >> (i + 1), k = UK[i], u = RATES[i];
+        if (k > 2 * u) { err = "transposed conv kernel wider than two strides"; return false; }
         std::string d = "U" + std::to_string(i) + ".";
         const float* w = L.get("dec.ups." + std::to_string(i) + ".weight", {cin, cout, k});
         const float* b = L.get("dec.ups." + std::to_string(i) + ".bias", {cout});

@@ -41,7 +41,18 @@ struct Packed {
 
 struct CvInfo { int32_t n_layers = 12, out_dim = 768; bool final_proj = false; };
 struct F0Info { float in_scale = 1.f, in_shift = 0.f; int32_t mel_nnz = 0; };
-struct SynInfo { int32_t sr = 40000, phone_dim = 768; float lin_w = 1.f, lin_b = 0.f; };
+struct SynInfo {
+    int32_t sr = 40000, phone_dim = 768; float lin_w = 1.f, lin_b = 0.f;
+    // generator config by output rate (upstream RVC configs: 32k / 40k / 48k): ConvTranspose1d strides and kernel sizes
+    int32_t rates[4] = {10, 10, 2, 2}, up_kernels[4] = {16, 16, 4, 4};
+};
+// fills rates / up_kernels for a supported output rate; false otherwise
+inline bool syn_config_for_rate(SynInfo& s) {
+    static const int R[3][9] = {{32000, 10, 8, 2, 2, 20, 16, 4, 4}, {40000, 10, 10, 2, 2, 16, 16, 4, 4}, {48000, 12, 10, 2, 2, 24, 20, 4, 4}};
+    for (const auto& r : R)
+        if (r[0] == s.sr) { for (int i = 0; i < 4; ++i) { s.rates[i] = r[1 + i]; s.up_kernels[i] = r[5 + i]; } return true; }
+    return false;
+}
 
 bool pack_contentvec(const RvcwFile& f, Packed& out, CvInfo& info, std::string& err);
 bool pack_rmvpe(const RvcwFile& f, Packed& out, F0Info& info, std::string& err);

@@ -414,7 +414,7 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
         g.alpha = -1.0f; g.R = x1; g.ldr = H;
     }
     // ---- GeneratorNSF ----------------------------------------------------------------------
-    const int upp = 400, L = R * upp, HH = 32;
+    const int upp = info.sr / 100, L = R * upp, HH = 32;   // samples per 10 ms feature frame = product of the upsample rates
     Ref harpad = b.alloc("", L + 2 * HH);
     Ref har = harpad.plus(HH);
     b.alias("sy.har", har, L);
@@ -428,7 +428,9 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
         op.sine.lin_b = info.lin_b;
         b.lane = 0;
     }
-    static const int RATES[4] = {10, 10, 2, 2}, UK[4] = {16, 16, 4, 4}, RK[3] = {3, 7, 11}, RD[3] = {1, 3, 5};
+    const int* RATES = info.rates; const int* UK = info.up_kernels;
+    static const int RK[3] = {3, 7, 11}, RD[3] = {1, 3, 5};
+    if (RATES[0] * RATES[1] * RATES[2] * RATES[3] != upp) { b.fail("generator upsample rates do not multiply to sr / 100"); return audio; }
     // the three ResBlocks of a stage run on three lanes at once: each conv is scheduled for a third of the GPU
     // so the lanes really overlap instead of queueing behind each other's full-width grids
     static const int rb_budget_env = sched_env("RVC_RB_WANT", 0);

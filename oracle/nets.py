@@ -271,14 +271,16 @@ def sine_gen(f0: torch.Tensor, upp: int, sr: int, noise: torch.Tensor, sine_amp=
     return sine[0, :, 0]
 
 
-RATES = (10, 10, 2, 2)
-UP_KERNELS = (16, 16, 4, 4)
+# upstream RVC v2 generator configs (configs/v2/{32k,48k}.json, configs/v1/40k.json): upsample_rates / upsample_kernel_sizes
+GEN_CONFIGS = {32000: ((10, 8, 2, 2), (20, 16, 4, 4)), 40000: ((10, 10, 2, 2), (16, 16, 4, 4)), 48000: ((12, 10, 2, 2), (24, 20, 4, 4))}
+RATES, UP_KERNELS = GEN_CONFIGS[40000]
 RES_KERNELS = (3, 7, 11)
 RES_DILATIONS = (1, 3, 5)
 
 
 def generator_nsf(w, z, f0, g, sr, noise_sine, rec=None):
-    """GeneratorNSF.forward: z (1,192,T), f0 (T,) -> audio (T*400,)."""
+    """GeneratorNSF.forward: z (1,192,T), f0 (T,) -> audio (T * sr / 100,)."""
+    RATES, UP_KERNELS = GEN_CONFIGS[int(sr)]
     upp = int(np.prod(RATES))
     sine = sine_gen(f0, upp, sr, noise_sine)
     _rec(rec, "sy.sine", sine)

@@ -218,7 +218,7 @@ def synth_rmvpe(seed: int = 2345) -> dict:
 def synth_voice(seed: int = 3456, sr: int = 40000, phone_dim: int = 768) -> dict:
     """SynthesizerTrnMs768NSFsid, 40k config; upstream state_dict names,
     weight-norm resolved.  Speaker id 0 is baked in like the reference's exported graph."""
-    assert sr == 40000, "only the 40k config is synthesised"
+    assert sr in (32000, 40000, 48000), "generator configs: 32k / 40k / 48k (oracle/nets.py GEN_CONFIGS)"
     g = _Gen(seed)
     H = 192
     g.normal("enc_p.emb_phone.weight", (H, phone_dim), np.sqrt(1.0 / phone_dim) / np.sqrt(H) * 2.0)
@@ -264,7 +264,8 @@ def synth_voice(seed: int = 3456, sr: int = 40000, phone_dim: int = 768) -> dict
     g.normal("dec.conv_pre.bias", (512,), 0.02)
     g.normal("dec.cond.weight", (512, 256, 1), np.sqrt(1.0 / 256) * 0.3)
     g.normal("dec.cond.bias", (512,), 0.02)
-    rates, kernels = (10, 10, 2, 2), (16, 16, 4, 4)
+    from .nets import GEN_CONFIGS
+    rates, kernels = GEN_CONFIGS[sr]
     for i in range(4):
         cin, cout = 512 >> i, 512 >> (i + 1)
         k, u = kernels[i], rates[i]
@@ -298,7 +299,7 @@ def synth_index(seed: int, n: int, c: int, std: float = 0.34) -> np.ndarray:
     return (rng.standard_normal((n, c), dtype=np.float32) * np.float32(std)).astype(np.float32)
 
 
-def make_data_dir(root: str, seed: int = 7, v1: bool = False, index_rows: int = 0) -> dict:
+def make_data_dir(root: str, seed: int = 7, v1: bool = False, index_rows: int = 0, sr: int = 40000) -> dict:
     """Writes the reference's on-disk layout (rvc.rs:48,57,66; models.rs:58-61,71-73) with
     `.rvcw` instead of `.onnx`:  <root>/contentvec/vec-{C}-layer-{L}.rvcw, <root>/f0/rmvpe.rvcw,
     <root>/voice.rvcw [, <root>/voice.index.rvcw].  Returns the paths."""
@@ -314,7 +315,7 @@ def make_data_dir(root: str, seed: int = 7, v1: bool = False, index_rows: int = 
     if not os.path.exists(paths["f0"]):
         write_rvcw(paths["f0"], synth_rmvpe(seed + 2))
     if not os.path.exists(paths["model"]):
-        write_rvcw(paths["model"], synth_voice(seed + 3, 40000, c))
+        write_rvcw(paths["model"], synth_voice(seed + 3, sr, c))
     if index_rows:
         paths["index"] = os.path.join(root, f"voice.{index_rows}x{c}.index.rvcw")
         if not os.path.exists(paths["index"]):

@@ -286,3 +286,32 @@ def test_c_smoke_program_links_and_runs(env):
     r = subprocess.run([exe, env["paths"]["data"], env["paths"]["model"]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "SMOKE_C ok" in r.stdout and "rvc_infer: 8400 samples" in r.stdout
+
+
+@pytest.mark.parametrize("sr", [32000, 48000])
+def test_other_generator_rates(env, sr):
+    """The 32 kHz and 48 kHz generator configs of upstream RVC (upsample rates 10-8-2-2 / 12-10-2-2; the OBS filter
+    offers 16-48 kHz destination rates, obs-rvc/src/lib.rs:345-352): two windows against the oracle, plus one block
+    through the streaming loop (model rate -> 48 kHz resampler with that rate)."""
+    rb, pl = env["rvc_b200"], env["pipeline"]
+    root = os.path.join(tempfile.gettempdir(), f"rvc_b200_data_sr{sr}")
+    paths = env["weights"].make_data_dir(root, seed=11, sr=sr)
+    e = rb.RvcInfer(root, noise_seed=2)
+    e.load_contentvec(2); e.load_f0(1); e.load_model(paths["model"])
+    ora = pl.RvcInfer(root, noise_seed=2)
+    ora.load_contentvec(2); ora.load_f0(1); ora.load_model(paths["model"])
+    g = pl.BASELINE_GEOM
+    pcm = pl.synthetic_pcm(g["n16k"] + 2 * g["sf16k"], seed=71)
+    for w in range(2):
+        x = pcm[w * g["sf16k"]: w * g["sf16k"] + g["n16k"]]
+        got = e.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"]).copy()
+        want = ora.infer(x, g["sf16k"], 12, g["skip_head"], g["return_length"])
+        assert got.shape == want.shape == (g["return_length"] * sr // 100,)
+        np.testing.assert_array_equal(e.get_last("pitch", np.int32), ora.last["pitch"])
+        assert _rms(got - want) < WAVE_RMS_TOL and _rms(want) > 0.05
+    frame = e.stream_open(sample_rate=48000, sample_length=0.16, crossfade_length=0.04, extra_inference_time=2.0)
+    info = e.stream_info()
+    assert info["model_sample_rate"] == sr and info["up"][0] == info["model_return_length"] * sr // 100
+    out = e.process_frame(pl.synthetic_pcm(frame, seed=72))
+    assert out.shape == (frame,) and np.isfinite(out).all()
+    e.close()
