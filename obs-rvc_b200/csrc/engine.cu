@@ -10,6 +10,7 @@
 //   * the pitch cache (rvc.rs:26,168-179) is per-context device state.
 // There is no CPU execution path: every op is a kernel launch and a missing device is an error.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cmath>
@@ -311,11 +312,35 @@ int issue_one(rvc_ctx* ctx, const Op& op, const DeviceBases& B, cudaStream_t s, 
     return RVC_OK;
 }
 
+// NVTX ranges per stage of the window - the reference's own timers (rvc.rs:145 hubert, :157 / :184 pitch, :217 synthesizer)
+// as profiler ranges (RVC_NVTX=1).  Host-side: they bracket the enqueue of a stage's kernels (eager pass / graph capture) and
+// the whole call; device time per stage comes from rvc_profile_timeline (RVC_TL_MARKS).
+static bool g_nvtx = false;
+static const char* stage_of(const Op& op) {
+    const std::string& n = op.name;
+    if (n.compare(0, 3, "cv.") == 0) return "contentvec (rvc.rs:81-97)";
+    if (n.compare(0, 3, "rm.") == 0 || n == "mel" || n == "f0") return "rmvpe f0 (rmvpe.rs:225-261)";
+    if (n.compare(0, 3, "knn") == 0 || n == "phone") return "retrieval (rvc.rs:159)";
+    if (n == "pitch") return "pitch cache (rvc.rs:167-181)";
+    if (n.compare(0, 3, "sy.") == 0) return "synthesizer (rvc.rs:193-214)";
+    return nullptr;
+}
+
 int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
     const DeviceBases B = ctx->bases(e);
     size_t ev = 0;
     int n = 0;
+    const char* cur_stage = nullptr;
+    struct RangeGuard { bool open = false; ~RangeGuard() { if (open) nvtxRangePop(); } } guard;
     for (const Op& op : e.plan.ops) {
+        if (g_nvtx && op.kind != OP_WAIT) {
+            const char* st = stage_of(op);
+            if (st != cur_stage) {
+                if (guard.open) { nvtxRangePop(); guard.open = false; }
+                if (st) { nvtxRangePushA(st); guard.open = true; }
+                cur_stage = st;
+            }
+        }
         if (op.kind == OP_WAIT) {
             if (ev >= ctx->events.size()) {
                 cudaEvent_t x; CK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
@@ -623,6 +648,7 @@ int enqueue_infer(rvc_ctx* ctx, const float* pcm, size_t n, bool pcm_on_device, 
     if (!ctx->f0.loaded) return ctx->fail(RVC_ERR_F0_NOT_LOADED, "F0NotLoaded");
     if (!pcm || !out || n == 0 || n > size_t(StateLayout::PCM_CAP)) return ctx->fail(RVC_ERR_INVALID_ARG, "bad pcm/out");
     Geometry g{int32_t(n), int32_t(sf16k), int32_t(skip_head), int32_t(return_length)};
+    struct CallRange { bool on; CallRange(bool o) : on(o) { if (on) nvtxRangePushA("RvcInfer::infer (rvc.rs:133-220)"); } ~CallRange() { if (on) nvtxRangePop(); } } call_range(g_nvtx);
     PlanEntry* e = nullptr;
     int rc = get_plan(ctx, PLAN_INFER, g, &e);
     if (rc != RVC_OK) return rc;
@@ -820,6 +846,7 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_UMMA"); ctx->allow_umma = !(ev && ev[0] == '0'); }
     { const char* ev = getenv("RVC_SYNC_EACH"); g_sync_each = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_PDL"); rvc::g_use_pdl = (ev && ev[0] == '1'); }
+    { const char* ev = getenv("RVC_NVTX"); g_nvtx = (ev && ev[0] == '1'); }
     { const char* ev = getenv("RVC_KNN_UMMA"); ctx->knn_umma = !(ev && ev[0] == '0'); }
     {
         const char* ev = getenv("RVC_CVSTACK"); const char* eg = getenv("RVC_CVSTACK_G");

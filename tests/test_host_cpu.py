@@ -228,3 +228,152 @@ def test_rust_sys_mirror_is_complete():
                  "pub fn infer(&mut self, input: ndarray::ArrayView1<f32>, sample_frame_16k_size: usize, pitch_shift: i32, skip_head: u32",
                  "impl Drop for RvcInfer"):
         assert item in adapter, item
+
+
+def test_generator_body_equals_transformers_hifigan():
+    """Independent structural check of the synthesizer's vocoder body (the oracle's network bodies are
+    unpinned): oracle/nets.py `generator_nsf` with the NSF additions switched off (noise convs and speaker conditioning
+    zeroed) must be the plain HiFi-GAN v1 generator - checked against `transformers.SpeechT5HifiGan`, an implementation
+    written by other people, with the same weights: conv_pre, 4 x (leaky_relu 0.1, ConvTranspose1d, three ResBlocks of
+    three (dilated conv, conv) pairs averaged), leaky_relu 0.01, conv_post, tanh."""
+    import torch
+    transformers = pytest.importorskip("transformers")
+    from oracle import nets, weights
+    torch.manual_seed(0)
+    w = nets.to_torch(weights.synth_voice(3456, 40000, 768))
+    for i in range(4):
+        w[f"dec.noise_convs.{i}.weight"] = torch.zeros_like(w[f"dec.noise_convs.{i}.weight"])
+        w[f"dec.noise_convs.{i}.bias"] = torch.zeros_like(w[f"dec.noise_convs.{i}.bias"])
+    w["dec.cond.weight"] = torch.zeros_like(w["dec.cond.weight"])
+    w["dec.cond.bias"] = torch.zeros_like(w["dec.cond.bias"])
+    cfg = transformers.SpeechT5HifiGanConfig(model_in_dim=192, sampling_rate=40000, upsample_initial_channel=512,
+                                             upsample_rates=[10, 10, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+                                             resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                                             leaky_relu_slope=0.1, normalize_before=False)
+    m = transformers.SpeechT5HifiGan(cfg).eval()
+    sd = {"conv_pre.weight": w["dec.conv_pre.weight"], "conv_pre.bias": w["dec.conv_pre.bias"],
+          "conv_post.weight": w["dec.conv_post.weight"], "conv_post.bias": torch.zeros(1),
+          "mean": torch.zeros(192), "scale": torch.ones(192)}
+    for i in range(4):
+        sd[f"upsampler.{i}.weight"] = w[f"dec.ups.{i}.weight"]
+        sd[f"upsampler.{i}.bias"] = w[f"dec.ups.{i}.bias"]
+    for r in range(12):
+        for d in range(3):
+            for c in ("convs1", "convs2"):
+                for t in ("weight", "bias"):
+                    sd[f"resblocks.{r}.{c}.{d}.{t}"] = w[f"dec.resblocks.{r}.{c}.{d}.{t}"]
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not [k for k in missing if not k.startswith(("mean", "scale"))] and not unexpected, (missing, unexpected)
+    T = 21
+    z = torch.randn(1, 192, T)
+    with torch.no_grad():
+        want = m(z.transpose(1, 2)[0])                                    # (T, 192) -> waveform
+        got = nets.generator_nsf(w, z, torch.full((T,), 220.0), torch.zeros(1, 256, 1), 40000, torch.zeros(T * 400))
+    assert got.shape == want.shape == (T * 400,)
+    assert float((got - want).abs().max()) < 2e-5 and float(want.abs().max()) > 0.01
+
+
+def _wn_param(sd, prefix, w):
+    """plain conv weight -> HF's weight_norm parametrisation (g = ||v|| per output channel, v = w)."""
+    sd[prefix + ".parametrizations.weight.original1"] = w
+    sd[prefix + ".parametrizations.weight.original0"] = w.flatten(1).norm(dim=1).reshape(-1, 1, 1)
+
+
+def test_text_encoder_and_flow_equal_transformers_vits():
+    """Independent structural check of enc_p (6 relative-position attention layers, window 10, FFN kernel 3) and of the
+    reverse flow (4 mean-only residual coupling layers with a 3-layer WaveNet each, Flip between them): the oracle's
+    functional restatement against `transformers`' VITS modules (VitsEncoder, VitsResidualCouplingBlock) carrying the
+    same weights.  The RVC-specific parts around them (phone / pitch embedding, the projection to m / logs) are plain
+    linear algebra and stay outside the comparison."""
+    import torch
+    pytest.importorskip("transformers")
+    from transformers import VitsConfig
+    from transformers.models.vits import modeling_vits as mv
+    from oracle import nets, weights
+    torch.manual_seed(1)
+    w = nets.to_torch(weights.synth_voice(3456, 40000, 768))
+    cfg = VitsConfig(hidden_size=192, num_hidden_layers=6, num_attention_heads=2, window_size=10, ffn_dim=768, ffn_kernel_size=3,
+                     hidden_act="relu", layerdrop=0.0, hidden_dropout=0.0, attention_dropout=0.0, activation_dropout=0.0,
+                     use_bias=True, flow_size=192, prior_encoder_num_flows=4, prior_encoder_num_wavenet_layers=3,
+                     wavenet_kernel_size=5, wavenet_dilation_rate=1, speaker_embedding_size=256, num_speakers=2, layer_norm_eps=1e-5)
+    # ---- encoder
+    enc = mv.VitsEncoder(cfg).eval()
+    sd = {}
+    for i in range(6):
+        a, h = f"enc_p.encoder.attn_layers.{i}.", f"layers.{i}.attention."
+        for o, n in (("conv_q", "q_proj"), ("conv_k", "k_proj"), ("conv_v", "v_proj"), ("conv_o", "out_proj")):
+            sd[h + n + ".weight"] = w[a + o + ".weight"][:, :, 0]
+            sd[h + n + ".bias"] = w[a + o + ".bias"]
+        sd[h + "emb_rel_k"] = w[a + "emb_rel_k"]; sd[h + "emb_rel_v"] = w[a + "emb_rel_v"]
+        sd[f"layers.{i}.layer_norm.weight"] = w[f"enc_p.encoder.norm_layers_1.{i}.gamma"]
+        sd[f"layers.{i}.layer_norm.bias"] = w[f"enc_p.encoder.norm_layers_1.{i}.beta"]
+        sd[f"layers.{i}.final_layer_norm.weight"] = w[f"enc_p.encoder.norm_layers_2.{i}.gamma"]
+        sd[f"layers.{i}.final_layer_norm.bias"] = w[f"enc_p.encoder.norm_layers_2.{i}.beta"]
+        for c in ("conv_1", "conv_2"):
+            sd[f"layers.{i}.feed_forward.{c}.weight"] = w[f"enc_p.encoder.ffn_layers.{i}.{c}.weight"]
+            sd[f"layers.{i}.feed_forward.{c}.bias"] = w[f"enc_p.encoder.ffn_layers.{i}.{c}.bias"]
+    missing, unexpected = enc.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    T = 21
+    phone = torch.randn(T, 768) * 0.5
+    pitch = torch.randint(1, 255, (T,))
+    rec = {}
+    with torch.no_grad():
+        m_p, logs_p = nets.text_encoder(w, phone, pitch, rec)
+        x0 = torch.from_numpy(rec["sy.emb"])[None] if not torch.is_tensor(rec["sy.emb"]) else rec["sy.emb"][None]   # (1, T, 192): the encoder's input
+        hf = enc(x0.float(), torch.ones(1, T, 1), return_dict=True).last_hidden_state
+        last = rec["sy.enc5"]
+        last = torch.from_numpy(last) if not torch.is_tensor(last) else last
+    assert float((hf[0] - last.float()).abs().max()) < 2e-5 and float(last.abs().max()) > 0.1
+    # ---- flow (reverse)
+    flow = mv.VitsResidualCouplingBlock(cfg).eval()
+    sd = {}
+    for f in range(4):
+        p, h = f"flow.flows.{2 * f}.", f"flows.{f}."
+        sd[h + "conv_pre.weight"] = w[p + "pre.weight"]; sd[h + "conv_pre.bias"] = w[p + "pre.bias"]
+        sd[h + "conv_post.weight"] = w[p + "post.weight"]; sd[h + "conv_post.bias"] = w[p + "post.bias"]
+        for i in range(3):
+            _wn_param(sd, h + f"wavenet.in_layers.{i}", w[p + f"enc.in_layers.{i}.weight"])
+            sd[h + f"wavenet.in_layers.{i}.bias"] = w[p + f"enc.in_layers.{i}.bias"]
+            _wn_param(sd, h + f"wavenet.res_skip_layers.{i}", w[p + f"enc.res_skip_layers.{i}.weight"])
+            sd[h + f"wavenet.res_skip_layers.{i}.bias"] = w[p + f"enc.res_skip_layers.{i}.bias"]
+        _wn_param(sd, h + "wavenet.cond_layer", w[p + "enc.cond_layer.weight"])
+        sd[h + "wavenet.cond_layer.bias"] = w[p + "enc.cond_layer.bias"]
+    missing, unexpected = flow.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    z = torch.randn(1, 192, T)
+    g = torch.randn(1, 256, 1)
+    with torch.no_grad():
+        want = flow(z, torch.ones(1, 1, T), global_conditioning=g, reverse=True)
+        got = nets.flow_reverse(w, z, g)
+    assert float((got - want).abs().max()) < 2e-5 and float(want.abs().max()) > 0.1
+
+
+def test_rmvpe_body_equals_module_statement():
+    """Independent structural check of the RMVPE network: the oracle's functional restatement (oracle/nets.py
+    rmvpe_forward) against a module-based statement laid out like the published model code (tests/rmvpe_modules.py),
+    loaded with the same weights under strict=True - the state_dict keys must be exactly the checkpoint's keys - in
+    eval mode (BatchNorm running statistics, dropout off)."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import rmvpe_modules
+    from oracle import nets, weights
+    w = weights.synth_rmvpe(9)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in w.items() if not k.startswith(("meta.", "window", "mel."))}
+    model = rmvpe_modules.E2E().eval()
+    own = model.state_dict()
+    for k in own:
+        if k.endswith("num_batches_tracked"):
+            sd[k] = own[k]
+    extra = sorted(set(sd) - set(own))
+    assert not extra or all(not k.startswith(("unet.", "cnn.", "fc.")) for k in extra), extra[:5]
+    model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)
+    torch.manual_seed(3)
+    mel = torch.randn(128, 32) * 2.0 - 4.0
+    with torch.no_grad():
+        want = model(mel[None])[0]
+        got = nets.rmvpe_forward(nets.to_torch(w), mel)
+    assert got.shape == want.shape == (32, 360)
+    assert float((got - want).abs().max()) < 1e-5 and float(want.max()) > 0.01
+    assert torch.equal(got.argmax(dim=1), want.argmax(dim=1))
