@@ -34,6 +34,9 @@ struct ChainOpDev {
     float f0;
     // weights worth pulling into L2 while the previous phase runs: rows x row_bytes at stride
     const char* pf_base; long long pf_stride; int pf_rows, pf_row_bytes;
+    // slab chains (below): columns per CTA / per warp, k per 16 KB chunk, chunks of this op, index of its first chunk in
+    // the per-CTA weight stream
+    int slab_nc, slab_cw, slab_kc, slab_chunks, slab_chunk0, slab_pad;
 };
 
 struct ChainPhaseDev { int op0, op1, items, pad; };
@@ -45,10 +48,36 @@ struct ChainDev {
     unsigned long long* d_dbg = nullptr;  // optional: globaltimer at every phase start (+ end), CTA 0
     int n_ops = 0, n_phases = 0, grid = 0;
     int cluster = 0;   // 1: the grid is ONE thread-block cluster (<= 16 CTAs), phases separated by the hardware cluster barrier
+    // Slab chain (slab_chain_kernel): a single cluster whose GEMMs (M <= 24 rows) are split by output columns only - CTA c
+    // owns columns [c nc, (c + 1) nc) of EVERY GEMM with the full K, no split-K - and whose weights were re-packed once, per
+    // CTA, into one contiguous stream of 16 KB chunks in execution order: a CTA pulls its stream with bulk copies that run
+    // ahead of the phase barriers (weights do not depend on activations), so the HBM latency of every op but the first is hidden.
+    int slab = 0;
+    float* d_slabs = nullptr; long long slab_stream_floats = 0; int slab_total_chunks = 0;
+    int* d_chunk_bytes = nullptr;   // bytes of every chunk of the stream (the same for all CTAs)
 };
 
 constexpr int CHAIN_THREADS = 256;
 constexpr int CHAIN_SMEM_BYTES = 90 * 1024;  // stage rings of 75-90 KB (kernels_chain.cu tile table)
+constexpr int SLAB_CHUNK_FLOATS = 4096;      // 16 KB weight chunks
+constexpr int SLAB_RING = 6;                 // chunks in flight per CTA (96 KB)
+constexpr int SLAB_A_FLOATS = 18432;         // staged activation span of one GEMM (72 KB)
+constexpr int SLAB_SMEM_BYTES = (SLAB_RING * SLAB_CHUNK_FLOATS + SLAB_A_FLOATS) * 4 + 256;
+constexpr int SLAB_MAX_ROWS = 24;
+// columns per CTA / per warp and k per chunk of a GEMM inside a slab chain of G CTAs (host and device agree through ChainOpDev)
+inline void slab_shape(int N, int K, int G, bool gate, int& nc, int& cw, int& kc, int& chunks) {
+    nc = (N + G - 1) / G;
+    if (gate && (nc & 1)) ++nc;
+    cw = (nc + 7) / 8;
+    if (cw <= 2) cw = 2; else if (cw <= 4) cw = 4; else if (cw <= 6) cw = 6; else cw = 8;   // 8 only with <= 8 rows (registers)
+    kc = (SLAB_CHUNK_FLOATS / nc) / 32 * 32;
+    const int kpad = (K + 31) / 32 * 32;
+    if (kc > kpad) kc = kpad;
+    chunks = (K + kc - 1) / kc;
+}
+// packs the per-CTA weight streams of a slab chain (one launch per GEMM op, at plan build time)
+void launch_slab_pack(const float* W, long long ldw, int N, int K, int nc, int kc, int chunks, float* slabs, long long stream_floats,
+                      int chunk0, int G, cudaStream_t stream);
 
 int launch_chain(const ChainDev& c, cudaStream_t stream);  // returns kernels launched (1)
 void init_chain_attributes();

@@ -118,7 +118,7 @@ struct PlanEntry {
     ~PlanEntry() {
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
-        for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); }
+        for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); cudaFree(c.d_slabs); cudaFree(c.d_chunk_bytes); }
         cudaFree(cvs.d_maps); cudaFree(cvs.d_phases); cudaFree(cvs.d_bar);
         work.release(); bstate.release();
     }
@@ -442,10 +442,49 @@ int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
         ChainDev cd;
         cd.n_ops = ci.count; cd.n_phases = ci.n_phases;
         cd.grid = std::max(1, std::min(ci.grid, chain_max_coresident_ctas()));
+        {   // slab chain (chain.h): every GEMM of the run has few rows and fits the column-split shape -> one 16-CTA cluster
+            static const int max_cluster = chain_max_cluster_ctas();
+            const char* se = getenv("RVC_SLAB");
+            bool slab = se && se[0] == '1' && max_cluster >= 16;
+            const int G = 16;
+            std::vector<int> chunk_bytes;
+            for (int k = 0; k < ci.count && slab; ++k) {
+                ChainOpDev& d = ops[size_t(k)];
+                if (d.kind != CH_GEMM) continue;
+                const gemmk::GemmParams& g = d.g;
+                const int seg_len = g.seg_len >= g.K ? g.K : g.seg_len;
+                int nc, cw, kc, chunks;
+                slab_shape(g.N, g.K, G, g.act == ACT_GATE, nc, cw, kc, chunks);
+                const long long span = (long long)(g.M - 1) * g.lda + (long long)(g.K / seg_len - 1) * g.seg_stride + seg_len;
+                if (g.M > SLAB_MAX_ROWS || d.batch != 1 || g.K % seg_len != 0 || span > SLAB_A_FLOATS || span % 4 != 0 || nc > (g.M <= 8 ? 64 : 48) || nc * kc > SLAB_CHUNK_FLOATS ||
+                    (reinterpret_cast<uintptr_t>(g.A) & 15) != 0) {
+                    if (getenv("RVC_SLAB_VERBOSE")) std::fprintf(stderr, "slab: chain at op %d rejected: M=%d N=%d K=%d seg_len=%d batch=%d span=%lld nc=%d kc=%d align=%d\n", ci.first + k, g.M, g.N, g.K, seg_len, d.batch, span, nc, kc, int(reinterpret_cast<uintptr_t>(g.A) & 15));
+                    slab = false; break;
+                }
+                d.slab_nc = nc; d.slab_cw = cw; d.slab_kc = kc; d.slab_chunks = chunks; d.slab_chunk0 = int(chunk_bytes.size());
+                d.g.splitk = 1;
+                for (int j = 0; j < chunks; ++j) chunk_bytes.push_back(nc * kc * 4);
+            }
+            if (slab && !chunk_bytes.empty()) {
+                cd.slab = 1; cd.grid = G; cd.slab_total_chunks = int(chunk_bytes.size());
+                cd.slab_stream_floats = (long long)chunk_bytes.size() * SLAB_CHUNK_FLOATS;
+                CK(cudaMalloc(&cd.d_slabs, size_t(G) * size_t(cd.slab_stream_floats) * sizeof(float)));
+                CK(cudaMalloc(&cd.d_chunk_bytes, chunk_bytes.size() * sizeof(int)));
+                CK(cudaMemcpyAsync(cd.d_chunk_bytes, chunk_bytes.data(), chunk_bytes.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->streams[0]));
+                for (int k = 0; k < ci.count; ++k) {
+                    const ChainOpDev& d = ops[size_t(k)];
+                    if (d.kind != CH_GEMM) continue;
+                    launch_slab_pack(d.g.W, d.g.ldw, d.g.N, d.g.K, d.slab_nc, d.slab_kc, d.slab_chunks, cd.d_slabs, cd.slab_stream_floats, d.slab_chunk0, G,
+                                     ctx->streams[0]);
+                }
+                CK(cudaStreamSynchronize(ctx->streams[0]));
+                CK(cudaGetLastError());
+            }
+        }
         {   // small grids run as ONE thread-block cluster: hardware cluster barrier instead of the L2 grid barrier
             static const int max_cluster = chain_max_cluster_ctas();
             const char* ce = getenv("RVC_CHAIN_CLUSTER");
-            cd.cluster = (!(ce && ce[0] == '0') && cd.grid >= 2 && cd.grid <= max_cluster) ? 1 : 0;
+            cd.cluster = (!cd.slab && !(ce && ce[0] == '0') && cd.grid >= 2 && cd.grid <= max_cluster) ? 1 : 0;
         }
         CK(cudaMalloc(&cd.d_ops, ops.size() * sizeof(ChainOpDev)));
         CK(cudaMalloc(&cd.d_phases, phases.size() * sizeof(ChainPhaseDev)));

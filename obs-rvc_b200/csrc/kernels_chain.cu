@@ -12,7 +12,10 @@
 // (32 accumulators per thread: lanes along N, rows in registers), the 8 per-warp partial tiles
 // are summed through shared memory in fixed order; split-K slices go to a scratch area and the
 // last CTA to arrive on a tile (atomic ticket) adds them in z order - deterministic sums.
+#include <cuda.h>
+
 #include <cstdio>
+#include <cstring>
 
 #include "chain.h"
 #include "launch.h"
@@ -393,7 +396,10 @@ __device__ __forceinline__ void gemm_dispatch(const ChainOpDev& o, int local, fl
     case ID: {                                                                                                               \
         using T = TileCfg<BM, BN, LK, QPW, ST>;                                                                              \
         if (what == 0) gemm_tile<T, BM, BN, ST>(p, tm * BM, tn * BN, z, bz, tile, smem, s_last, w_preloaded, stamp_row);     \
-        else {                                                                                                               \
+        else if (what == 2) {                                                                                                \
+            const int nkt_total = (p.K + T::BK - 1) / T::BK, kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split); \
+            gemm_issue_w<T, BM>(p, tn * BN, bz, kt0, min(kt1, kt0 + ST - 1), 0, smem);                                       \
+        } else {                                                                                                             \
             const int nkt_total = (p.K + T::BK - 1) / T::BK, kt0 = z * p.kt_per_split, kt1 = min(nkt_total, kt0 + p.kt_per_split); \
             gemm_prefetch_w<T>(p, tn * BN, bz, kt0 * T::BK, min(p.K, kt1 * T::BK));                                          \
         }                                                                                                                    \
@@ -523,7 +529,13 @@ __device__ __forceinline__ void layernorm_item(const ChainOpDev& o, int local) {
 // tables of the head are staged in shared memory with every load in flight at once (a dependent chain of L2 /
 // cold-HBM round trips otherwise); the reductions keep the order of relattn_kernel (kernels_misc.cu), so the
 // chain and the stand-alone kernel agree bit for bit.
-__device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, float* sm) {
+// CTA-wide sync of the chain kernel (256 threads) / named barrier of the slab kernel's 256 compute threads (its
+// producer warp does not take part)
+template <bool NAMED> __device__ __forceinline__ void chain_sync() {
+    if (NAMED) asm volatile("bar.sync 2, 256;" ::: "memory"); else __syncthreads();
+}
+template <bool NAMED>
+__device__ __forceinline__ void relattn_item_t(const ChainOpDev& o, int local, float* sm) {
     const int T = o.i0, heads = o.i1, dim = o.i2, window = o.i3;
     const int h = local / T, i = local - h * T;
     const int HD = heads * dim, nrel = 2 * window + 1;
@@ -543,7 +555,7 @@ __device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, flo
         vs[e] = __ldcg(qkv + (long long)j * ld + 2 * HD + h * dim + d);
     }
     for (int e = tid; e < nrel * dim; e += CHAIN_THREADS) { rks[e] = __ldg(o.x1 + e); rvs[e] = __ldg(o.x2 + e); }
-    __syncthreads();
+    chain_sync<NAMED>();
     for (int j = warp; j < T; j += nw) {
         const int rel = j - i + window;
         const bool inw = rel >= 0 && rel < nrel;
@@ -552,7 +564,7 @@ __device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, flo
         a = warp_sum(a);
         if (lane == 0) ps[j] = a;
     }
-    __syncthreads();
+    chain_sync<NAMED>();
     if (warp == 0) {
         float mx = -3.402823466e+38f;
         for (int j = lane; j < T; j += 32) mx = fmaxf(mx, ps[j]);
@@ -563,7 +575,7 @@ __device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, flo
         const float inv = 1.0f / sum;
         for (int j = lane; j < T; j += 32) ps[j] *= inv;
     }
-    __syncthreads();
+    chain_sync<NAMED>();
     for (int d = tid; d < dim; d += CHAIN_THREADS) {
         float a = 0.f;
         for (int j = 0; j < T; ++j) {
@@ -576,6 +588,12 @@ __device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, flo
     }
 }
 
+__device__ __forceinline__ void relattn_item(const ChainOpDev& o, int local, float* sm) { relattn_item_t<false>(o, local, sm); }
+__device__ __forceinline__ void relattn_item_sync2(const ChainOpDev& o, int local, float* sm) { relattn_item_t<true>(o, local, sm); chain_sync<true>(); }
+
+
+__device__ int g_chain_wpre = 0;     // RVC_CHAIN_WPRE=1: first weight stages of the next tile requested before the barrier wait
+__device__ int g_chain_poll = 0;     // RVC_CHAIN_POLL=1: waiters poll the arrival counter itself (one hop less than the published phase word)
 constexpr int CHAIN_MAX_OPS = 256;   // table entries kept in shared memory (plan.cpp splits longer runs)
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 1)
@@ -592,7 +610,8 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
     for (int i = tid; i < n_ops; i += CHAIN_THREADS) s_item_end[i] = ops[i].item0 + ops[i].items;
     __syncthreads();
     int cur = -1;            // op whose descriptor sits in s_op
-    bool pre = false;        // s_op + the W stages of this CTA's first item of the phase are already in flight
+    bool pre = false;        // s_op of this CTA's first item of the phase is already loaded
+    bool wpre = false;       // ... and the first W stages of that item are in flight (RVC_CHAIN_WPRE)
     auto fetch_op = [&](const ChainPhaseDev& P, int item) {   // all threads; ends with a barrier
         int o = P.op0;
         while (o + 1 < P.op1 && item >= s_item_end[o]) ++o;
@@ -633,7 +652,7 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
             first = false;
             const int local = item - s_op.item0;
             switch (s_op.kind) {
-                case CH_GEMM: gemm_dispatch(s_op, local, smem, &s_last, false, 0, stamp_row); break;
+                case CH_GEMM: gemm_dispatch(s_op, local, smem, &s_last, preloaded && wpre, 0, stamp_row); break;
                 case CH_GEMM_DIRECT: gemm_direct_item(s_op.g, local); break;
                 case CH_AVGPOOL: avgpool_item(s_op, local); break;
                 case CH_LAYERNORM: layernorm_item(s_op, local); break;
@@ -641,7 +660,7 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 default: break;
             }
         }
-        pre = false;
+        pre = false; wpre = false;
         if (ph + 1 < n_phases) {
             // arrive first, then use the wait: descriptor + first weight stages of this CTA's next item
             if (cluster_mode) {
@@ -665,8 +684,10 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 if (tid < OP_WORDS) reinterpret_cast<int*>(&s_op)[tid] = nxt_word;
                 cur = nxt_o;
                 __syncthreads();
-                if (s_op.kind == CH_GEMM) gemm_dispatch(s_op, int(blockIdx.x) - s_op.item0, smem, &s_last, false, 1);
-                else if (s_op.kind == CH_LAYERNORM || s_op.kind == CH_RELATTN) {
+                if (s_op.kind == CH_GEMM) {
+                    gemm_dispatch(s_op, int(blockIdx.x) - s_op.item0, smem, &s_last, false, 1);
+                    if (g_chain_wpre) { gemm_dispatch(s_op, int(blockIdx.x) - s_op.item0, smem, &s_last, false, 2); wpre = true; }
+                } else if (s_op.kind == CH_LAYERNORM || s_op.kind == CH_RELATTN) {
                     // parameter vectors of the next op towards L2 (they are cold every window)
                     const int bytes = (s_op.kind == CH_LAYERNORM ? s_op.i1 : (2 * s_op.i3 + 1) * s_op.i2) * 4;
                     for (int l = tid * 128; l < bytes; l += CHAIN_THREADS * 128) {
@@ -687,8 +708,13 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
                 if (blockIdx.x == 0 && ph < 256) g_chain_stamp2[ph * 2] = t0;
                 while (true) {
                     unsigned int v;
+                    if (g_chain_poll) {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+                        if (v >= target * G) break;
+                    } else {
                     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 32) : "memory");   // plain L2 poll ...
                     if (v >= target) break;
+                    }
                     if (nxt_o < 0) __nanosleep(200);   // CTAs with nothing to do next phase poll gently
                     if (clock64() - t0 > (6ll << 30)) __trap();  // a CTA that never arrives must fail loudly, not hang the GPU
                 }
@@ -708,13 +734,313 @@ chain_kernel(const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict
     }
 }
 
+
+// ================================================================================================================
+// Slab chain (chain.h): ONE thread-block cluster, GEMMs split by output columns only, weights streamed from a per-CTA
+// contiguous stream of 16 KB chunks (cp.async.bulk + mbarrier) that runs ahead of the phase barriers.
+// ================================================================================================================
+__device__ __forceinline__ uint32_t sl_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sl_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sl_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sl_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sl_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sl_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = sl_smem_u32(bar);
+    uint32_t done = 0;
+    long long spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1ll << 27)) __trap();   // a chunk that never lands must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void sl_bulk_g2s(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sl_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(sl_smem_u32(bar)) : "memory");
+}
+
+__device__ int g_slab_dbg = 0;   // timing experiments (RVC_SLAB_DBG): 1 = no FMA loop, 2 = no activation staging, 3 = no weight stream waits
+
+__device__ __forceinline__ void sl_tma_2d(const CUtensorMap* map, float* smem_dst, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(sl_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(sl_smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+struct SlabStream {
+    const CUtensorMap* map; // the slab buffer as [rows of 32 floats]: a chunk = a box of 128 rows (tensor-map TMA streams at
+                            // ~55 B/clk per SM here, 1-D cp.async.bulk measured ~7 B/clk)
+    long long row0;         // first row of this CTA's stream
+    const float* base;     // this CTA's weight stream
+    const int* bytes;      // bytes of every chunk of the chain (shared by all CTAs)
+    int total;             // chunks in the stream
+    int issued, consumed;  // uniform across the CTA
+};
+
+// Compute threads only count: the producer warp (warp 8) issues the copies (an issuing thread is busy for ~1000 cycles
+// per bulk copy, which stalled the whole CTA at its next barrier when thread 0 did it between chunks).  After every
+// consumed chunk compute thread 0 publishes the count; chunk i may be requested once chunk i - SLAB_RING is consumed.
+__device__ __forceinline__ void slab_top_up(SlabStream& st, float* ring, uint64_t* full, volatile int* s_consumed) {
+    (void)ring; (void)full;
+    if (threadIdx.x == 0) *s_consumed = st.consumed;
+}
+__device__ __forceinline__ void slab_produce(SlabStream& st, float* ring, uint64_t* full, volatile int* s_consumed) {
+    const int lim = min(st.total, *s_consumed + SLAB_RING);
+    while (st.issued < lim) {
+        const int slot = st.issued % SLAB_RING;
+        if (st.map) {
+            sl_mbar_expect_tx(&full[slot], SLAB_CHUNK_FLOATS * 4);   // whole 16 KB boxes (the tail of a chunk is zero padding)
+            sl_tma_2d(st.map, ring + slot * SLAB_CHUNK_FLOATS, &full[slot], 0, int(st.row0 + (long long)st.issued * (SLAB_CHUNK_FLOATS / 32)));
+        } else {
+            const uint32_t nb = uint32_t(st.bytes[st.issued]);
+            sl_mbar_expect_tx(&full[slot], nb);
+            sl_bulk_g2s(ring + slot * SLAB_CHUNK_FLOATS, st.base + (long long)st.issued * SLAB_CHUNK_FLOATS, nb, &full[slot]);
+        }
+        ++st.issued;
+    }
+}
+
+// One GEMM of a slab chain on this CTA's column slice: lanes split k inside a chunk, warps split the columns (CW each),
+// every thread carries MR x CW partial sums over its k's through all chunks; a halving butterfly then leaves each lane
+// with NV / 32 finished outputs (fixed summation order) for the epilogue.
+template <int MR, int CW>
+__device__ __forceinline__ void slab_gemm(const ChainOpDev& o, SlabStream& st, float* ring, float* abuf, uint64_t* full, volatile int* s_consumed) {
+    const GemmParams& p = o.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int M = p.M, K = p.K, nc = o.slab_nc, kc = o.slab_kc;
+    const int n_base = blockIdx.x * nc;
+    const int ncols = max(0, min(nc, p.N - n_base));
+    const int seg_len = p.seg_len >= K ? K : p.seg_len;
+    const int nseg = K / seg_len;
+    // ---- activations of this op: the span the (overlapping / segmented) rows cover, L2 -> shared memory ----
+    const long long span = (long long)(M - 1) * p.lda + (long long)(nseg - 1) * p.seg_stride + seg_len;
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.A);
+        float4* dst = reinterpret_cast<float4*>(abuf);
+        const int n4 = int(span >> 2);
+        if (g_slab_dbg != 2) for (int i = tid; i < n4; i += CHAIN_THREADS) dst[i] = __ldcg(src + i);
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const int col0 = warp * CW;                 // first column (inside the slice) of this warp
+    const bool active = col0 < ncols;
+    const int lda = int(p.lda), seg_stride = int(p.seg_stride);
+    // ---- where this lane's finished outputs will sit after the halving butterfly: their bias / residual are requested
+    //      NOW (parameter vectors are cold in L2 every window: an HBM round trip each if fetched in the epilogue) ----
+    constexpr int NV = (MR * CW + 63) / 64 * 64;   // PER even: the two columns of a gate pair end up in the same lane
+    constexpr int PER = NV / 32;
+    int first = 0;
+#pragma unroll
+    for (int sft = 0; sft < 5; ++sft) if (lane & (16 >> sft)) first += NV >> (sft + 1);
+    const bool plain = p.out_mode == OUT_PLAIN && p.act != ACT_GATE;
+    float bpre[PER], rpre[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int idx = first + i, r = idx / CW, c = idx - r * CW, n = n_base + col0 + c;
+        const bool ok = active && r < M && idx < MR * CW && (col0 + c) < ncols && n < p.N;
+        bpre[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+        rpre[i] = (ok && plain && p.R) ? __ldcg(p.R + (long long)r * p.ldr + n) : 0.f;
+    }
+    float acc[MR][CW];
+#pragma unroll
+    for (int r = 0; r < MR; ++r)
+#pragma unroll
+        for (int c = 0; c < CW; ++c) acc[r][c] = 0.f;
+    for (int ch = 0; ch < o.slab_chunks; ++ch) {
+        const int slot = st.consumed % SLAB_RING;
+        if (g_slab_dbg != 3) sl_mbar_wait(&full[slot], (st.consumed / SLAB_RING) & 1);
+        if (active && g_slab_dbg != 1) {
+            const float* wch = ring + slot * SLAB_CHUNK_FLOATS + col0 * kc;   // chunk layout [nc][kc]
+            const int k0 = ch * kc, kn = min(kc, K - k0);
+#pragma unroll 1
+            for (int kk = lane; kk < kn; kk += 32) {
+                const int k = k0 + kk;
+                const int sg = k / seg_len;
+                const float* ap = abuf + sg * seg_stride + (k - sg * seg_len);
+                float wv[CW], av[MR];
+#pragma unroll
+                for (int c = 0; c < CW; ++c) wv[c] = wch[c * kc + kk];
+#pragma unroll
+                for (int r = 0; r < MR; ++r) av[r] = r < M ? ap[r * lda] : 0.f;     // all loads of the step first, then the FMAs
+#pragma unroll
+                for (int r = 0; r < MR; ++r)
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) acc[r][c] = fmaf(av[r], wv[c], acc[r][c]);
+            }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // every compute warp is done with the chunk: its slot may be refilled
+        ++st.consumed;
+        slab_top_up(st, ring, full, s_consumed);
+    }
+    if (!active) return;
+    // ---- halving butterfly: NV values per lane -> NV / 32 finished sums per lane ----
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = i < MR * CW ? acc[i / CW][i % CW] : 0.f;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int half = NV >> (s + 1);
+        const int mask = 16 >> s;
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < NV / 2; ++i) {
+            if (i < half) {
+                const float keep = upper ? v[i + half] : v[i];
+                const float send = upper ? v[i] : v[i + half];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+            }
+        }
+    }
+    // ---- epilogue: value index = r * CW + c ----
+    const bool gate = p.act == ACT_GATE;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int idx = first + i;
+        const int r = idx / CW, c = idx - r * CW;
+        const float partner = v[i ^ 1];   // the other column of a gate pair (2j, 2j + 1): same lane, neighbouring slot
+        const int n = n_base + col0 + c;
+        if (!(r < M && idx < MR * CW && (col0 + c) < ncols && n < p.N)) continue;
+        if (plain) {
+            // common case inline, bias / residual already in registers (same arithmetic as chain_epilogue)
+            float ov = chain_act_fast(p.act, fmaf(p.alpha, v[i], bpre[i])) + rpre[i];
+            const bool masked = p.mask_period > 0 && (r % p.mask_period) >= p.mask_valid;
+            if (masked) ov = 0.f;
+            p.C[(long long)r * p.ldc + n] = ov;
+            if (p.C2) p.C2[(long long)r * p.ldc2 + n] = masked ? 0.f : chain_act_fast(p.act2, ov);
+        } else if (gate && p.out_mode == OUT_PLAIN) {
+            if (n & 1) continue;
+            const float v0 = fmaf(p.alpha, v[i], bpre[i]), v1 = fmaf(p.alpha, partner, bpre[i ^ 1]);
+            float gv = tanhf(v0) * sigmoid_f(v1);
+            const int col = n >> 1;
+            if (p.R) gv += __ldcg(p.R + (long long)r * p.ldr + col);
+            const bool masked = p.mask_period > 0 && (r % p.mask_period) >= p.mask_valid;
+            if (masked) gv = 0.f;
+            p.C[(long long)r * p.ldc + col] = gv;
+            if (p.C2) p.C2[(long long)r * p.ldc2 + col] = masked ? 0.f : apply_act(p.act2, gv);
+        } else {
+            chain_epilogue(p, p.bias, p.C, p.C2, p.R, r, n, v[i], partner);
+        }
+    }
+}
+
+__device__ __forceinline__ void slab_gemm_dispatch(const ChainOpDev& o, SlabStream& st, float* ring, float* abuf, uint64_t* full, volatile int* s_consumed) {
+    const bool small = o.g.M <= 8;
+    switch (o.slab_cw) {
+        case 2: if (small) slab_gemm<8, 2>(o, st, ring, abuf, full, s_consumed); else slab_gemm<SLAB_MAX_ROWS, 2>(o, st, ring, abuf, full, s_consumed); break;
+        case 4: if (small) slab_gemm<8, 4>(o, st, ring, abuf, full, s_consumed); else slab_gemm<SLAB_MAX_ROWS, 4>(o, st, ring, abuf, full, s_consumed); break;
+        case 8: slab_gemm<8, 8>(o, st, ring, abuf, full, s_consumed); break;   // the host only picks 8 columns per warp for <= 8 rows
+        default: if (small) slab_gemm<8, 6>(o, st, ring, abuf, full, s_consumed); else slab_gemm<SLAB_MAX_ROWS, 6>(o, st, ring, abuf, full, s_consumed); break;
+    }
+}
+
+constexpr int SLAB_THREADS = CHAIN_THREADS + 32;   // 8 compute warps + the weight-stream producer warp
+
+__global__ void __launch_bounds__(SLAB_THREADS, 1)
+slab_chain_kernel(const __grid_constant__ CUtensorMap slab_map, int use_map, const ChainOpDev* __restrict__ ops, const ChainPhaseDev* __restrict__ phases,
+                  int n_ops, int n_phases, const float* __restrict__ slabs, long long stream_floats, const int* __restrict__ chunk_bytes,
+                  int total_chunks, unsigned long long* dbg) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ ChainOpDev s_op;
+    __shared__ __align__(8) uint64_t s_full[SLAB_RING];
+    __shared__ volatile int s_consumed, s_phase_done;
+    float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~uintptr_t(127));   // TMA destinations: 128-byte aligned
+    float* abuf = ring + SLAB_RING * SLAB_CHUNK_FLOATS;
+    const int tid = threadIdx.x;
+    const int G = gridDim.x;
+    if (tid == 0) {
+        for (int i = 0; i < SLAB_RING; ++i) sl_mbar_init(&s_full[i], 1);
+        s_consumed = 0; s_phase_done = -1;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    SlabStream st;
+    st.base = slabs + (long long)blockIdx.x * stream_floats; st.bytes = chunk_bytes; st.total = total_chunks; st.issued = 0; st.consumed = 0;
+    st.map = use_map ? &slab_map : nullptr; st.row0 = (long long)blockIdx.x * (stream_floats / 32);
+    if (tid >= CHAIN_THREADS) {
+        // ===== producer warp: keeps SLAB_RING chunks of this CTA's weight stream in flight, across op and phase boundaries
+        // (weights do not depend on activations); joins the cluster barrier of a phase once the compute warps are through it =====
+        const int lane = tid & 31;
+        for (int ph = 0; ph < n_phases; ++ph) {
+            if (lane == 0) {
+                long long spins = 0;
+                while (true) {
+                    slab_produce(st, ring, s_full, &s_consumed);
+                    if (s_phase_done >= ph) break;
+                    __nanosleep(256);   // a tight poll of shared memory starves the compute warps' own shared-memory loads
+                    if (++spins > (1ll << 31)) __trap();
+                }
+            }
+            __syncwarp();
+            if (ph + 1 < n_phases) {
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            }
+        }
+        return;
+    }
+    constexpr int OP_WORDS = int(sizeof(ChainOpDev) / 4);
+    for (int ph = 0; ph < n_phases; ++ph) {
+        const ChainPhaseDev P = phases[ph];
+        if (dbg && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[ph] = t; }
+        for (int oi = P.op0; oi < P.op1; ++oi) {
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // the previous op is done with s_op / the staging buffer
+            if (tid < OP_WORDS) reinterpret_cast<int*>(&s_op)[tid] = __ldg(reinterpret_cast<const int*>(ops + oi) + tid);
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (s_op.kind == CH_GEMM) {
+                slab_gemm_dispatch(s_op, st, ring, abuf, s_full, &s_consumed);
+            } else {
+                for (int local = blockIdx.x; local < s_op.items; local += G) {
+                    switch (s_op.kind) {
+                        case CH_GEMM_DIRECT: gemm_direct_item(s_op.g, local); break;
+                        case CH_AVGPOOL: avgpool_item(s_op, local); break;
+                        case CH_LAYERNORM: layernorm_item(s_op, local); break;
+                        case CH_RELATTN: relattn_item_sync2(s_op, local, abuf); break;
+                        default: break;
+                    }
+                }
+            }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (tid == 0) s_phase_done = ph;     // the producer warp may now join this phase's cluster barrier
+        if (ph + 1 < n_phases) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+    }
+    if (dbg && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); dbg[n_phases] = t; }
+}
+
+// W[n][k] (row pitch ldw) -> the per-CTA streams: CTA c, chunk j of this op = [nc][kc] floats of columns [c nc, (c + 1) nc),
+// k in [j kc, (j + 1) kc), zero-filled outside N x K
+__global__ void slab_pack_kernel(const float* __restrict__ W, long long ldw, int N, int K, int nc, int kc, int chunks, float* __restrict__ slabs,
+                                 long long stream_floats, int chunk0) {
+    const int c = blockIdx.y, j = blockIdx.z;
+    float* dst = slabs + (long long)c * stream_floats + (long long)(chunk0 + j) * SLAB_CHUNK_FLOATS;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nc * kc; e += gridDim.x * blockDim.x) {
+        const int col = e / kc, kk = e - col * kc;
+        const int n = c * nc + col, k = j * kc + kk;
+        dst[e] = (n < N && k < K) ? W[(long long)n * ldw + k] : 0.f;
+    }
+}
+
 int g_chain_max_ctas = 0;
 
 }  // namespace
 
 void init_chain_attributes() {
+    { const char* w = getenv("RVC_CHAIN_WPRE"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_chain_wpre, &v, sizeof(int)); }
+    { const char* w = getenv("RVC_SLAB_DBG"); int v = w ? atoi(w) : 0; cudaMemcpyToSymbol(g_slab_dbg, &v, sizeof(int)); }
+    { const char* w = getenv("RVC_CHAIN_POLL"); int v = (w && w[0] == '1') ? 1 : 0; cudaMemcpyToSymbol(g_chain_poll, &v, sizeof(int)); }
     cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES);
     cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // single-cluster chains of 16 CTAs
+    cudaFuncSetAttribute(slab_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BYTES);
+    cudaFuncSetAttribute(slab_chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -727,7 +1053,54 @@ int chain_max_coresident_ctas() { return g_chain_max_ctas; }
 void chain_debug_read(long long* out, int n) { cudaMemcpyFromSymbol(out, g_chain_stamp, sizeof(long long) * size_t(n)); }
 void chain_debug_read2(long long* out, int n) { cudaMemcpyFromSymbol(out, g_chain_stamp2, sizeof(long long) * size_t(n)); }
 
+void launch_slab_pack(const float* W, long long ldw, int N, int K, int nc, int kc, int chunks, float* slabs, long long stream_floats,
+                      int chunk0, int G, cudaStream_t stream) {
+    slab_pack_kernel<<<dim3(4, unsigned(G), unsigned(chunks)), 256, 0, stream>>>(W, ldw, N, K, nc, kc, chunks, slabs, stream_floats, chunk0);
+}
+
 int launch_chain(const ChainDev& c, cudaStream_t stream) {
+    if (c.slab) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(SLAB_THREADS); cfg.dynamicSmemBytes = SLAB_SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = unsigned(c.grid); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributePriority;
+        attr[1].val.priority = g_launch_priority;
+        cfg.attrs = attr; cfg.numAttrs = g_launch_priority != 0 ? 2 : 1;
+        const ChainOpDev* ops = c.d_ops; const ChainPhaseDev* phases = c.d_phases; int no = c.n_ops, n = c.n_phases;
+        const float* slabs = c.d_slabs; long long sf = c.slab_stream_floats; const int* cb = c.d_chunk_bytes; int tc = c.slab_total_chunks;
+        unsigned long long* dbg = c.d_dbg;
+        CUtensorMap map;
+        std::memset(&map, 0, sizeof(map));
+        int use_map = 0;
+        {
+            static const bool want = getenv("RVC_SLAB_TMA") && getenv("RVC_SLAB_TMA")[0] == '1';   // measured slower than the 1-D bulk copies (profiles/README.md): opt-in
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static EncodeFn fn = nullptr;
+            static bool tried = false;
+            if (!tried) {
+                tried = true;
+                void* pfn = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+                    fn = reinterpret_cast<EncodeFn>(pfn);
+            }
+            if (want && fn) {
+                const cuuint64_t rows = cuuint64_t(c.grid) * cuuint64_t(sf / 32);
+                cuuint64_t dims[2] = {32, rows};
+                cuuint64_t strides[1] = {128};
+                cuuint32_t box[2] = {32, cuuint32_t(SLAB_CHUNK_FLOATS / 32)};
+                cuuint32_t estr[2] = {1, 1};
+                if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(slabs), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                    use_map = 1;
+            }
+        }
+        cudaLaunchKernelEx(&cfg, slab_chain_kernel, map, use_map, ops, phases, no, n, slabs, sf, cb, tc, dbg);
+        return 1;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = CHAIN_SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[2];

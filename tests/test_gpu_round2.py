@@ -315,3 +315,25 @@ def test_other_generator_rates(env, sr):
     out = e.process_frame(pl.synthetic_pcm(frame, seed=72))
     assert out.shape == (frame,) and np.isfinite(out).all()
     e.close()
+
+
+def test_slab_chains_match_separate_kernels(env, monkeypatch):
+    """Slab chains (chain.h, opt-in with RVC_SLAB=1): enc_p, flow and RMVPE's bottleneck as single 16-CTA clusters whose
+    GEMMs are split by output columns, weights re-packed into per-CTA streams pulled by a producer warp ahead of the
+    cluster barriers.  Same integers / audio as the separate kernels."""
+    monkeypatch.setenv("RVC_CHAIN", "2")
+    monkeypatch.setenv("RVC_SLAB", "1")
+    e1 = _engine(env, noise_seed=9)
+    a1, am1, p1 = _two_windows(e1, env, 49)
+    chains = e1.profile_chains()
+    assert len(chains) >= 3 and all(c["grid"] == 16 for c in chains)
+    e1.close()
+    monkeypatch.setenv("RVC_SLAB", "0")
+    monkeypatch.setenv("RVC_CHAIN", "0")
+    e0 = _engine(env, noise_seed=9)
+    a0, am0, p0 = _two_windows(e0, env, 49)
+    e0.close()
+    np.testing.assert_array_equal(am1, am0)
+    np.testing.assert_array_equal(p1, p0)
+    for a, b in zip(a1, a0):
+        np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
