@@ -481,6 +481,8 @@ def main():
         step_us = dev_ms / args.steps * 1e3
 
         def family(o):
+            if o["kind"] == "cvstack":
+                return "cvstack_kernel(tcgen05 2xFP16 split, persistent: 12 ContentVec layers in one launch)"
             if o["kind"] != "gemm":
                 return o["kind"]
             v = o.get("variant", 0)
@@ -502,7 +504,7 @@ def main():
         def roof_of(name, f):
             tfl = f["flops"] / (f["us"] * 1e-6) / 1e12
             gbs = f["bytes"] / (f["us"] * 1e-6) / 1e9
-            if name.startswith("umma"):
+            if name.startswith("umma") or name.startswith("cvstack"):
                 r = {"bound": "tensor", "achieved": tfl, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tfl / pk["bf16"]}
             else:
                 r = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}

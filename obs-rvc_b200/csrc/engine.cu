@@ -226,6 +226,7 @@ struct rvc_ctx {
     int f0_priority = 0;        // launch priority of the F0 lanes' kernels (highest stream priority of the device; RVC_F0_PRIO=0 disables)
     bool chain_force = false;   // RVC_CHAIN=2: keep chains even when several contexts share the device
     int cvstack_grid = 64;      // CTAs of the persistent ContentVec stack kernel (RVC_CVSTACK=0 disables, RVC_CVSTACK_G sets the grid)
+    bool cvstack_all = false;   // RVC_CVSTACK=1: also for the hubert / feature plans
     bool knn_umma = true;       // RVC_KNN_UMMA=0: retrieval always on the fp32 scan (kernels_knn.cu)
 
     int fail(int code, const std::string& m) { err = m; return code; }
@@ -605,7 +606,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
     opt.allow_umma = ctx->allow_umma;
     opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
     opt.chain_side_max_m = ctx->chain_side_max_m;
-    opt.cv_stack = key.chains && ctx->cvstack_grid > 0 && ctx->allow_umma;
+    opt.cv_stack = key.chains && ctx->cvstack_grid > 0 && ctx->allow_umma && (kind == PLAN_INFER || ctx->cvstack_all);
     opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;
     if (ctx->index.loaded && ctx->knn_umma) { opt.index_planes_off = ctx->index.d->planes_off; opt.index_ymax2 = ctx->index.d->ymax2; }
     {   // RVC_F0_UMMA: 0 never, 1 always, default = batched plans only
@@ -889,7 +890,10 @@ int rvc_create(const char* data_path, const rvc_config* cfg, rvc_ctx** out) {
     { const char* ev = getenv("RVC_KNN_UMMA"); ctx->knn_umma = !(ev && ev[0] == '0'); }
     {
         const char* ev = getenv("RVC_CVSTACK"); const char* eg = getenv("RVC_CVSTACK_G");
-        ctx->cvstack_grid = (ev && ev[0] == '1') ? (eg ? atoi(eg) : 64) : 0;   // opt-in: measured on par with the separate kernels (profiles/README.md)
+        ctx->cvstack_grid = (ev && ev[0] == '0') ? 0 : (eg ? atoi(eg) : 64);
+        ctx->cvstack_all = ev && ev[0] == '1';   // default: infer plans only (ContentVec has ~0.3 ms of slack behind the F0 lane there and
+                                                 // the stack keeps 84 SMs free for it: 2.72 vs 2.76 ms / window); rvc_hubert alone is
+                                                 // 0.14 ms faster on the separate kernels.  RVC_CVSTACK=1: every plan, =0: never
     }
     {   // persistent chains: CTA budgets (0 = off).  RVC_CHAIN=0 disables both.
         const char* ev = getenv("RVC_CHAIN"); const bool on = !(ev && ev[0] == '0');
@@ -1654,9 +1658,31 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
                                "knn_blend", "gather_rows", "fill", "wait"};
     std::string js = "[";
     bool first = true;
+    double st_flops = 0, st_wbytes = 0, st_iobytes = 0;   // the persistent ContentVec stack: one launch, timed as a whole
     for (const Op& op : e.plan.ops) {
         if (op.kind == OP_WAIT || op.kind == OP_FILL) continue;
         if (op.kind == OP_F0POST) continue;  // stateful (rolls the pitch cache)
+        if (op.stack && e.cvs.grid > 0) {
+            if (op.kind == OP_GEMM) {
+                const GemmOp& g = op.gemm;
+                st_flops += 2.0 * g.M * double(g.N) * g.K; st_wbytes += 4.0 * double(g.N) * g.K;
+                st_iobytes += 4.0 * (double(g.M) * g.K + double(g.M) * g.N * (g.R.null() ? 1 : 2));
+            }
+            if (&op != &e.plan.ops[size_t(e.plan.cvstack.first + e.plan.cvstack.count - 1)]) continue;
+            launch_cvstack(e.cvs, s);
+            CK(cudaStreamSynchronize(s));
+            CK(cudaEventRecord(t0, s));
+            for (int i = 0; i < iters; ++i) launch_cvstack(e.cvs, s);   // cooperative launches are not captured into a graph here
+            CK(cudaEventRecord(t1, s));
+            CK(cudaEventSynchronize(t1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, t0, t1));
+            char buf[512];
+            std::snprintf(buf, sizeof(buf), "%s{\"name\": \"cv.stack\", \"kind\": \"cvstack\", \"lane\": %d, \"us\": %.3f, \"flops\": %.0f, \"wbytes\": %.0f, \"iobytes\": %.0f, \"M\": %d, \"variant\": -1, \"splitk\": 1, \"chain\": -1}",
+                          first ? "" : ", ", op.lane, double(ms) * 1e3 / iters, st_flops, st_wbytes, st_iobytes, e.plan.cvstack.T);
+            js += buf; first = false;
+            continue;
+        }
         int n = 0;
         issue_one(ctx, op, B, s, &n);  // warm (also sets kernel attributes outside capture)
         CK(cudaStreamSynchronize(s));
