@@ -15,7 +15,7 @@
 namespace rvc {
 
 struct GemmSched {
-    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM32/BN32 (v2);
+    int variant = 0;  // 0: v1 (kernels_gemm.cu); 1: BM8/BN256; 2: BM16/BN128; 3: BM32/BN64; 4: BM32/BN32 (v2; six-stage ring when a split-K slice has <= 5 k-tiles);
                       // 5/6/7/8/9: tcgen05 kernel (kernels_umma.cu) with BN = 128/64/32/256/16
     int bm = 0, bn = 0, splitk = 1, tiles = 0;
 };
@@ -82,7 +82,8 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma, int nb = 1, boo
     // weight-streaming convs with a single row tile (RMVPE's deep levels: <= 32 pixels x 256..512 channels x K in the
     // thousands): 32-wide column tiles double the CTAs that pull the weights (RVC_V2_NARROW=0 restores 64-wide tiles)
     static const int kNarrow = sched_env("RVC_V2_NARROW", 1);
-    if (kNarrow && g.M <= 32 && g.N >= 128 && g.K >= 1024 && s.variant == 3) { s.variant = 4; s.bm = 32; s.bn = 32; }
+    static const int kNarrowM = sched_env("RVC_V2_NARROW_M", 32);
+    if (kNarrow && g.M <= kNarrowM && g.N >= 64 && g.K >= 512 && s.variant == 3) { s.variant = 4; s.bm = 32; s.bn = 32; }
     // narrow outputs: do not waste a 256/128-wide tile on a 32..64-column problem
     if (s.variant == 1 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
     if (s.variant == 2 && g.N <= 64) { s.variant = 3; s.bm = 32; s.bn = 64; }
@@ -93,6 +94,16 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma, int nb = 1, boo
     int maxsplit = std::max(1, nkt / 4);                        // at least 4 k-tiles per split
     // every extra split costs a partial-tile round trip through L2 in the last CTA: keep the group small
     s.splitk = std::max(1, std::min(std::min(want, maxsplit), 8));
+    // Weight-streaming convs with one row tile (RMVPE's deep levels): a CTA's k extent is a chain of HBM round trips
+    // (ring of 3 k-tiles in flight) - more, shorter slices whose k-tiles are ALL in flight at once (six-stage ring,
+    // <= 5 k-tiles per CTA) cut the chain to one round trip.  RVC_V2_DEEP = largest split-K factor (0 = off)
+    static const int kDeep = sched_env("RVC_V2_DEEP", 0);   // measured: 2.79 vs 2.72-2.75 ms / window with 15-16 slices (the last CTA's reduction of 15 partial tiles costs more than the shorter load chain saves): off
+    if (kDeep > 8 && s.variant == 4 && g.M <= kNarrowM && g.N >= 64 && g.K >= 512 && nb == 1) {
+        const int sk = std::min(std::min(kDeep, (nkt + 4) / 5 > 0 ? nkt : 1), std::max(1, (NUM_SMS + s.tiles - 1) / s.tiles));
+        int best = s.splitk;
+        for (int c = s.splitk; c <= sk; ++c) if ((nkt + c - 1) / c <= 5) { best = c; break; }
+        if (best > s.splitk) s.splitk = best;   // launch_gemm_v2 picks the six-stage instance when a slice has <= 5 k-tiles
+    }
     if (g.out_mode != OUT_PLAIN && false) s.splitk = 1;
     return s;
 }

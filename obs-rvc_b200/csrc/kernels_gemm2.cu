@@ -283,7 +283,11 @@ int launch_gemm_v2(const GemmOp& g, const DeviceBases& B, cudaStream_t stream) {
         // (deeper rings were measured slower: profiles/README.md)
         case 1: launch_v2<8, 256, 3>(g, p, B.nb, stream); break;
         case 2: launch_v2<16, 128, 4>(g, p, B.nb, stream); break;
-        case 4: launch_v2<32, 32, 4>(g, p, B.nb, stream); break;
+        case 4:
+            // a short split-K slice (<= 5 k-tiles): the six-stage ring has every k-tile in flight at once - one HBM round trip
+            if (g.splitk > 1 && ((g.K + BK2 - 1) / BK2 + g.splitk - 1) / g.splitk <= 5) launch_v2<32, 32, 6>(g, p, B.nb, stream);
+            else launch_v2<32, 32, 4>(g, p, B.nb, stream);
+            break;
         default: launch_v2<32, 64, 4>(g, p, B.nb, stream); break;
     }
     return 1;
@@ -297,6 +301,7 @@ void init_gemm_v2_attributes() {
     cudaFuncSetAttribute(gemm_v2_kernel<16, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(float) * 4 * (16 + 128) * LDS2));
     cudaFuncSetAttribute(gemm_v2_kernel<32, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(gemm_v2_kernel<32, 32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(gemm_v2_kernel<32, 32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
 }
 
 }  // namespace rvc
