@@ -1447,6 +1447,7 @@ static int upload_resampler(rvc_ctx* ctx, int fs_in, int fs_out, int chunk, Resa
     }
     r.cur = 0;
     std::vector<float>().swap(r.t.kappa);
+    CK(cudaDeviceSynchronize());   // the memsets above run on the legacy stream: they must not trail the first launch on the context's own stream
     return RVC_OK;
 }
 
@@ -1506,6 +1507,7 @@ int rvc_stream_open(rvc_ctx* ctx, const rvc_stream_config* cfg, uint32_t* sample
                         size_t(st.sola_search) + 64 + size_t(st.sola_buf) + 1024;
     CK(cudaMalloc(&st.scratch, st.scratch_floats * 4));
     CK(cudaMemset(st.scratch, 0, st.scratch_floats * 4));
+    CK(cudaDeviceSynchronize());   // (memsets on the legacy stream, launches on the context's stream)
     st.cur = 0; st.frames = 0; st.open = true;
     if (sample_frame_size) *sample_frame_size = uint32_t(st.sample_frame_size);
     return RVC_OK;
