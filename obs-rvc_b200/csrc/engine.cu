@@ -280,6 +280,9 @@ int upload(rvc_ctx* ctx, ModelData& m, bool with_hilo) {
 }
 
 int issue_one(rvc_ctx* ctx, const Op& op, const DeviceBases& B, cudaStream_t s, int* n) {
+    // RMVPE residual block run by one kernel: launched where the block's last GEMM stood, the other ops are covered
+    if (op.fuse == 1) return RVC_OK;
+    if (op.fuse == 2) { *n += launch_cbr(op.cbr, B, s); return RVC_OK; }
     switch (op.kind) {
         case OP_GEMM: *n += launch_gemm(op.gemm, B, s); break;
         case OP_LAYERNORM: *n += launch_layernorm(op.ln, B, s); break;
@@ -606,6 +609,10 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
     opt.allow_umma = ctx->allow_umma;
     opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
     opt.chain_side_max_m = ctx->chain_side_max_m;
+    // fused residual blocks of RMVPE's two full-resolution levels (kernels_cbr.cu): 0 off, 1 encoder + decoder, 2 decoder
+    // only - beside ContentVec's conv stem the encoder's fused blocks lose more than they gain (profiles/README.md)
+    const int fuse_cbr = [] { const char* ev = getenv("RVC_CBR"); return ev ? atoi(ev) : 2; }();
+    opt.fuse_cbr = fuse_cbr;
     opt.cv_stack = key.chains && ctx->cvstack_grid > 0 && ctx->allow_umma && (kind == PLAN_INFER || ctx->cvstack_all);
     opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;
     if (ctx->index.loaded && ctx->knn_umma) { opt.index_planes_off = ctx->index.d->planes_off; opt.index_ymax2 = ctx->index.d->ymax2; }
@@ -1664,6 +1671,7 @@ int rvc_profile_ops(rvc_ctx* ctx, int iters, char* out, size_t cap_bytes, size_t
     for (const Op& op : e.plan.ops) {
         if (op.kind == OP_WAIT || op.kind == OP_FILL) continue;
         if (op.kind == OP_F0POST) continue;  // stateful (rolls the pitch cache)
+        if (op.fuse == 1) continue;          // covered by the fused residual-block kernel, timed under the block's last op
         if (op.stack && e.cvs.grid > 0) {
             if (op.kind == OP_GEMM) {
                 const GemmOp& g = op.gemm;

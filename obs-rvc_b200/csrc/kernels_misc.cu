@@ -543,6 +543,7 @@ void init_kernel_attributes() {
     init_umma_attributes();
     init_chain_attributes();
     init_cvstack_attributes();
+    init_cbr_attributes();
 }
 
 void launch_split_hilo16(const float* src, unsigned short* dst_hi, unsigned short* dst_lo, size_t n, cudaStream_t stream) {

@@ -30,6 +30,9 @@ struct DeviceBases {
 // Each launcher enqueues exactly the kernels of one op on `stream` and returns how many kernels
 // it launched (0 for memset-only ops).  Errors are reported through cudaGetLastError by the caller.
 int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);
+// fused RMVPE residual block (kernels_cbr.cu)
+int launch_cbr(const CbrOp& o, const DeviceBases& B, cudaStream_t stream);
+void init_cbr_attributes();
 int launch_layernorm(const LayerNormOp& o, const DeviceBases& B, cudaStream_t stream);
 int launch_attn(const AttnOp& o, const DeviceBases& B, cudaStream_t stream);
 int launch_relattn(const RelAttnOp& o, const DeviceBases& B, cudaStream_t stream);

@@ -89,6 +89,7 @@ struct PlanOptions {
     int64_t index_planes_off = 0;  // > 0: the index carries fp16 planes (tensor-core candidate pass, kernels_knn_umma.cu)
     float index_ymax2 = 0.f;       // max |y|^2 over the index rows (error bound of the candidate pass)
     bool cv_stack = false;         // ContentVec transformer layers as one persistent tcgen05 kernel (single-window plans, T <= 128)
+    int fuse_cbr = 0;              // RMVPE residual blocks of U-Net levels 0 / 1 as one kernel each (kernels_cbr.cu): 1 all, 2 decoder only
     bool f0_umma = false;          // RMVPE's wide levels on the tcgen05 FP16-split kernel (batched plans; needs the f0 weight planes)
 };
 

@@ -163,6 +163,16 @@ struct GatherRowsOp {  // out[r] = src[min((skip+r)/2, T-1) - row0]  (rvc.rs:99-
 struct FillOp { Ref dst; int64_t bytes = 0; };
 struct WaitOp { int32_t src_lane = 0, dst_lane = 0; };
 
+// RMVPE ConvBlockRes executed by one kernel (kernels_cbr.cu); carried by the block's LAST GEMM op (Op::fuse == 2)
+struct CbrOp {
+    Ref in; Ref w1, b1, w2, b2, wsc, bsc; Ref dst; int64_t ld_dst = 0;
+    int32_t T = 0, F = 0, Cin = 0, C = 0;
+};
+// shapes the fused kernel is instantiated for: 16 / 32 output channels, strips of 32 / 8 or 16 pixels
+inline bool cbr_supported(int C, int Cin, int F) {
+    return Cin % 4 == 0 && Cin <= 64 && ((C == 16 && F % 32 == 0) || (C == 32 && F % 16 == 0));
+}
+
 enum OpKind : int32_t {
     OP_GEMM, OP_LAYERNORM, OP_ATTN, OP_RELATTN, OP_CONV0_STATS, OP_CONV0_APPLY, OP_STFTMEL,
     OP_AVGPOOL, OP_GRU, OP_F0DECODE, OP_F0POST, OP_EMBED, OP_ZP, OP_SINEGEN, OP_AVG3,
@@ -174,12 +184,13 @@ struct Op {
     int32_t lane = 0;
     int32_t chain = -1;  // index into Plan::chains when the op executes inside a persistent chain kernel
     int32_t stack = 0;   // 1: the op is executed by the persistent ContentVec stack kernel (Plan::cvstack, kernels_cvstack.cu)
+    int32_t fuse = 0;    // RMVPE residual block run by the fused kernel: 1 = covered by it (no launch), 2 = launches it (Op::cbr)
     std::string name;  // plan-unique; debug lookups + parity tests
     // exactly one of these is meaningful, selected by `kind`
     GemmOp gemm; LayerNormOp ln; AttnOp attn; RelAttnOp relattn; Conv0StatsOp c0s; Conv0ApplyOp c0a;
     StftMelOp stft; AvgPoolOp pool; GruOp gru; F0DecodeOp f0d; F0PostOp f0p; EmbedOp embed; ZpOp zp;
     SineGenOp sine; Avg3Op avg3; ConvPostOp cpost; KnnScanOp kd; KnnSelectOp ks; KnnBlendOp kb;
-    GatherRowsOp gather; FillOp fill; WaitOp wait;
+    GatherRowsOp gather; FillOp fill; WaitOp wait; CbrOp cbr;
 };
 
 // Runtime parameters that change per call without changing the plan (device-resident block,

@@ -27,6 +27,7 @@ struct PB {
     bool allow_umma = true;
     bool f0_umma = false;
     bool cv_stack = false;
+    int fuse_cbr = 0;
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
 
@@ -206,10 +207,14 @@ void conv_block_res(PB& b, const Packed* P, const std::string& name, const std::
     Map2d t1{b.pad2d(name + "t1", in.T, in.F, cout), in.T, in.F, cout};
     Ref R; int64_t ldr;
     const int M = in.T * (in.F + 2);
+    // levels 0 / 1 of the U-Net: the whole block is one kernel on the GPU (kernels_cbr.cu).  The three GEMM ops stay in
+    // the plan - they ARE the block's definition (CPU interpreter, cost accounting) - and are marked as covered.
+    const bool fuse = (b.fuse_cbr == 1 || (b.fuse_cbr == 2 && name.compare(0, 6, "rm.dec") == 0)) && cbr_supported(cout, in.C, in.F);
+    const size_t first = b.plan.ops.size();
     if (in.C != cout) {
         Ref sc = b.alloc(name + "sc", int64_t(M) * cout);
         const int home = b.lane;
-        const bool side = b.sc_lane >= 0 && b.sc_lane != home;
+        const bool side = !fuse && b.sc_lane >= 0 && b.sc_lane != home;
         if (side) { b.wait(home, b.sc_lane); b.lane = b.sc_lane; }   // shortcut and c1 both only read `in`
         b.gemm(name + "sc", in.base.plus(interior(in)), in.C, in.C, 0, b.w(P, SP_F0, wp + "sc.w"), in.C,
                b.w(P, SP_F0, wp + "sc.b"), sc, cout, M, cout, in.C, ACT_NONE);
@@ -222,6 +227,16 @@ void conv_block_res(PB& b, const Packed* P, const std::string& name, const std::
         R = in.base.plus(interior(in)); ldr = in.C;
     }
     conv3x3(b, P, name + "c2", wp + "c2", t1, cout, dst_interior, ld_dst, ACT_RELU, R, ldr);
+    if (fuse && b.ok) {
+        for (size_t i = first; i < b.plan.ops.size(); ++i) b.plan.ops[i].fuse = 1;
+        Op& last = b.plan.ops.back();
+        last.fuse = 2;
+        CbrOp& c = last.cbr;
+        c.in = in.base; c.T = in.T; c.F = in.F; c.Cin = in.C; c.C = cout; c.dst = dst_interior; c.ld_dst = ld_dst;
+        c.w1 = b.w(P, SP_F0, wp + "c1.w"); c.b1 = b.w(P, SP_F0, wp + "c1.b");
+        c.w2 = b.w(P, SP_F0, wp + "c2.w"); c.b2 = b.w(P, SP_F0, wp + "c2.b");
+        if (in.C != cout) { c.wsc = b.w(P, SP_F0, wp + "sc.w"); c.bsc = b.w(P, SP_F0, wp + "sc.b"); }
+    }
 }
 
 struct F0Out { Ref salience, f0, argmax, mel; int T; };
@@ -557,6 +572,7 @@ bool gemm_aligned(const GemmOp& g) {
 
 bool chain_eligible(const Op& op, int side_max_m) {
     if (op.stack) return false;   // runs inside the persistent ContentVec stack kernel
+    if (op.fuse) return false;    // runs inside the fused residual-block kernel
     switch (op.kind) {
         case OP_GEMM: {
             const GemmOp& g = op.gemm;
@@ -675,6 +691,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     b.allow_umma = opt.allow_umma;
     b.f0_umma = opt.f0_umma;
     b.cv_stack = opt.cv_stack && opt.nb <= 1;
+    b.fuse_cbr = opt.fuse_cbr;
     plan.params = Ref{SP_STATE, StateLayout::off_params};
     plan.cache = Ref{SP_STATE, StateLayout::off_cache};
     plan.pcm = Ref{SP_STATE, StateLayout::off_pcm};
@@ -809,7 +826,13 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
             return false;
         }
         const bool um = opt.index_planes_off > 0 && knn_umma_ok(C, k);
-        const int parts = um ? knn_umma_parts(Nrows) : knn_parts(Q, C, k, Nrows), kc = um ? KNN_UMMA_KC : k;
+        int parts = um ? knn_umma_parts(Nrows) : knn_parts(Q, C, k, Nrows);
+        const int kc = um ? KNN_UMMA_KC : k;
+        {
+            // the scan runs beside the F0 lane (the longer branch): RVC_KNN_WPARTS caps its CTAs (0 = one or two per SM)
+            static const int wparts = sched_env("RVC_KNN_WPARTS", 0);
+            if (wparts > 0 && ml && !um && opt.nb <= 1 && wparts < parts) parts = wparts;
+        }
         Ref cd = b.alloc("knn_cand_d", int64_t(Q) * parts * kc), ci = b.alloc("knn_cand_i", int64_t(Q) * parts * kc, true);
         Ref idx = b.alloc("knn_idx", int64_t(Q) * k, true), d2 = b.alloc("knn_d2", int64_t(Q) * k);
         Ref xb = b.alloc("knn_blend", int64_t(Q) * C);

@@ -140,8 +140,8 @@ def _two_windows(e, env, seed):
 
 
 def test_cvstack_kernel_matches_separate_kernels(env, monkeypatch):
-    """The persistent ContentVec stack kernel (kernels_cvstack.cu: 12 layers in one cooperative tcgen05 launch, opt-in
-    with RVC_CVSTACK=1) against the oracle at the reference's feature tolerance and against the same window on the
+    """The persistent ContentVec stack kernel (kernels_cvstack.cu: 12 layers in one cooperative tcgen05 launch; the default
+    for infer plans, RVC_CVSTACK=1 extends it to the other plan kinds) against the oracle at the reference's feature tolerance and against the same window on the
     separate kernels: integers identical, audio equal up to fp32 summation order."""
     pl = env["pipeline"]
     g = pl.BASELINE_GEOM
@@ -337,3 +337,23 @@ def test_slab_chains_match_separate_kernels(env, monkeypatch):
     np.testing.assert_array_equal(p1, p0)
     for a, b in zip(a1, a0):
         np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_fused_residual_blocks_match_separate_gemms(env, monkeypatch):
+    """kernels_cbr.cu: RMVPE's ConvBlockRes at U-Net levels 0 / 1 as one kernel per block (default: the decoder's blocks,
+    RVC_CBR=1: the encoder's too, RVC_CBR=0: three implicit GEMMs per block).  Same pitch bins / argmax, audio within 1e-4,
+    and fewer launches."""
+    out = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("RVC_CBR", mode)
+        e = _engine(env, noise_seed=9)
+        a, am, p = _two_windows(e, env, 49)
+        out[mode] = (a, am, p, e.kernel_launches())
+        e.close()
+    assert out["1"][3] < out["2"][3] < out["0"][3]
+    for mode in ("1", "2"):
+        np.testing.assert_array_equal(out[mode][1], out["0"][1])
+        np.testing.assert_array_equal(out[mode][2], out["0"][2])
+        for a, b in zip(out[mode][0], out["0"][0]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
