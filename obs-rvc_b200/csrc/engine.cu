@@ -1850,6 +1850,16 @@ int rvc_debug_cvstack_stamps(rvc_ctx* ctx, long long* out, int n) {
     return ctx->last->cvs.n_phases;
 }
 
+// %globaltimer (ns) of the marker kernels of the last window: STFT start, F0 decode start, pitch cache start, retrieval
+// gather start, conv_post end, RMVPE pool 0..4 start, GRU start (11 values).  Written by the kernels themselves: no event nodes, the graph replays unperturbed.
+int rvc_debug_lane_stamps(rvc_ctx* ctx, unsigned long long* out11) {
+    int rc = enter(ctx); if (rc) return rc;
+    ctx->sync_all();
+    dsp_read_stamps(out11);
+    misc_read_stamps(out11 + 3);
+    return RVC_OK;
+}
+
 int rvc_debug_chain_stamps(rvc_ctx* ctx, int chain, long long* out2048) {
     int rc = enter(ctx); if (rc) return rc;
     if (!ctx->last || chain < 0 || size_t(chain) >= ctx->last->chains.size()) return RVC_ERR_INVALID_ARG;

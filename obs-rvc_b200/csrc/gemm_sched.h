@@ -90,7 +90,8 @@ inline GemmSched gemm_schedule(const GemmOp& g, bool allow_umma, int nb = 1, boo
     const int tm = (g.M + s.bm - 1) / s.bm, tn = (g.N + s.bn - 1) / s.bn;
     s.tiles = tm * tn * g.batch;
     const int nkt = (g.K + GEMM2_BK - 1) / GEMM2_BK;
-    int want = (2 * NUM_SMS + s.tiles * nb - 1) / (s.tiles * nb);   // ~2 CTAs per SM in total
+    static const int kV2Want = sched_env("RVC_V2_WANT", 2 * NUM_SMS);
+    int want = (kV2Want + s.tiles * nb - 1) / (s.tiles * nb);   // ~2 CTAs per SM in total
     int maxsplit = std::max(1, nkt / 4);                        // at least 4 k-tiles per split
     // every extra split costs a partial-tile round trip through L2 in the last CTA: keep the group small
     s.splitk = std::max(1, std::min(std::min(want, maxsplit), 8));

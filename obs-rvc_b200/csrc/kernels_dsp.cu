@@ -17,6 +17,8 @@ namespace {
 // (rmvpe.rs:47-68 pad_reflect, 80-116 stft, 159-205 mel_extract).  HBM traffic per frame is the
 // 1024 input samples and 128 outputs; the filterbank (1010 non-zeros) stays in L2/L1.
 // ------------------------------------------------------------------------------------------
+__device__ unsigned long long g_dsp_stamps[4];   // [0] STFT start, [1] F0 decode start, [2] pitch cache start
+
 __global__ void __launch_bounds__(256)
 stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restrict__ window,
                     const int* __restrict__ band_start, const int* __restrict__ band_count,
@@ -24,6 +26,7 @@ stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restric
                     float* __restrict__ out2, long long out2_pitch, float scale, float shift, float clamp,
                     long long wPcm, long long wMel, long long wOut2) {
     pdl_enter();
+    lane_stamp(&g_dsp_stamps[0]);
     pcm += blockIdx.z * wPcm; mel += blockIdx.z * wMel;
     if (out2) out2 += blockIdx.z * wOut2;
     __shared__ float2 buf[1024];
@@ -77,6 +80,7 @@ f0_decode_kernel(const float* __restrict__ sal, float* __restrict__ f0, int* __r
                  const RunParams* __restrict__ rp, int bins, float threshold, int upstream_window,
                  long long wSal, long long wF0, long long wArg, long long wRp) {
     pdl_enter();
+    lane_stamp(&g_dsp_stamps[1]);
     sal += blockIdx.z * wSal; f0 += blockIdx.z * wF0; argmax += blockIdx.z * wArg;
     rp = reinterpret_cast<const RunParams*>(reinterpret_cast<const float*>(rp) + blockIdx.z * wRp);
     const int t = blockIdx.x, tid = threadIdx.x;
@@ -123,6 +127,7 @@ f0_post_kernel(const float* __restrict__ f0, float* __restrict__ cache, int* __r
                int return_length, int n, float mel_min, float mel_max,
                int seq_windows, long long wF0, long long wCache, long long wPitch, long long wPitchf) {
     pdl_enter();
+    lane_stamp(&g_dsp_stamps[2]);
     // Batched plans: independent streams (grid.z = windows, one cache each) or `seq_windows` consecutive windows of
     // ONE stream (grid.z = 1): they update the single cache of window 0 one after the other, as the reference would.
     cache += blockIdx.z * wCache;
@@ -261,5 +266,7 @@ int launch_sinegen(const SineGenOp& o, const DeviceBases& B, cudaStream_t s) {
                                          o.R, o.upp, o.sr, o.lin_w, o.lin_b, B.ws(o.pitchf), B.ws(o.out), B.ws(o.sine_dbg), B.ws(o.params));
     return 1;
 }
+
+void dsp_read_stamps(unsigned long long* out3) { cudaMemcpyFromSymbol(out3, g_dsp_stamps, 3 * sizeof(unsigned long long)); }
 
 }  // namespace rvc

@@ -327,9 +327,11 @@ conv0_apply_kernel(const float* __restrict__ pcm, const float* __restrict__ w, c
 // ------------------------------------------------------------------------------------------
 // 2x2 average pool on halo-padded NHWC
 // ------------------------------------------------------------------------------------------
+__device__ unsigned long long g_misc_stamps[8];   // [0] retrieval gather ("phone") start, [1] conv_post end (CTA 0), [2..6] RMVPE pool 0..4 start, [7] GRU start
 __global__ void avgpool_kernel(const float* __restrict__ in, long long ldin, float* __restrict__ out, int T, int F, int C,
                                long long wIn, long long wOut) {
     pdl_enter();
+    lane_stamp(&g_misc_stamps[2 + min(4, max(0, 31 - __clz(C >> 4)))]);
     in += blockIdx.z * wIn; out += blockIdx.z * wOut;
     const int To = T / 2, Fo = F / 2;
     const long long n = (long long)To * Fo * C;
@@ -356,6 +358,7 @@ __global__ void __cluster_dims__(GRU_CL, 1, 1) __launch_bounds__(768)
 gru_cluster_kernel(const float* __restrict__ gi, const float* __restrict__ whh_t, const float* __restrict__ bhh,
                    float* __restrict__ out, int T, long long wGi, long long wOut) {
     pdl_enter();
+    lane_stamp(&g_misc_stamps[7]);
     gi += blockIdx.z * wGi; out += blockIdx.z * wOut;
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int H = GRU_H, G = 3 * GRU_H;
@@ -472,6 +475,7 @@ __global__ void avg3_kernel(const float* __restrict__ a, const float* __restrict
     }
 }
 
+
 // conv_post: tanh(conv1d(C -> 1, k)); thread per output sample, weights in smem
 __global__ void __launch_bounds__(256)
 convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out, int T, int C, int k,
@@ -492,11 +496,13 @@ convpost_kernel(const float* __restrict__ in, const float* __restrict__ w, float
         a2 = fmaf(v.z, ws[4 * j + 2], a2); a3 = fmaf(v.w, ws[4 * j + 3], a3);
     }
     out[t] = tanhf((a0 + a1) + (a2 + a3));
+    lane_stamp(&g_misc_stamps[1]);
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, long long lds, float* __restrict__ out, int T, int C,
                                    int skip, int R, int row0, long long wSrc, long long wOut) {
     pdl_enter();
+    lane_stamp(&g_misc_stamps[0]);
     src += blockIdx.z * wSrc; out += blockIdx.z * wOut;
     const long long n = (long long)R * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -533,6 +539,8 @@ size_t attn_smem(int T) { const int Tp = (T | 1) + 2; return sizeof(float) * (si
 size_t relattn_smem(int T, int dim) { return sizeof(float) * (size_t(dim) + size_t(T)); }
 
 }  // namespace
+
+void misc_read_stamps(unsigned long long* out8) { cudaMemcpyFromSymbol(out8, g_misc_stamps, 8 * sizeof(unsigned long long)); }
 
 void init_kernel_attributes() {
     static unsigned long long done = 0;

@@ -20,6 +20,17 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // common prologue of the simple kernels: nothing to overlap but the launch latency itself
 __device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 
+// Lane stamps: %globaltimer written by the first thread of a few marker kernels (STFT start, F0 decode, retrieval gather,
+// pitch cache, conv_post) into a per-file device array - where the two front-end lanes and the tail stand inside a
+// graph-replayed window WITHOUT event nodes in the graph (rvc_debug_lane_stamps; an event after an op perturbs the lanes).
+__device__ __forceinline__ void lane_stamp(unsigned long long* slot) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *slot = t;
+    }
+}
+
 extern bool g_use_pdl;  // RVC_PDL=0 disables (engine.cu)
 // Launch priority of the kernels issued next by this thread (0 = default).  engine.cu raises it for the ops of the
 // F0 lanes: the F0 chain is the longest branch of the window and must not queue behind ContentVec's wide grids.

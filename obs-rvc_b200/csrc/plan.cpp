@@ -28,6 +28,7 @@ struct PB {
     bool f0_umma = false;
     bool cv_stack = false;
     int fuse_cbr = 0;
+    int cv_gate = -1;   // >= 0: lane 0 (ContentVec) waits for RMVPE encoder level cv_gate
 
     void fail(const std::string& m) { if (ok) err = m; ok = false; }
 
@@ -287,6 +288,9 @@ F0Out build_rmvpe(PB& b, const Packed* P, const F0Info& info, Ref pcm_window, in
             op.pool.T = Tl; op.pool.F = Fl; op.pool.C = C;
         }
         cur = pooled; Tl /= 2; Fl /= 2; C *= 2;
+        // ContentVec's conv stem (wide grids, ~0.2 ms) starts once this level is done: beside it the full-resolution
+        // convs of level 0 take twice as long, and the ContentVec lane has the slack (PB::cv_gate)
+        if (i == b.cv_gate && b.lane != 0) b.wait(b.lane, 0);
     }
     // intermediate: 16 blocks at (T/32) x 4, 256 -> 512
     for (int i = 0; i < 4; ++i)
@@ -763,7 +767,12 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     const int Lf0 = 5120 * ((g.sf16k + 800 - 1) / 5120 + 1) - 160;  // rmvpe.rs:256
     if (Lf0 > N) { err = "input shorter than the f0 window (rmvpe.rs:257)"; return false; }
     if (kind == PLAN_PITCH) {
+        // RVC_PITCH_ML=1 (experiment): the pitch plan with the lane structure the F0 branch has inside an infer plan
+        // (lane 1, shortcut convs on lane 3, side-lane chains) - its stand-alone time is what ContentVec's concurrency costs
+        static const bool as_side = sched_env("RVC_PITCH_ML", 0) != 0;
+        if (as_side && opt.multi_lane) { b.wait(0, 1); b.lane = 1; b.sc_lane = sched_env("RVC_SC_LANE", 1) != 0 ? 3 : -1; }
         F0Out o = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
+        if (as_side && opt.multi_lane) { b.lane = 0; b.sc_lane = -1; b.wait(1, 0); }
         plan.f0_T = o.T;
         schedule_gemms(b);
     form_chains(b, opt);
@@ -787,9 +796,10 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     static const bool f0_first = sched_env("RVC_F0_FIRST", 1) != 0;
     auto emit_f0 = [&]() {
         static const bool sc_side = sched_env("RVC_SC_LANE", 1) != 0;   // 0: shortcut convs stay on the F0 lane (same chain phase as c1)
-        if (ml) { b.lane = 1; b.sc_lane = sc_side ? 3 : -1; }
+        static const int cv_gate = sched_env("RVC_CV_GATE", -1);
+        if (ml) { b.lane = 1; b.sc_lane = sc_side ? 3 : -1; b.cv_gate = (f0_first && opt.nb <= 1) ? cv_gate : -1; }
         fo = build_rmvpe(b, f0, *f0i, plan.pcm.plus(N - Lf0), Lf0, plan.params, false, opt.upstream_cents_window);
-        b.lane = 0; b.sc_lane = -1;
+        b.lane = 0; b.sc_lane = -1; b.cv_gate = -1;
     };
     // The lane whose ops are emitted (= whose graph nodes are created) first gets the SMs first when both lanes have
     // work ready.  Since the tcgen05 GEMMs got faster the F0 chain is the longer branch: it goes first.
