@@ -6,7 +6,10 @@
 
 namespace rvc {
 
-constexpr int CVS_BN = 48;          // output columns per GEMM tile (N of every stack GEMM is a multiple of 48)
+#ifndef RVC_CVS_BN
+#define RVC_CVS_BN 48
+#endif
+constexpr int CVS_BN = RVC_CVS_BN;   // output columns per GEMM tile (N of every stack GEMM is a multiple of it; 48 or 96)
 constexpr int CVS_ATT_ROWS = 24;    // most query rows per attention item
 constexpr int CVS_SCRATCH_BYTES = 46 * 1024;   // worker scratch of a CTA: K^T / V staging, scores, q rows
 // query rows per attention item that fit the scratch at T rows: K^T [64][Tp] + per row (scores [Tp], 1 / sum, q [64])

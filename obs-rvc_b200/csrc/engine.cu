@@ -36,7 +36,7 @@
 using namespace rvc;
 
 static bool g_sync_each = false;
-namespace rvc { bool g_use_pdl = false; thread_local int g_launch_priority = 0; }  // measured: no gain on this path (profiles/README), opt-in with RVC_PDL=1
+namespace rvc { bool g_use_pdl = false; thread_local bool g_pdl_op = false; thread_local int g_launch_priority = 0; }  // measured: no gain on this path (profiles/README), opt-in with RVC_PDL=1
 
 namespace {
 
@@ -330,8 +330,32 @@ static const char* stage_of(const Op& op) {
     return nullptr;
 }
 
+// RVC_PDL_OPS=pattern,pattern,...: programmatic dependent launch for the ops whose names match (the kernel may be
+// scheduled while its predecessor on the lane still runs and waits at griddepcontrol.wait).  Which ops gain is an
+// empirical matter (profiles/README.md, tools/pdl_search.py): a dependent launch costs 1.3-3 us more while ANY other grid
+// is resident, PDL hides that for the F0 encoder and the vocoder, and costs elsewhere.
+#define RVC_PDL_OPS_DEFAULT "rm.enc,rm.dec0,rm.dec1,rm.dec*c2,sy.,knn_scan,phone"   // tools/pdl_search.py: 2.74 -> 2.66-2.67 ms / window
+static std::vector<std::string> pdl_patterns() {
+    std::vector<std::string> v;
+    const char* e = getenv("RVC_PDL_OPS");
+    std::string s(e ? e : RVC_PDL_OPS_DEFAULT), t;
+    for (char c : s + ",") { if (c == ',') { if (!t.empty()) v.push_back(t); t.clear(); } else t += c; }
+    return v;
+}
+// "prefix" or "prefix*suffix"
+static bool pdl_for(const std::vector<std::string>& pre, const std::string& name) {
+    for (const std::string& p : pre) {
+        const size_t star = p.find('*');
+        if (star == std::string::npos) { if (name.compare(0, p.size(), p) == 0) return true; continue; }
+        const std::string a = p.substr(0, star), b = p.substr(star + 1);
+        if (name.size() >= a.size() + b.size() && name.compare(0, a.size(), a) == 0 && name.compare(name.size() - b.size(), b.size(), b) == 0) return true;
+    }
+    return false;
+}
+
 int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
     const DeviceBases B = ctx->bases(e);
+    const std::vector<std::string> pdl_pat = pdl_patterns();
     size_t ev = 0;
     int n = 0;
     const char* cur_stage = nullptr;
@@ -356,6 +380,7 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
             continue;
         }
         rvc::g_launch_priority = (ctx->f0_priority != 0 && (op.lane == 1 || op.lane == 3) && op.name.compare(0, 3, "sy.") != 0) ? ctx->f0_priority : 0;
+        rvc::g_pdl_op = pdl_for(pdl_pat, op.name);
         if (op.stack && e.cvs.grid > 0) {
             // ContentVec's transformer layers: one persistent tcgen05 kernel, launched where the first op stood
             if (&op == &e.plan.ops[size_t(e.plan.cvstack.first)]) n += launch_cvstack(e.cvs, ctx->streams[op.lane]);
@@ -374,7 +399,7 @@ int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
             if (se != cudaSuccess) return ctx->fail(RVC_ERR_CUDA, "op '" + op.name + "' failed: " + cudaGetErrorString(se));
         }
     }
-    rvc::g_launch_priority = 0;
+    rvc::g_launch_priority = 0; rvc::g_pdl_op = false;
     CK(cudaGetLastError());
     *launches = n;
     return RVC_OK;
@@ -1816,7 +1841,8 @@ int rvc_profile_chains(rvc_ctx* ctx, char* out, size_t cap_bytes, size_t* out_by
         std::vector<unsigned long long> t(size_t(ci.n_phases + 1));
         CK(cudaMemcpy(t.data(), e.chains[c].d_dbg, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         char buf[256];
-        std::snprintf(buf, sizeof(buf), "%s{\"chain\": %zu, \"lane\": %d, \"grid\": %d, \"phases\": [", c ? ", " : "", c, ci.lane, e.chains[c].grid);
+        std::snprintf(buf, sizeof(buf), "%s{\"chain\": %zu, \"lane\": %d, \"grid\": %d, \"t0_ns\": %llu, \"t1_ns\": %llu, \"phases\": [", c ? ", " : "", c, ci.lane, e.chains[c].grid,
+                      t[0], t[size_t(ci.n_phases)]);
         js += buf;
         for (int ph = 0; ph < ci.n_phases; ++ph) {
             std::string names;

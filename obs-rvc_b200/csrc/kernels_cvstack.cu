@@ -25,6 +25,9 @@
 #include <cstdio>
 #include <vector>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "cvstack.h"
 #include "gemm_common.cuh"
 
@@ -35,7 +38,7 @@ namespace {
 using gemmk::gelu_f;
 
 constexpr int CS_BN = CVS_BN;                 // output columns per tile
-constexpr int CS_STAGES = 4;
+constexpr int CS_STAGES = CVS_BN > 48 ? 3 : 4;
 constexpr int CS_A_BYTES = 128 * 128;         // one fp16 plane of an A k-block: 128 rows x 64 halves
 constexpr int CS_W_BYTES = CS_BN * 128;       // one fp16 plane of a W k-block: 48 rows x 64 halves
 constexpr int CS_STAGE_BYTES = 2 * CS_A_BYTES + 2 * CS_W_BYTES;   // 45056
@@ -43,7 +46,7 @@ constexpr int CS_SCRATCH_BYTES = CVS_SCRATCH_BYTES;   // worker scratch (attenti
 constexpr int CS_SMEM_BYTES = CS_STAGES * CS_STAGE_BYTES + CS_SCRATCH_BYTES + 1024;
 constexpr int CS_THREADS = 320;
 constexpr int CS_WORKERS = 256;
-constexpr int CS_TMEM_COLS = 128;             // 2 x 48 accumulator columns, power of two
+constexpr int CS_TMEM_COLS = CVS_BN > 64 ? 256 : 128;   // 2 x BN accumulator columns, power of two
 constexpr float CS_LO_SCALE = 2048.0f;
 constexpr int CS_ATT_ROWS = CVS_ATT_ROWS;     // query rows per attention item
 constexpr int CS_D = 64;                      // head dim
@@ -649,7 +652,25 @@ void init_cvstack_attributes() {
 }
 int cvstack_max_ctas() { return g_cvs_max_ctas; }
 
+// Experiment (RVC_EXP_SPIN=us[,smem]): instead of the stack, a kernel of the same grid that only waits - no memory
+// traffic, no tensor pipe.  What the F0 lane then loses beside it is the cost of a co-resident grid as such.
+__global__ void __launch_bounds__(CS_THREADS) cvstack_spin_kernel(unsigned long long ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { __nanosleep(1000); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+
 int launch_cvstack(const CvsDev& c, cudaStream_t stream) {
+    static const char* spin = getenv("RVC_EXP_SPIN");
+    if (spin && *spin) {
+        const unsigned long long ns = 1000ull * (unsigned long long)atoi(spin);
+        const char* comma = strchr(spin, ',');
+        const int smem = comma ? atoi(comma + 1) : CS_SMEM_BYTES;
+        static bool once = false;
+        if (!once) { cudaFuncSetAttribute(cvstack_spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM_BYTES); once = true; }
+        cvstack_spin_kernel<<<c.grid, CS_THREADS, smem, stream>>>(ns);
+        return 1;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(CS_THREADS); cfg.dynamicSmemBytes = CS_SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[1];

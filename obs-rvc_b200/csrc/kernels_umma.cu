@@ -728,7 +728,7 @@ bool launch_umma_cfg(const GemmOp& g, GemmParams& p, const void* w_hi, const voi
     attr[0].id = cudaLaunchAttributeClusterDimension;   // split-K group = one thread-block cluster along z
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = unsigned(g.splitk);
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    attr[1].val.programmaticStreamSerializationAllowed = (g_use_pdl || g_pdl_op) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 2;
     if (cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmWlo, p) != cudaSuccess) return false;
     return true;

@@ -31,7 +31,8 @@ __device__ __forceinline__ void lane_stamp(unsigned long long* slot) {
     }
 }
 
-extern bool g_use_pdl;  // RVC_PDL=0 disables (engine.cu)
+extern bool g_use_pdl;  // RVC_PDL=1: every launch (engine.cu)
+extern thread_local bool g_pdl_op;   // this op only (RVC_PDL_OPS, engine.cu issue_ops)
 // Launch priority of the kernels issued next by this thread (0 = default).  engine.cu raises it for the ops of the
 // F0 lanes: the F0 chain is the longest branch of the window and must not queue behind ContentVec's wide grids.
 // Set as a launch attribute so that it survives stream capture (kernel-node attribute of the CUDA graph).
@@ -43,7 +44,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_use_pdl || g_pdl_op) ? 1 : 0;
     attr[1].id = cudaLaunchAttributePriority;
     attr[1].val.priority = g_launch_priority;
     cfg.attrs = attr; cfg.numAttrs = g_launch_priority != 0 ? 2 : 1;

@@ -24,6 +24,9 @@ for i in range(int(os.environ.get("N", "40"))):
     L.rvc_debug_lane_stamps(eng.handle, out)
     t = np.array(list(out), dtype=np.float64)
     rows.append((t[1:] - t[0]) / 1e3)
+    if i == int(os.environ.get("N", "40")) - 1:
+        for c in eng.profile_chains():
+            print(f"CHAIN lane {c['lane']} grid {c['grid']} phases {len(c['phases'])}: start {(c['t0_ns'] - t[0]) / 1e3:.0f} end {(c['t1_ns'] - t[0]) / 1e3:.0f} us  ({c['phases'][0]['ops'][:24]} ...)")
 r = np.median(np.array(rows[8:]), axis=0)
 f0 = f"pool0..4 {r[4]:.0f} {r[5]:.0f} {r[6]:.0f} {r[7]:.0f} {r[8]:.0f}, gru {r[9]:.0f}, f0 decode {r[0]:.0f}"
 if pitch_only: print("STAMPS us after STFT start:", f0)
