@@ -335,10 +335,13 @@ static const char* stage_of(const Op& op) {
 // empirical matter (profiles/README.md, tools/pdl_search.py): a dependent launch costs 1.3-3 us more while ANY other grid
 // is resident, PDL hides that for the F0 encoder and the vocoder, and costs elsewhere.
 #define RVC_PDL_OPS_DEFAULT "rm.enc,rm.dec0,rm.dec1,rm.dec*c2,sy.,knn_scan,phone"   // tools/pdl_search.py: 2.74 -> 2.66-2.67 ms / window
-static std::vector<std::string> pdl_patterns() {
+static std::vector<std::string> pdl_patterns(int nb) {
     std::vector<std::string> v;
     const char* e = getenv("RVC_PDL_OPS");
-    std::string s(e ? e : RVC_PDL_OPS_DEFAULT), t;
+    // the default set was searched on the single-window plan (tools/pdl_search.py); batched plans (throughput-bound
+    // kernels whose early-launched successors take SM slots) want less: 8 streams 1111 -> 1133, 32 offline windows
+    // 1378 -> 1388 windows/s with the RMVPE encoder + synthesizer only
+    std::string s(e ? e : (nb > 1 ? "rm.enc,sy." : RVC_PDL_OPS_DEFAULT)), t;
     for (char c : s + ",") { if (c == ',') { if (!t.empty()) v.push_back(t); t.clear(); } else t += c; }
     return v;
 }
@@ -355,7 +358,7 @@ static bool pdl_for(const std::vector<std::string>& pre, const std::string& name
 
 int issue_ops(rvc_ctx* ctx, PlanEntry& e, int* launches) {
     const DeviceBases B = ctx->bases(e);
-    const std::vector<std::string> pdl_pat = pdl_patterns();
+    const std::vector<std::string> pdl_pat = pdl_patterns(e.plan.nb);
     size_t ev = 0;
     int n = 0;
     const char* cur_stage = nullptr;
@@ -637,7 +640,7 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
     // fused residual blocks of RMVPE's two full-resolution levels (kernels_cbr.cu): 0 off, 1 encoder + decoder, 2 decoder
     // only - beside ContentVec's conv stem the encoder's fused blocks lose more than they gain (profiles/README.md)
     const int fuse_cbr = [] { const char* ev = getenv("RVC_CBR"); return ev ? atoi(ev) : 2; }();
-    opt.fuse_cbr = fuse_cbr;
+    opt.fuse_cbr = key.nb > 1 ? 0 : fuse_cbr;   // batched plans run these levels on the tensor cores (f0_umma)
     opt.cv_stack = key.chains && ctx->cvstack_grid > 0 && ctx->allow_umma && (kind == PLAN_INFER || ctx->cvstack_all);
     opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;
     if (ctx->index.loaded && ctx->knn_umma) { opt.index_planes_off = ctx->index.d->planes_off; opt.index_ymax2 = ctx->index.d->ymax2; }
