@@ -485,9 +485,15 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
             g.R = xu; g.ldr = cout; g.C2 = xa; g.ldc2 = cout; g.act2 = ACT_LRELU01;
         }
         Ref ys[3];
-        if (multi_lane) { b.wait(0, 1); b.wait(0, 2); }  // the three ResBlocks run concurrently
+        // RVC_SY_RB_LANES (experiment): 3 = the three ResBlocks of a stage on three lanes (default), 2 = rk 3 + rk 7 share
+        // lane 1 beside rk 11 on lane 0 (equal work: 3 + 7 ~ 11 taps), 1 = one lane
+        static const int rb_lanes = sched_env("RVC_SY_RB_LANES", 3);
+        const int rbl = multi_lane ? rb_lanes : 1;
+        auto rb_lane = [&](int j) { return rbl >= 3 ? j : (rbl == 2 ? (j == 2 ? 0 : 1) : 0); };
+        if (rbl >= 2) b.wait(0, 1);
+        if (rbl >= 3) b.wait(0, 2);  // the three ResBlocks run concurrently
         for (int j = 0; j < 3; ++j) {
-            b.lane = multi_lane ? j : 0;
+            b.lane = rb_lane(j);
             const int rk = RK[j];
             std::string rn = n + "rb" + S(j) + ".";
             Ref ta_pad = b.alloc("", int64_t(Tout + 2 * HH) * cout);
@@ -511,7 +517,8 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
             }
             b.lane = 0;
         }
-        if (multi_lane) { b.wait(1, 0); b.wait(2, 0); }
+        if (rbl >= 2) b.wait(1, 0);
+        if (rbl >= 3) b.wait(2, 0);
         Ref raw = b.alloc("sy.stage" + S(i), int64_t(Tout) * cout);
         Op& op = b.add(OP_AVG3, "sy.stage" + S(i));
         op.avg3.a = ys[0]; op.avg3.b = ys[1]; op.avg3.c = ys[2]; op.avg3.ld = cout; op.avg3.raw = raw;
