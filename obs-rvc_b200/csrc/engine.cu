@@ -637,9 +637,10 @@ int get_plan(rvc_ctx* ctx, PlanKind kind, const Geometry& g, PlanEntry** out, in
     opt.allow_umma = ctx->allow_umma;
     opt.chain_grid_main = key.chains ? ctx->chain_grid_main : 0; opt.chain_grid_side = key.chains ? ctx->chain_grid_side : 0;
     opt.chain_side_max_m = ctx->chain_side_max_m;
-    // fused residual blocks of RMVPE's two full-resolution levels (kernels_cbr.cu): 0 off, 1 encoder + decoder, 2 decoder
-    // only - beside ContentVec's conv stem the encoder's fused blocks lose more than they gain (profiles/README.md)
-    const int fuse_cbr = [] { const char* ev = getenv("RVC_CBR"); return ev ? atoi(ev) : 2; }();
+    // fused residual blocks of RMVPE's two full-resolution levels (kernels_cbr.cu): 0 off (default), 1 encoder + decoder,
+    // 2 decoder only.  Opt-in: with programmatic dependent launch on the block's GEMMs the two launches are cheaper
+    // than the fused kernel (F0 branch alone 1273 vs 1327 us, window 2.643 vs 2.657 ms; profiles/README.md)
+    const int fuse_cbr = [] { const char* ev = getenv("RVC_CBR"); return ev ? atoi(ev) : 0; }();
     opt.fuse_cbr = key.nb > 1 ? 0 : fuse_cbr;   // batched plans run these levels on the tensor cores (f0_umma)
     opt.cv_stack = key.chains && ctx->cvstack_grid > 0 && ctx->allow_umma && (kind == PLAN_INFER || ctx->cvstack_all);
     opt.nb = key.nb; opt.sequential = key.sequential != 0; opt.index_cols = ctx->index_c;

@@ -23,6 +23,8 @@ namespace rvc {
 
 namespace {
 
+constexpr int CBR_THREADS = 512;   // 16 warps: four per scheduler to cover the shared-memory latency
+
 struct CbrParams {
     const float* in;      // halo-padded NHWC map [T + 2][F + 2][Cin]
     float* dst;           // interior pixel (0, 0) of the destination map, pixel stride ld_dst
@@ -44,53 +46,63 @@ template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.as
 template <int C>
 __device__ __forceinline__ void stage_filters(float4* ws, const float* __restrict__ W, int K) {
     const int nq = K >> 2;
-    for (int i = threadIdx.x; i < nq * C; i += 256) {
+    for (int i = threadIdx.x; i < nq * C; i += CBR_THREADS) {
         const int co = i % C, kq = i / C;
         cp16(ws + kq * (C + 1) + co, W + (long long)co * K + kq * 4);
     }
 }
 
 // One 3x3 conv over a shared-memory strip.  src: [rows][SW][Cs + 4]; output pixels p in [0, NP), p = (p / PW, p % PW)
-// on the strip shifted by one pixel (the 3x3 window of output (r, c) starts at source (r, c)).
+// on the strip shifted by one pixel (the 3x3 window of output (r, c) starts at source (r, c)).  The k loop is flat over
+// the 9 * Cs / 4 k-quads (filter row = k-quad index) and software-pipelined: the operands of quad i + 1 are requested
+// before the FMAs of quad i - with two to four warps per scheduler the shared-memory latency is otherwise exposed
+// (ncu, first version: short-scoreboard stall 3.4 per issue, 0.26 instructions / clock / scheduler).
 template <int C, int PXT, int KS, typename Emit>
 __device__ __forceinline__ void conv_pass(const float* __restrict__ src, int SW, int Cs, const float4* __restrict__ w,
                                           int NP, int PW, Emit&& emit) {
-    constexpr int CG = C / 4, NSLOT = 256 / (CG * KS);
+    constexpr int CG = C / 4, NSLOT = CBR_THREADS / (CG * KS);
+    static_assert(CG * KS <= 32, "k-slices are summed with warp shuffles");
     const int cg = threadIdx.x % CG, ks = (threadIdx.x / CG) % KS, slot = threadIdx.x / (CG * KS);
-    const int Q = Cs >> 2, NI = 9 * Q, ps = Cs + 4;
+    const int Q = Cs >> 2, lq = 31 - __clz(Q), NI = 9 * Q, ps = Cs + 4;
     const int i0 = ks * NI / KS, i1 = (ks + 1) * NI / KS;
+    const float4* wc = w + cg;
     for (int base = 0; base < NP; base += NSLOT * PXT) {
         float acc[PXT][4];
-        int off[PXT];
+        const float* sp[PXT];
 #pragma unroll
         for (int i = 0; i < PXT; ++i) {
             const int p = min(base + slot + i * NSLOT, NP - 1);
-            off[i] = ((p / PW) * SW + p % PW) * ps;
+            sp[i] = src + ((p / PW) * SW + p % PW) * ps;
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
         }
+        float4 an[PXT], wn[4];
+        auto request = [&](int it) {
+            const int tap = it >> lq, q4 = it & (Q - 1), kt = (tap * 11) >> 5, kf = tap - 3 * kt;
+            const int toff = (kt * SW + kf) * ps + q4 * 4;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int toff = ((tap / 3) * SW + tap % 3) * ps;
-            const int qa = max(i0 - tap * Q, 0), qb = min(i1 - tap * Q, Q);
-            const float4* wt = w + (long long)(tap * Q) * (C + 1) + cg;
+            for (int i = 0; i < PXT; ++i) an[i] = *reinterpret_cast<const float4*>(sp[i] + toff);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wn[q] = wc[it * (C + 1) + q * CG];
+        };
+        request(i0);
 #pragma unroll 2
-            for (int q4 = qa; q4 < qb; ++q4) {
-                float4 a[PXT];
+        for (int it = i0; it < i1; ++it) {
+            float4 a[PXT], ww[4];
 #pragma unroll
-                for (int i = 0; i < PXT; ++i) a[i] = *reinterpret_cast<const float4*>(src + off[i] + toff + q4 * 4);
+            for (int i = 0; i < PXT; ++i) a[i] = an[i];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 ww = wt[q4 * (C + 1) + q * CG];
+            for (int q = 0; q < 4; ++q) ww[q] = wn[q];
+            if (it + 1 < i1) request(it + 1);
 #pragma unroll
-                    for (int i = 0; i < PXT; ++i) {
-                        acc[i][q] = fmaf(a[i].x, ww.x, acc[i][q]);
-                        acc[i][q] = fmaf(a[i].y, ww.y, acc[i][q]);
-                        acc[i][q] = fmaf(a[i].z, ww.z, acc[i][q]);
-                        acc[i][q] = fmaf(a[i].w, ww.w, acc[i][q]);
-                    }
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < PXT; ++i) {
+                    acc[i][q] = fmaf(a[i].x, ww[q].x, acc[i][q]);
+                    acc[i][q] = fmaf(a[i].y, ww[q].y, acc[i][q]);
+                    acc[i][q] = fmaf(a[i].z, ww[q].z, acc[i][q]);
+                    acc[i][q] = fmaf(a[i].w, ww[q].w, acc[i][q]);
                 }
-            }
         }
         if (KS > 1) {
 #pragma unroll
@@ -114,8 +126,8 @@ __device__ __forceinline__ void conv_pass(const float* __restrict__ src, int SW,
 }
 
 // grid (F / TC, T, nb): one output strip of 1 x TC pixels per CTA
-template <int C, int TC, int PXT1, int KS2>
-__global__ void __launch_bounds__(256) cbr_kernel(CbrParams p) {
+template <int C, int TC, int PXT1, int KS1, int KS2>
+__global__ void __launch_bounds__(CBR_THREADS) cbr_kernel(CbrParams p) {
     extern __shared__ __align__(16) float sm[];
     constexpr int IW = TC + 4, IH = 5, MW = TC + 2, MH = 3;
     const int Cin = p.Cin, ips = Cin + 4;
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(256) cbr_kernel(CbrParams p) {
     pdl_wait();
     {   // input strip with a 2-pixel halo; pixels outside the padded map are zero
         const int Q = Cin >> 2;
-        for (int i = threadIdx.x; i < IH * IW * Q; i += 256) {
+        for (int i = threadIdx.x; i < IH * IW * Q; i += CBR_THREADS) {
             const int q = i % Q, px = i / Q, pr = px / IW, pc = px % IW;
             const int gr = r0 - 1 + pr, gc = c0 - 1 + pc;   // padded-map coordinates
             float* d = in_s + px * ips + q * 4;
@@ -151,7 +163,7 @@ __global__ void __launch_bounds__(256) cbr_kernel(CbrParams p) {
     __syncthreads();
 
     // conv 1 over the strip grown by one pixel; positions outside the map are conv 2's zero padding
-    conv_pass<C, PXT1, 1>(in_s, IW, Cin, w1_s, MH * MW, MW, [&](int px, int co, float v) {
+    conv_pass<C, PXT1, KS1>(in_s, IW, Cin, w1_s, MH * MW, MW, [&](int px, int co, float v) {
         const int r = r0 - 1 + px / MW, c = c0 - 1 + px % MW;
         const bool inside = r >= 0 && r < p.T && c >= 0 && c < p.F;
         t1_s[px * (C + 4) + co] = inside ? fmaxf(v + __ldg(p.b1 + co), 0.f) : 0.f;
@@ -189,8 +201,8 @@ constexpr int CBR_TC16 = 32, CBR_TC32 = 8;
 }  // namespace
 
 void init_cbr_attributes() {
-    cudaFuncSetAttribute(cbr_kernel<16, CBR_TC16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cbr_smem<16, CBR_TC16>(64, true)));
-    cudaFuncSetAttribute(cbr_kernel<32, CBR_TC32, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cbr_smem<32, CBR_TC32>(64, true)));
+    cudaFuncSetAttribute(cbr_kernel<16, CBR_TC16, 1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cbr_smem<16, CBR_TC16>(64, true)));
+    cudaFuncSetAttribute(cbr_kernel<32, CBR_TC32, 1, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cbr_smem<32, CBR_TC32>(64, true)));
 }
 
 int launch_cbr(const CbrOp& o, const DeviceBases& B, cudaStream_t s) {
@@ -202,9 +214,9 @@ int launch_cbr(const CbrOp& o, const DeviceBases& B, cudaStream_t s) {
     p.T = o.T; p.F = o.F; p.Cin = o.Cin;
     const bool sc = !o.wsc.null();
     if (o.C == 16)
-        launch_k(cbr_kernel<16, CBR_TC16, 2, 2>, dim3(o.F / CBR_TC16, o.T, B.nb), dim3(256), cbr_smem<16, CBR_TC16>(o.Cin, sc), s, p);
+        launch_k(cbr_kernel<16, CBR_TC16, 1, 1, 4>, dim3(o.F / CBR_TC16, o.T, B.nb), dim3(CBR_THREADS), cbr_smem<16, CBR_TC16>(o.Cin, sc), s, p);
     else
-        launch_k(cbr_kernel<32, CBR_TC32, 1, 4>, dim3(o.F / CBR_TC32, o.T, B.nb), dim3(256), cbr_smem<32, CBR_TC32>(o.Cin, sc), s, p);
+        launch_k(cbr_kernel<32, CBR_TC32, 1, 2, 4>, dim3(o.F / CBR_TC32, o.T, B.nb), dim3(CBR_THREADS), cbr_smem<32, CBR_TC32>(o.Cin, sc), s, p);
     return 1;
 }
 

@@ -341,9 +341,9 @@ def test_slab_chains_match_separate_kernels(env, monkeypatch):
 
 @pytest.mark.gpu
 def test_fused_residual_blocks_match_separate_gemms(env, monkeypatch):
-    """kernels_cbr.cu: RMVPE's ConvBlockRes at U-Net levels 0 / 1 as one kernel per block (default: the decoder's blocks,
-    RVC_CBR=1: the encoder's too, RVC_CBR=0: three implicit GEMMs per block).  Same pitch bins / argmax, audio within 1e-4,
-    and fewer launches."""
+    """kernels_cbr.cu: RMVPE's ConvBlockRes at U-Net levels 0 / 1 as one kernel per block (opt-in: RVC_CBR=2 the decoder's
+    blocks, RVC_CBR=1 the encoder's too; default RVC_CBR=0: three implicit GEMMs per block).  Same pitch bins / argmax,
+    audio within 1e-4, and fewer launches."""
     out = {}
     for mode in ("0", "1", "2"):
         monkeypatch.setenv("RVC_CBR", mode)
