@@ -611,7 +611,26 @@ int launch_gru(const GruOp& o, const DeviceBases& B, cudaStream_t s) {
     return 1;
 }
 
+// the pitch half of the embedding when the phone projection was computed ahead of the join (EmbedOp::pre)
+__global__ void __launch_bounds__(256)
+embed_add_kernel(const float* __restrict__ pre, const int* __restrict__ pitch, const float* __restrict__ emb_pitch, float* __restrict__ out,
+                 long long ldo, int R, int H, long long wPre, long long wPitch, long long wOut) {
+    pdl_enter();
+    pre += blockIdx.z * wPre; pitch += blockIdx.z * wPitch; out += blockIdx.z * wOut;
+    const float sc = sqrtf(float(H));
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < R * H; e += gridDim.x * blockDim.x) {
+        const int r = e / H, h = e - r * H;
+        const float v = (pre[e] + emb_pitch[pitch[r] * H + h]) * sc;
+        out[(long long)r * ldo + h] = v > 0.f ? v : 0.1f * v;
+    }
+}
+
 int launch_embed(const EmbedOp& o, const DeviceBases& B, cudaStream_t s) {
+    if (!o.pre.null()) {
+        launch_k(embed_add_kernel, dim3((o.R * o.H + 255) / 256, 1, B.nb), dim3(256), size_t(0), s, B.p<float>(o.pre), B.p<int>(o.pitch), B.p<float>(o.emb_pitch),
+                 B.p<float>(o.out), o.ldo, o.R, o.H, B.ws(o.pre), B.ws(o.pitch), B.ws(o.out));
+        return 1;
+    }
     launch_k(embed_kernel, dim3(o.R, 1, B.nb), dim3(256), size_t(sizeof(float) * o.Cin), s, B.p<float>(o.phone), B.p<int>(o.pitch), B.p<float>(o.wp), B.p<float>(o.bp),
                                                          B.p<float>(o.emb_pitch), B.p<float>(o.out), o.ldo, o.Cin, o.H, B.ws(o.phone), B.ws(o.pitch), B.ws(o.out));
     return 1;

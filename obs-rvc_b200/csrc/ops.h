@@ -117,6 +117,7 @@ struct F0PostOp {  // rvc.rs:167-181 + f0/mod.rs:7-12
 
 struct EmbedOp {  // lrelu_0.1((phone Wp^T + bp + emb_pitch[pitch]) * sqrt(H))
     Ref phone; Ref pitch; Ref wp; Ref bp; Ref emb_pitch; Ref out; int64_t ldo = 0;
+    Ref pre;  // non-null: [R, H] = phone Wp^T + bp, computed by an earlier GEMM (it does not need the pitch: off the critical path)
     int32_t R = 0, Cin = 0, H = 0;
 };
 

@@ -355,7 +355,7 @@ F0Out build_rmvpe(PB& b, const Packed* P, const F0Info& info, Ref pcm_window, in
 // Synthesizer (rvc.rs:193-214): phone [R,C], pitch i32[R], pitchf [R] -> audio [R*400]
 // ------------------------------------------------------------------------------------------
 Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitch, Ref pitchf, Ref params,
-                Ref audio, int R, bool multi_lane) {
+                Ref audio, int R, bool multi_lane, Ref emb_pre = Ref{}) {
     const int H = 192;
     auto W = [&](const std::string& n) { return b.w(P, SP_SYN, n); };
     // ---- enc_p ---------------------------------------------------------------------------
@@ -366,7 +366,7 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
         Op& op = b.add(OP_EMBED, "sy.emb");
         op.embed.phone = phone; op.embed.pitch = pitch; op.embed.wp = W("emb.wp"); op.embed.bp = W("emb.bp");
         op.embed.emb_pitch = W("emb.pitch"); op.embed.out = x; op.embed.ldo = H; op.embed.R = R;
-        op.embed.Cin = info.phone_dim; op.embed.H = H;
+        op.embed.Cin = info.phone_dim; op.embed.H = H; op.embed.pre = emb_pre;
     }
     for (int i = 0; i < 6; ++i) {
         std::string d = "E" + S(i) + ".", n = "sy.E" + S(i) + ".";
@@ -871,6 +871,14 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         op.gather.src = src; op.gather.lds = C; op.gather.out = phone; op.gather.T = T; op.gather.C = C;
         op.gather.skip = skip; op.gather.R = R; op.gather.row0 = row0;
     }
+    // enc_p's phone projection needs no pitch: it runs here, while the F0 lane is still busy, and the embedding op after the
+    // join only adds the pitch embedding (RVC_EMB_PRE=0: one op after the join, as the reference orders it)
+    Ref emb_pre{};
+    static const bool emb_early = sched_env("RVC_EMB_PRE", 1) != 0;
+    if (emb_early && ml) {
+        emb_pre = b.alloc("sy.emb_pre", int64_t(R) * 192);
+        b.gemm("sy.emb_pre", phone, C, C, 0, b.w(syn, SP_SYN, "emb.wp"), C, b.w(syn, SP_SYN, "emb.bp"), emb_pre, 192, R, 192, C, ACT_NONE);
+    }
     if (ml) b.wait(1, 0);
     Ref pitch = b.alloc("pitch", R, true), pitchf = b.alloc("pitchf", R);
     {
@@ -884,7 +892,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     }
     const int audio_len = R * (syi->sr / 100);
     if (audio_len > StateLayout::AUDIO_CAP) { err = "output too long"; return false; }
-    build_synth(b, syn, *syi, phone, pitch, pitchf, plan.params, plan.audio, R, ml);
+    build_synth(b, syn, *syi, phone, pitch, pitchf, plan.params, plan.audio, R, ml, emb_pre);
     plan.audio_len = audio_len;
     schedule_gemms(b, plan.nb);
     form_chains(b, opt);

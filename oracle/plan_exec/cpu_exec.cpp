@@ -304,9 +304,11 @@ void run_embed(const EmbedOp& o, const Bases& B) {
     const float* wp = P<float>(B, o.wp); const float* bp = P<float>(B, o.bp); const float* ep = P<float>(B, o.emb_pitch);
     float* out = P<float>(B, o.out);
     const float sc = std::sqrt(float(o.H));
+    const float* pre = o.pre.null() ? nullptr : P<float>(B, o.pre);
     for (int r = 0; r < o.R; ++r) for (int h = 0; h < o.H; ++h) {
         double a = bp[h];
-        for (int k = 0; k < o.Cin; ++k) a += double(ph[int64_t(r) * o.Cin + k]) * wp[int64_t(h) * o.Cin + k];
+        if (pre) a = pre[int64_t(r) * o.H + h];
+        else for (int k = 0; k < o.Cin; ++k) a += double(ph[int64_t(r) * o.Cin + k]) * wp[int64_t(h) * o.Cin + k];
         float v = (float(a) + ep[pi[r] * o.H + h]) * sc;
         out[int64_t(r) * o.ldo + h] = v > 0 ? v : 0.1f * v;
     }
