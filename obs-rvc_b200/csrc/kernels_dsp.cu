@@ -17,7 +17,7 @@ namespace {
 // (rmvpe.rs:47-68 pad_reflect, 80-116 stft, 159-205 mel_extract).  HBM traffic per frame is the
 // 1024 input samples and 128 outputs; the filterbank (1010 non-zeros) stays in L2/L1.
 // ------------------------------------------------------------------------------------------
-__device__ unsigned long long g_dsp_stamps[4];   // [0] STFT start, [1] F0 decode start, [2] pitch cache start
+__device__ unsigned long long g_dsp_stamps[4];   // [0] STFT start, [1] F0 decode start, [2] pitch cache start, [3] sine source start
 
 __global__ void __launch_bounds__(256)
 stft_mel_log_kernel(const float* __restrict__ pcm, int L, const float* __restrict__ window,
@@ -169,6 +169,7 @@ sinegen_kernel(const float* __restrict__ f0, float* __restrict__ out, float* __r
                const RunParams* __restrict__ rp, int T, int upp, float sr, float lin_w, float lin_b,
                long long wF0, long long wOut, long long wDbg, long long wRp) {
     pdl_enter();
+    lane_stamp(&g_dsp_stamps[3]);
     f0 += blockIdx.z * wF0; out += blockIdx.z * wOut;
     if (dbg) dbg += blockIdx.z * wDbg;
     rp = reinterpret_cast<const RunParams*>(reinterpret_cast<const float*>(rp) + blockIdx.z * wRp);
@@ -267,6 +268,6 @@ int launch_sinegen(const SineGenOp& o, const DeviceBases& B, cudaStream_t s) {
     return 1;
 }
 
-void dsp_read_stamps(unsigned long long* out3) { cudaMemcpyFromSymbol(out3, g_dsp_stamps, 3 * sizeof(unsigned long long)); }
+void dsp_read_stamps(unsigned long long* out4) { cudaMemcpyFromSymbol(out4, g_dsp_stamps, 4 * sizeof(unsigned long long)); }
 
 }  // namespace rvc

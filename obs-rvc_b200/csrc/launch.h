@@ -30,8 +30,8 @@ struct DeviceBases {
 // Each launcher enqueues exactly the kernels of one op on `stream` and returns how many kernels
 // it launched (0 for memset-only ops).  Errors are reported through cudaGetLastError by the caller.
 int launch_gemm(const GemmOp& g, const DeviceBases& B, cudaStream_t stream);
-// lane stamps (pdl.cuh lane_stamp): {STFT start, F0 decode start, pitch cache start}, {retrieval gather start, conv_post end, RMVPE pool 0..4 start, GRU start}
-void dsp_read_stamps(unsigned long long* out3);
+// lane stamps (pdl.cuh lane_stamp): {STFT start, F0 decode start, pitch cache start, sine source start}, {retrieval gather start, conv_post end, RMVPE pool 0..4 start, GRU start}
+void dsp_read_stamps(unsigned long long* out4);
 void misc_read_stamps(unsigned long long* out8);
 // fused RMVPE residual block (kernels_cbr.cu)
 int launch_cbr(const CbrOp& o, const DeviceBases& B, cudaStream_t stream);

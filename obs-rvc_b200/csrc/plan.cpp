@@ -358,6 +358,25 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
                 Ref audio, int R, bool multi_lane, Ref emb_pre = Ref{}) {
     const int H = 192;
     auto W = [&](const std::string& n) { return b.w(P, SP_SYN, n); };
+    // ---- NSF sine source ------------------------------------------------------------------
+    // It needs only pitchf: forked onto lane 1 HERE, before enc_p / flow are emitted - a fork emitted after them would
+    // record lane 0's position behind the flow chain and the kernel would run on the critical path, beside conv_pre
+    // (measured with a lane stamp: sine source at 2044 us, right after the flow chain; RVC_SINE_EARLY=0 restores that).
+    const int upp = info.sr / 100, L = R * upp, HH = 32;   // samples per 10 ms feature frame = product of the upsample rates
+    Ref harpad = b.alloc("", L + 2 * HH);
+    Ref har = harpad.plus(HH);
+    b.alias("sy.har", har, L);
+    Ref sine_dbg = b.alloc("sy.sine", L);
+    auto emit_sine = [&]() {
+        if (multi_lane) { b.wait(0, 1); b.lane = 1; }
+        Op& op = b.add(OP_SINEGEN, "sy.sine");
+        op.sine.pitchf = pitchf; op.sine.out = har; op.sine.sine_dbg = sine_dbg; op.sine.params = params;
+        op.sine.R = R; op.sine.upp = upp; op.sine.sr = float(info.sr); op.sine.lin_w = info.lin_w;
+        op.sine.lin_b = info.lin_b;
+        b.lane = 0;
+    };
+    static const bool sine_early = sched_env("RVC_SINE_EARLY", 1) != 0;
+    if (sine_early) emit_sine();
     // ---- enc_p ---------------------------------------------------------------------------
     Ref xpad = b.alloc("", int64_t(R + 2) * H);  // 1 zero row either side (FFN k=3)
     Ref x = xpad.plus(H);
@@ -433,20 +452,7 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
         g.alpha = -1.0f; g.R = x1; g.ldr = H;
     }
     // ---- GeneratorNSF ----------------------------------------------------------------------
-    const int upp = info.sr / 100, L = R * upp, HH = 32;   // samples per 10 ms feature frame = product of the upsample rates
-    Ref harpad = b.alloc("", L + 2 * HH);
-    Ref har = harpad.plus(HH);
-    b.alias("sy.har", har, L);
-    Ref sine_dbg = b.alloc("sy.sine", L);
-    {
-        // the sine source only needs pitchf: it runs on lane 1 while enc_p / flow occupy lane 0
-        if (multi_lane) { b.wait(0, 1); b.lane = 1; }
-        Op& op = b.add(OP_SINEGEN, "sy.sine");
-        op.sine.pitchf = pitchf; op.sine.out = har; op.sine.sine_dbg = sine_dbg; op.sine.params = params;
-        op.sine.R = R; op.sine.upp = upp; op.sine.sr = float(info.sr); op.sine.lin_w = info.lin_w;
-        op.sine.lin_b = info.lin_b;
-        b.lane = 0;
-    }
+    if (!sine_early) emit_sine();
     const int* RATES = info.rates; const int* UK = info.up_kernels;
     static const int RK[3] = {3, 7, 11}, RD[3] = {1, 3, 5};
     if (RATES[0] * RATES[1] * RATES[2] * RATES[3] != upp) { b.fail("generator upsample rates do not multiply to sr / 100"); return audio; }

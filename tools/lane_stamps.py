@@ -20,7 +20,7 @@ for i in range(int(os.environ.get("N", "40"))):
     w = x[(i % 60) * g["sf16k"]: (i % 60) * g["sf16k"] + g["n16k"]]
     if pitch_only: eng.pitch(w, 12, g["sf16k"])
     else: eng.infer(w, g["sf16k"], 12, g["skip_head"], g["return_length"])
-    out = (ctypes.c_ulonglong * 11)()
+    out = (ctypes.c_ulonglong * 12)()
     L.rvc_debug_lane_stamps(eng.handle, out)
     t = np.array(list(out), dtype=np.float64)
     rows.append((t[1:] - t[0]) / 1e3)
@@ -30,4 +30,4 @@ for i in range(int(os.environ.get("N", "40"))):
 r = np.median(np.array(rows[8:]), axis=0)
 f0 = f"pool0..4 {r[4]:.0f} {r[5]:.0f} {r[6]:.0f} {r[7]:.0f} {r[8]:.0f}, gru {r[9]:.0f}, f0 decode {r[0]:.0f}"
 if pitch_only: print("STAMPS us after STFT start:", f0)
-else: print(f"STAMPS us after STFT start: {f0}, pitch cache {r[1]:.0f}, retrieval gather {r[2]:.0f}, conv_post end {r[3]:.0f}")
+else: print(f"STAMPS us after STFT start: {f0}, pitch cache {r[1]:.0f}, retrieval gather {r[2]:.0f}, sine source {r[10]:.0f}, conv_post end {r[3]:.0f}")
