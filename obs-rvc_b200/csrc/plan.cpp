@@ -495,10 +495,14 @@ Ref build_synth(PB& b, const Packed* P, const SynInfo& info, Ref phone, Ref pitc
         // lane 1 beside rk 11 on lane 0 (equal work: 3 + 7 ~ 11 taps), 1 = one lane
         static const int rb_lanes = sched_env("RVC_SY_RB_LANES", 3);
         const int rbl = multi_lane ? rb_lanes : 1;
-        auto rb_lane = [&](int j) { return rbl >= 3 ? j : (rbl == 2 ? (j == 2 ? 0 : 1) : 0); };
+        // RVC_SY_RB_ORDER=1 (experiment): the longest ResBlock (rk 11) stays on lane 0 - no fork event in front of it - and is
+        // emitted first; the short ones take the forked lanes
+        static const int rb_order = sched_env("RVC_SY_RB_ORDER", 0);
+        auto rb_lane = [&](int j) { return rbl >= 3 ? (rb_order ? 2 - j : j) : (rbl == 2 ? (j == 2 ? 0 : 1) : 0); };
         if (rbl >= 2) b.wait(0, 1);
         if (rbl >= 3) b.wait(0, 2);  // the three ResBlocks run concurrently
-        for (int j = 0; j < 3; ++j) {
+        for (int jj = 0; jj < 3; ++jj) {
+            const int j = (rb_order && rbl >= 3) ? 2 - jj : jj;
             b.lane = rb_lane(j);
             const int rk = RK[j];
             std::string rn = n + "rb" + S(j) + ".";
