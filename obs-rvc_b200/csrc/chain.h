@@ -41,12 +41,22 @@ struct ChainOpDev {
 
 struct ChainPhaseDev { int op0, op1, items, pad; };
 
+// One step of a weight-streaming chain (kernels_wstream.cu): a skinny GEMM, at most four valid rows, contiguous A rows
+struct WsOpDev {
+    const float* A; const float* W; const float* bias; const float* R; float* C;
+    long long ldw, ldc, ldr;
+    int K, a_floats, n_rows, relu;
+    int row[4], row_off[4];   // valid rows m and their offsets m * lda inside the activation span
+};
+
 struct ChainDev {
     ChainOpDev* d_ops = nullptr;
     ChainPhaseDev* d_phases = nullptr;
     unsigned int* d_bar = nullptr;   // [0] arrivals, [1] exits (self-cleaning)
     unsigned long long* d_dbg = nullptr;  // optional: globaltimer at every phase start (+ end), CTA 0
     int n_ops = 0, n_phases = 0, grid = 0;
+    int wstream = 0;   // 1: every op is a skinny GEMM of the same width: the weight-streaming kernel runs the chain (kernels_wstream.cu)
+    WsOpDev* d_wsops = nullptr;
     int cluster = 0;   // 1: the grid is ONE thread-block cluster (<= 16 CTAs), phases separated by the hardware cluster barrier
     // Slab chain (slab_chain_kernel): a single cluster whose GEMMs (M <= 24 rows) are split by output columns only - CTA c
     // owns columns [c nc, (c + 1) nc) of EVERY GEMM with the full K, no split-K - and whose weights were re-packed once, per
@@ -80,6 +90,9 @@ void launch_slab_pack(const float* W, long long ldw, int N, int K, int nc, int k
                       int chunk0, int G, cudaStream_t stream);
 
 int launch_chain(const ChainDev& c, cudaStream_t stream);  // returns kernels launched (1)
+int launch_wstream(const ChainDev& c, cudaStream_t stream);
+bool wstream_shape_ok(int M, int N, int K, long long lda, int valid_rows);
+void init_wstream_attributes();
 void init_chain_attributes();
 void chain_debug_read(long long* out, int n);  // [256 phases][8] clock64 stamps of the LAST chain launch, CTA 0
 void chain_debug_read2(long long* out, int n); // [256 phases][2]: barrier spin start / end of CTA 0

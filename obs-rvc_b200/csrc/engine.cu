@@ -118,7 +118,7 @@ struct PlanEntry {
     ~PlanEntry() {
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
-        for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); cudaFree(c.d_slabs); cudaFree(c.d_chunk_bytes); }
+        for (ChainDev& c : chains) { cudaFree(c.d_ops); cudaFree(c.d_phases); cudaFree(c.d_bar); cudaFree(c.d_dbg); cudaFree(c.d_slabs); cudaFree(c.d_chunk_bytes); cudaFree(c.d_wsops); }
         cudaFree(cvs.d_maps); cudaFree(cvs.d_phases); cudaFree(cvs.d_bar);
         work.release(); bstate.release();
     }
@@ -513,10 +513,45 @@ int build_chain_tables(rvc_ctx* ctx, PlanEntry& e) {
                 CK(cudaGetLastError());
             }
         }
+        {   // a side-lane chain made only of skinny GEMMs of one width (RMVPE's bottleneck: 4 valid rows x 512 x 1536) runs on
+            // the weight-streaming kernel: 8 columns per CTA, filters fetched whole steps ahead (kernels_wstream.cu)
+            const char* we = getenv("RVC_WSTREAM");
+            bool ws = !(we && we[0] == '0') && !cd.slab && ci.n_phases == ci.count && ci.count >= 2;
+            std::vector<WsOpDev> wops;
+            int N0 = 0;
+            for (int k = 0; ws && k < ci.count; ++k) {
+                const Op& op = e.plan.ops[size_t(ci.first + k)];
+                if (op.kind != OP_GEMM || ci.phase[size_t(k)] != k) { ws = false; break; }
+                const GemmOp& g = op.gemm;
+                WsOpDev w; std::memset(&w, 0, sizeof(w));
+                int nv = 0;
+                for (int m = 0; m < g.M; ++m) {
+                    if (g.mask_period > 0 && (m % g.mask_period) >= g.mask_valid) continue;
+                    if (nv < 4) { w.row[nv] = m; w.row_off[nv] = int(int64_t(m) * g.lda); }
+                    ++nv;
+                }
+                if (k == 0) N0 = g.N;
+                if (g.batch != 1 || g.out_mode != OUT_PLAIN || (g.act != ACT_NONE && g.act != ACT_RELU) || g.alpha != 1.0f || !g.C2.null() || g.seg_len < g.K ||
+                    g.N != N0 || nv > 4 || !wstream_shape_ok(g.M, g.N, g.K, g.lda, nv)) { ws = false; break; }
+                const gemmk::GemmParams gp = gemmk::make_params(g, B);
+                w.A = gp.A; w.W = gp.W; w.bias = gp.bias; w.R = gp.R; w.C = gp.C; w.ldw = g.ldw; w.ldc = g.ldc; w.ldr = g.ldr;
+                w.K = g.K; w.n_rows = nv; w.relu = g.act == ACT_RELU ? 1 : 0;
+                w.a_floats = w.row_off[nv - 1] + g.K;
+                for (int i = nv; i < 4; ++i) { w.row[i] = w.row[nv - 1]; w.row_off[i] = w.row_off[nv - 1]; }
+                if ((reinterpret_cast<uintptr_t>(w.A) & 15) || (reinterpret_cast<uintptr_t>(w.W) & 15) || (g.ldw & 3)) { ws = false; break; }
+                wops.push_back(w);
+            }
+            if (ws) {
+                cd.wstream = 1; cd.grid = N0 / 8;
+                CK(cudaMalloc(&cd.d_wsops, wops.size() * sizeof(WsOpDev)));
+                CK(cudaMemcpyAsync(cd.d_wsops, wops.data(), wops.size() * sizeof(WsOpDev), cudaMemcpyHostToDevice, ctx->streams[0]));
+                CK(cudaStreamSynchronize(ctx->streams[0]));
+            }
+        }
         {   // small grids run as ONE thread-block cluster: hardware cluster barrier instead of the L2 grid barrier
             static const int max_cluster = chain_max_cluster_ctas();
             const char* ce = getenv("RVC_CHAIN_CLUSTER");
-            cd.cluster = (!cd.slab && !(ce && ce[0] == '0') && cd.grid >= 2 && cd.grid <= max_cluster) ? 1 : 0;
+            cd.cluster = (!cd.slab && !cd.wstream && !(ce && ce[0] == '0') && cd.grid >= 2 && cd.grid <= max_cluster) ? 1 : 0;
         }
         CK(cudaMalloc(&cd.d_ops, ops.size() * sizeof(ChainOpDev)));
         CK(cudaMalloc(&cd.d_phases, phases.size() * sizeof(ChainPhaseDev)));

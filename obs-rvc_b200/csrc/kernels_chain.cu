@@ -1059,6 +1059,7 @@ void launch_slab_pack(const float* W, long long ldw, int N, int K, int nc, int k
 }
 
 int launch_chain(const ChainDev& c, cudaStream_t stream) {
+    if (c.wstream) return launch_wstream(c, stream);
     if (c.slab) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(unsigned(c.grid)); cfg.blockDim = dim3(SLAB_THREADS); cfg.dynamicSmemBytes = SLAB_SMEM_BYTES; cfg.stream = stream;

@@ -552,6 +552,7 @@ void init_kernel_attributes() {
     init_chain_attributes();
     init_cvstack_attributes();
     init_cbr_attributes();
+    init_wstream_attributes();
 }
 
 void launch_split_hilo16(const float* src, unsigned short* dst_hi, unsigned short* dst_lo, size_t n, cudaStream_t stream) {

@@ -674,7 +674,16 @@ void form_chains(PB& b, const PlanOptions& opt) {
     while (i < n) {
         if (!chain_eligible(ops[i], opt.chain_side_max_m)) { ++i; continue; }
         int j = i;
-        while (j < n && j - i < 256 && ops[j].lane == ops[i].lane && chain_eligible(ops[j], opt.chain_side_max_m)) ++j;  // 256 = table size of the kernel
+        // side lanes: a run of skinny GEMMs of one width (RMVPE's bottleneck) ends where that shape ends, so that the whole
+        // chain can run on the weight-streaming kernel (kernels_wstream.cu) instead of the generic tile engine
+        const bool ws_on = sched_env("RVC_WSTREAM", 1) != 0;
+        auto ws_sig = [&](const Op& o) {
+            if (!ws_on || o.lane == 0 || o.kind != OP_GEMM) return -1;
+            const GemmOp& g = o.gemm;
+            return (g.M <= 8 && g.out_mode == OUT_PLAIN && g.seg_len >= g.K && g.N % 8 == 0 && g.K % 128 == 0 && g.K <= 1536 && g.batch == 1) ? g.N : -1;
+        };
+        const int sig0 = ws_sig(ops[i]);
+        while (j < n && j - i < 256 && ops[j].lane == ops[i].lane && chain_eligible(ops[j], opt.chain_side_max_m) && ws_sig(ops[j]) == sig0) ++j;  // 256 = table size of the kernel
         const int G = ops[i].lane == 0 ? opt.chain_grid_main : opt.chain_grid_side;
         if (j - i >= 4 && G > 0) {
             ChainInfo c;
@@ -810,7 +819,7 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
     int T = 0;
     Ref x{};
     F0Out fo{};
-    static const bool f0_first = sched_env("RVC_F0_FIRST", 1) != 0;
+    static const bool f0_first = sched_env("RVC_F0_FIRST", 0) != 0;
     auto emit_f0 = [&]() {
         static const bool sc_side = sched_env("RVC_SC_LANE", 1) != 0;   // 0: shortcut convs stay on the F0 lane (same chain phase as c1)
         static const int cv_gate = sched_env("RVC_CV_GATE", -1);
@@ -819,15 +828,17 @@ bool build_plan(PlanKind kind, const Geometry& g, const PlanOptions& opt, const 
         b.lane = 0; b.sc_lane = -1; b.cv_gate = -1;
     };
     // The lane whose ops are emitted (= whose graph nodes are created) first gets the SMs first when both lanes have
-    // work ready.  Since the tcgen05 GEMMs got faster the F0 chain is the longer branch: it goes first.
+    // work ready.  With the weight-streaming bottleneck kernel the F0 branch ends ~170 us before ContentVec + retrieval:
+    // ContentVec goes first again (RVC_F0_FIRST=1: the order of the rounds in which the F0 chain was the longer branch).
     if (f0_first) emit_f0();
     const size_t cv_first_op = b.plan.ops.size();
     x = build_contentvec(b, cv, *cvi, plan.pcm, N, T);
     if (!b.ok) return false;
     {
-        // ContentVec finishes ~0.3 ms before the F0 lane (profiles/README.md, sparse timeline): a CTA budget below the
-        // tcgen05 default (96) leaves the F0 lane - the critical path of the front end - more SMs (RVC_CV_WANT; 0 = scheduler default)
-        static const int cv_want = sched_env("RVC_CV_WANT", 80);
+        // CTA budget of ContentVec's conv stem / pos-conv GEMMs beside the F0 lane (RVC_CV_WANT; 0 = scheduler default 96).
+        // 80 while the F0 lane was the critical branch; since the weight-streaming bottleneck kernel ContentVec + retrieval
+        // is, and 120 measures best (2.529 vs 2.539 ms; with ContentVec emitted first 2.504)
+        static const int cv_want = sched_env("RVC_CV_WANT", 120);
         if (cv_want > 0 && ml && opt.nb <= 1)
             for (size_t i = cv_first_op; i < b.plan.ops.size(); ++i)
                 if (b.plan.ops[i].kind == OP_GEMM && b.plan.ops[i].gemm.cta_budget == 0) b.plan.ops[i].gemm.cta_budget = cv_want;

@@ -357,3 +357,27 @@ def test_fused_residual_blocks_match_separate_gemms(env, monkeypatch):
         np.testing.assert_array_equal(out[mode][2], out["0"][2])
         for a, b in zip(out[mode][0], out["0"][0]):
             np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_weight_streaming_bottleneck_matches_generic_chain(env, monkeypatch):
+    """kernels_wstream.cu: RMVPE's U-Net bottleneck (31 skinny GEMMs, 4 valid rows x 512 x 1536) on the weight-streaming
+    kernel (default) against the same ops on the generic chain kernel (RVC_WSTREAM=0) and on separate launches
+    (RVC_CHAIN=0): identical argmax / pitch bins, audio within 1e-4."""
+    out = {}
+    for tag, envs in (("ws", {}), ("chain", {"RVC_WSTREAM": "0"}), ("plain", {"RVC_CHAIN": "0"})):
+        for k in ("RVC_WSTREAM", "RVC_CHAIN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in envs.items():
+            monkeypatch.setenv(k, v)
+        e = _engine(env, noise_seed=9)
+        a, am, p = _two_windows(e, env, 53)
+        grids = sorted(c["grid"] for c in e.profile_chains())
+        out[tag] = (a, am, p, grids)
+        e.close()
+    assert 64 in out["ws"][3] and 64 not in out["chain"][3] and out["plain"][3] == []
+    for tag in ("chain", "plain"):
+        np.testing.assert_array_equal(out["ws"][1], out[tag][1])
+        np.testing.assert_array_equal(out["ws"][2], out[tag][2])
+        for a, b in zip(out["ws"][0], out[tag][0]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=1e-4)
