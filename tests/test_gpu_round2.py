@@ -174,6 +174,7 @@ def test_single_cluster_chains_match_separate_kernels(env, monkeypatch):
     monkeypatch.setenv("RVC_CHAIN", "2")
     monkeypatch.setenv("RVC_CHAIN_MAIN", "16")
     monkeypatch.setenv("RVC_CHAIN_SIDE", "16")
+    monkeypatch.setenv("RVC_WSTREAM", "0")   # the bottleneck on the generic chain kernel too (its own kernel always takes 64 CTAs)
     e1 = _engine(env, noise_seed=8)
     a1, am1, p1 = _two_windows(e1, env, 47)
     chains = e1.profile_chains()
