@@ -492,13 +492,13 @@ def main():
         for o in prof:
             if o.get("chain", -1) >= 0:
                 # executed inside a persistent chain kernel: its work counts there, its time is the chain's own clock
-                f = fam.setdefault("chain_kernel(fp32, persistent)", {"us": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+                f = fam.setdefault("chain_kernel + wstream_kernel (fp32, persistent)", {"us": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
                 f["flops"] += o["flops"]; f["bytes"] += o["wbytes"] + o["iobytes"]
                 continue
             f = fam.setdefault(family(o), {"us": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
             f["us"] += o["us"]; f["flops"] += o["flops"]; f["bytes"] += o["wbytes"] + o["iobytes"]; f["n"] += 1
         if chains:
-            f = fam["chain_kernel(fp32, persistent)"]
+            f = fam["chain_kernel + wstream_kernel (fp32, persistent)"]
             f["us"] = sum(ph["us"] for c in chains for ph in c["phases"]); f["n"] = len(chains)
 
         def roof_of(name, f):
